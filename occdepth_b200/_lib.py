@@ -1,0 +1,81 @@
+"""ctypes binding of include/occdepth_b200.h (the C-ABI drop-in boundary).
+
+The library is mandatory: there is no CPU or PyTorch fallback behind these calls.  `lib()` raises if
+libocc_b200.so has not been built (python -m occdepth_b200._build / __graft_entry__.build()).
+"""
+import ctypes as C
+import os
+
+from . import _build
+
+_LIB = None
+
+MAX_SCALES = 4
+DTYPE_F32, DTYPE_BF16 = 0, 1
+SFA_OUT_F32_PLANAR, SFA_OUT_BF16_CL, SFA_OUT_F32_CL = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SILU, ACT_SIGMOID = 0, 1, 2, 3, 4
+
+
+class SfaParams(C.Structure):
+    _fields_ = [
+        ("feat", C.c_void_p * MAX_SCALES),
+        ("h", C.c_int * MAX_SCALES),
+        ("w", C.c_int * MAX_SCALES),
+        ("div", C.c_int * MAX_SCALES),
+        ("n_scales", C.c_int),
+        ("n_views", C.c_int),
+        ("C", C.c_int),
+        ("feat_dtype", C.c_int),
+        ("pix", C.c_void_p),
+        ("fov", C.c_void_p),
+        ("N", C.c_longlong),
+        ("P", C.c_int),
+        ("out", C.c_void_p),
+        ("out_mode", C.c_int),
+        ("out_cstride", C.c_int),
+        ("perm_nyu", C.c_int),
+        ("S1", C.c_int),
+        ("S2", C.c_int),
+        ("prior", C.c_void_p),
+        ("scale_const", C.c_float),
+    ]
+
+
+# every symbol include/occdepth_b200.h declares: name -> (restype, argtypes)
+_vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+SYMBOLS = {
+    "occd_abi_version": (C.c_int, []),
+    "occd_last_error": (C.c_char_p, []),
+    "occd_sfa_lift_fwd": (C.c_int, [C.POINTER(SfaParams), _vp]),
+    "occd_planar_to_cl": (C.c_int, [_vp, _vp, _i, _ll, _i, _ll, _i, _vp]),
+    "occd_cl_to_planar": (C.c_int, [_vp, _i, _vp, _ll, _i, _ll, _i, _vp]),
+}
+
+
+def lib():
+    """Load libocc_b200.so (once).  Fails loudly when it is missing -- never falls back."""
+    global _LIB
+    if _LIB is None:
+        path = _build.lib_path()
+        if not os.path.exists(path):
+            raise RuntimeError(
+                "occdepth_b200: %s is missing -- build it with `python -m occdepth_b200._build` "
+                "(or __graft_entry__.build()); there is no CPU fallback" % path)
+        L = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().occd_last_error()
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, (msg or b"").decode()))
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

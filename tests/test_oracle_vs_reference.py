@@ -1,0 +1,126 @@
+"""Pins oracle/functional.py against the UNMODIFIED reference modules (CPU fp32, seeded weights).
+
+Runs only where /root/reference exists (the build container); elsewhere the committed fixtures in
+tests/golden/ (generated from the same reference runs, oracle/gen_golden.py) carry the pin.
+"""
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import functional as OF
+from oracle import ref_import, synth
+
+pytestmark = pytest.mark.reference
+TOL = dict(rtol=1e-4, atol=1e-5)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_import.modules()
+
+
+def _close(a, b, **kw):
+    tol = dict(TOL)
+    tol.update(kw)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert torch.allclose(a, b, **tol), float((a - b).abs().max())
+
+
+@pytest.mark.parametrize("dataset,V,P", [("kitti", 2, 1), ("kitti", 1, 1), ("NYU", 2, 1), ("kitti", 2, 5), ("kitti", 3, 1)])
+def test_sfa(ref, dataset, V, P):
+    torch.manual_seed(0)
+    scene = (16, 12, 8)
+    ps = 2
+    S = [s // ps for s in scene]
+    N = S[0] * S[1] * S[2]
+    C, h, w = 16, 11, 23
+    x2d = torch.randn(V, C, h, w)
+    pix, fov = synth.random_indices(N, w, h, n_views=V, P=P, seed=3, margin=(5, 4))
+    m = ref.SFA.SFA(scene, dataset, ps)
+    want = m(x2d, pix.clone(), fov.clone())
+    got = OF.sfa(x2d, pix, fov, scene, dataset, ps)
+    _close(got, want.contiguous(), rtol=1e-5, atol=1e-6)
+
+
+def test_bottleneck_process_downsample(ref):
+    torch.manual_seed(0)
+    with ref_import.quiet():
+        proc = ref.modules.Process(16, nn.BatchNorm3d, 0.1, dilations=[1, 2, 3]).eval()
+        down = ref.modules.Downsample(16, nn.BatchNorm3d, 0.1).eval()
+        up = ref.modules.Upsample(32, 16, nn.BatchNorm3d, 0.1).eval()
+    for m in (proc, down, up):
+        synth.randomize_bn_(m)
+    x = torch.randn(1, 16, 8, 10, 6)
+    with torch.no_grad():
+        _close(OF.process({"p." + k: v for k, v in proc.state_dict().items()}, "p", x), proc(x))
+        y = down(x)
+        _close(OF.downsample({"p." + k: v for k, v in down.state_dict().items()}, "p", x), y)
+        _close(OF.upsample({"p." + k: v for k, v in up.state_dict().items()}, "p", y), up(y))
+
+
+@pytest.mark.parametrize("which", ["kitti", "nyu"])
+def test_unet3d(ref, which):
+    torch.manual_seed(0)
+    with ref_import.quiet():
+        if which == "kitti":
+            full, ps, f = (32, 32, 16), 2, 16
+            m = ref.unet3d_kitti.UNet3D(5, nn.BatchNorm3d, full, f, ps, context_prior=True, cascade_cls=True,
+                                        occluded_cls=True).eval()
+            x = torch.randn(1, f, 16, 16, 8)
+        else:
+            full, f = (12, 8, 12), 16
+            m = ref.unet3d_nyu.UNet3D(5, nn.BatchNorm3d, f, full, context_prior=True, cascade_cls=False).eval()
+            x = torch.randn(1, f, 12, 8, 12)
+    synth.randomize_bn_(m)
+    sd = {"n." + k: v for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        want = m({"x3d": x})
+        if which == "kitti":
+            got = OF.unet3d_kitti(sd, "n", x, full, ps, True, True, True)
+        else:
+            got = OF.unet3d_nyu(sd, "n", x, full, 4, True, False)
+    assert set(got.keys()) == set(want.keys())
+    for k in want:
+        _close(got[k], want[k], rtol=1e-3, atol=1e-4)
+
+
+def test_unet2d(ref):
+    torch.manual_seed(0)
+    with ref_import.quiet():
+        m = ref.unet2d.UNet2D.build(out_feature=16, use_decoder=True, backbone_2d_name="tf_efficientnet_b3_ns",
+                                    return_up_feats=1).eval()
+    synth.randomize_bn_(m)
+    sd = {"net_rgb." + k: v for k, v in m.state_dict().items()}
+    x = torch.randn(1, 3, 70, 93)
+    with torch.no_grad():
+        want = m(x)
+        got = OF.unet2d(sd, "net_rgb", x, "tf_efficientnet_b3_ns", 1)
+    assert set(got.keys()) == set(want.keys())
+    for k in want:
+        _close(got[k], want[k], rtol=1e-3, atol=1e-4)
+
+
+def test_occdepth_forward_small(ref):
+    """whole OccDepth.forward ("flosp", kitti decoder with CRP + cascade) on a tiny stereo pair."""
+    torch.manual_seed(0)
+    full = (32, 32, 16)
+    cfg = synth.occdepth_cfg(full_scene_size=full, feature=16, feature_2d_oc=16, n_classes=6,
+                             backbone_2d_name="tf_efficientnet_b3_ns")
+    with ref_import.quiet():
+        m = ref.OccDepth.OccDepth(class_names=["c"] * 6, class_weights=torch.ones(6), full_scene_size=full,
+                                  project_res=["1", "2", "4", "8"], config=cfg).eval()
+    synth.randomize_bn_(m)
+    H, W = 47, 85
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(1, 2, 3, H, W, generator=g)
+    N = 16 * 16 * 8
+    pix, fov = synth.random_indices(N, W, H, n_views=2, P=1, seed=5, margin=(10, 6))
+    batch = {"img": img, "projected_pix_2": [pix], "fov_mask_2": [fov]}
+    with torch.no_grad():
+        want = m(batch)
+        ocfg = dict(cfg)
+        ocfg["project_res"] = ["1", "2", "4", "8"]
+        got = OF.occdepth_forward(m.state_dict(), batch, ocfg)
+    assert set(got.keys()) == set(want.keys())
+    for k in want:
+        _close(got[k], want[k], rtol=2e-3, atol=2e-4)
