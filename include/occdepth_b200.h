@@ -70,6 +70,98 @@ int occd_planar_to_cl(const float* in, void* out, int out_dtype, long long B, in
 int occd_cl_to_planar(const void* in, int in_dtype, float* out, long long B, int C, long long S,
                       int cstride, void* stream);
 
+
+/* -------------------------------------------------------------------------------------------- */
+/* Generalised N-d convolution as implicit GEMM on tcgen05 (sm_100a)                              */
+/* replaces, with BatchNorm folded into weights/bias and the activation / residual adds fused:    */
+/*   nn.Conv3d / nn.Conv2d (+BN +ReLU/LeakyReLU/SiLU)  modules.py:6-48,51-235; DDR.py:51-139;      */
+/*     unet2d.py:24-46,65-165; CRP3D.py:22-52; flosp_depth.py:201-257; geffnet 1x1 convs           */
+/*   nn.ConvTranspose3d k3 s2 (modules.py:278-296) as 8 sub-pixel phase launches                   */
+/*   AvgPool3d + 1x1x1 conv (DDR.py:95-109, modules.py:329-339) as strided multi-tap convs          */
+/*   torch.bmm of CRP3D.py:81 (as a 1x1x1 conv whose weights are the mega-context)                 */
+/* The GEMM:  M = output positions (tile of 128 = TDxTHxTW box), N = output channels,              */
+/*            K = sum over "taps" of the source channels.  A tap = (source tensor, integer offset) */
+/* so dilation, padding, multi-branch accumulation (ASPP: three sources, three dilations, one      */
+/* accumulator) and concat-free skip connections are all tap lists.                                */
+#define OCCD_CONV_MAX_TAPS 81
+#define OCCD_CONV_MAX_SRC 3
+#define OCCD_ACT_NONE 0
+#define OCCD_ACT_RELU 1
+#define OCCD_ACT_LEAKY 2 /* slope 0.01 */
+#define OCCD_ACT_SILU 3
+#define OCCD_ACT_SIGMOID 4
+#define OCCD_CONV_IMPL_TC 0   /* tcgen05 + TMA implicit GEMM                                       */
+#define OCCD_CONV_IMPL_SIMT 1 /* CUDA-core direct convolution (cross-check / odd shapes)           */
+#define OCCD_OUT1_NONE 0
+#define OCCD_OUT1_BF16_CL 1    /* pre-activation copy, channels-last bf16                          */
+#define OCCD_OUT1_F32_PLANAR 2 /* pre-activation copy, fp32 [B][C][positions] (reference layout)   */
+
+typedef struct {
+  int src;        /* which source tensor                                                          */
+  int dz, dy, dx; /* input coordinate = output coordinate * stride + (dz,dy,dx) (padding folded)  */
+} occd_conv_tap;
+
+typedef struct {
+  int impl; /* OCCD_CONV_IMPL_*                                                                   */
+  /* sources: channels-last bf16 [B][ID][IH][IW][cstride], channels [coff, coff+C) are read        */
+  int n_src;
+  const void* src[OCCD_CONV_MAX_SRC];
+  int src_C[OCCD_CONV_MAX_SRC];
+  int src_cstride[OCCD_CONV_MAX_SRC];
+  int src_coff[OCCD_CONV_MAX_SRC];
+  int B, ID, IH, IW; /* shared by all sources                                                      */
+  int stride[3];     /* (sd, sh, sw)                                                               */
+  int n_taps;
+  occd_conv_tap taps[OCCD_CONV_MAX_TAPS];
+  /* weights: bf16 [n_taps][Cout_pad][Kpad], K contiguous, zero padded; bias fp32 [Cout_pad]        */
+  const void* weight;
+  const float* bias;
+  int Cout, Cout_pad, Kpad;
+  /* iteration space of the launch and its mapping to output coordinates: o_full = o*omul + oadd    */
+  int OD, OH, OW;
+  int omul[3], oadd[3];
+  int ODf, OHf, OWf; /* full output grid (== OD,OH,OW unless omul != 1)                            */
+  /* out0: channels-last bf16.  v = acc + bias + res1 (+ res2 if !res2_post); out1 = v;             */
+  /*       out0 = act(v) (+ res2 if res2_post)                                                      */
+  void* out0;
+  int out0_cstride, out0_coff;
+  int act;
+  const void* res1; /* channels-last bf16 on the full output grid, or NULL                         */
+  int res1_cstride, res1_coff;
+  const void* res2;
+  int res2_cstride, res2_coff;
+  int res2_post; /* 1: res2 is added AFTER the activation (modules.py Upsample + skip)            */
+  /* out1: optional second output holding the PRE-activation value                                  */
+  int out1_mode;
+  void* out1;
+  int out1_cstride, out1_coff; /* channels-last mode                                               */
+  int out1_C;                  /* planar mode: channels of the planar tensor, written at coff+n    */
+} occd_conv_desc;
+
+typedef struct occd_conv_plan occd_conv_plan;
+
+/* Validates the descriptor, encodes the TMA tensor maps (pointers are baked in: buffers must stay  */
+/* allocated and in place) and picks the tiling.  Host call; needs a current CUDA context for TC.   */
+int occd_conv_plan_create(const occd_conv_desc* desc, occd_conv_plan** plan);
+int occd_conv_plan_destroy(occd_conv_plan* plan);
+int occd_conv_run(const occd_conv_plan* plan, void* stream);
+/* introspection for tests / profiling: tile box (TD,TH,TW), N tile, K chunk, stages, grid          */
+int occd_conv_plan_info(const occd_conv_plan* plan, int* info8);
+
+/* -------------------------------------------------------------------------------------------- */
+/* small channels-last helpers                                                                   */
+/* nn.Softmax(dim=1) over C<=32 planar fp32 channels, written as a bf16 channel window (the      */
+/* torch.cat([x_in, softmax(x_occ)]) of modules.py:168-171)                                        */
+int occd_softmax_planar_to_cl(const float* in, void* out, long long B, int C, long long S, int cstride,
+                              int coff, void* stream);
+/* out[b][c][p] = in[b][p][coff+c]: turns a channels-last activation into a K-major GEMM weight  */
+/* (the mega-context operand of torch.bmm, CRP3D.py:62-63,81); out rows have leading dim ldo      */
+int occd_cl_transpose(const void* in, void* out, int B, int P, int C, int cstride, int coff, int ldo,
+                      long long out_bstride, void* stream);
+/* copy a channel window (C % 8 == 0) between channels-last buffers (torch.cat of CRP3D.py:90)    */
+int occd_copy_channels(const void* in, void* out, long long positions, int C, int in_cstride, int in_coff,
+                       int out_cstride, int out_coff, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,48 @@ class SfaParams(C.Structure):
     ]
 
 
+CONV_MAX_TAPS, CONV_MAX_SRC = 81, 3
+CONV_IMPL_TC, CONV_IMPL_SIMT = 0, 1
+OUT1_NONE, OUT1_BF16_CL, OUT1_F32_PLANAR = 0, 1, 2
+
+
+class ConvTap(C.Structure):
+    _fields_ = [("src", C.c_int), ("dz", C.c_int), ("dy", C.c_int), ("dx", C.c_int)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("impl", C.c_int),
+        ("n_src", C.c_int),
+        ("src", C.c_void_p * CONV_MAX_SRC),
+        ("src_C", C.c_int * CONV_MAX_SRC),
+        ("src_cstride", C.c_int * CONV_MAX_SRC),
+        ("src_coff", C.c_int * CONV_MAX_SRC),
+        ("B", C.c_int), ("ID", C.c_int), ("IH", C.c_int), ("IW", C.c_int),
+        ("stride", C.c_int * 3),
+        ("n_taps", C.c_int),
+        ("taps", ConvTap * CONV_MAX_TAPS),
+        ("weight", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("Cout", C.c_int), ("Cout_pad", C.c_int), ("Kpad", C.c_int),
+        ("OD", C.c_int), ("OH", C.c_int), ("OW", C.c_int),
+        ("omul", C.c_int * 3), ("oadd", C.c_int * 3),
+        ("ODf", C.c_int), ("OHf", C.c_int), ("OWf", C.c_int),
+        ("out0", C.c_void_p),
+        ("out0_cstride", C.c_int), ("out0_coff", C.c_int),
+        ("act", C.c_int),
+        ("res1", C.c_void_p),
+        ("res1_cstride", C.c_int), ("res1_coff", C.c_int),
+        ("res2", C.c_void_p),
+        ("res2_cstride", C.c_int), ("res2_coff", C.c_int),
+        ("res2_post", C.c_int),
+        ("out1_mode", C.c_int),
+        ("out1", C.c_void_p),
+        ("out1_cstride", C.c_int), ("out1_coff", C.c_int),
+        ("out1_C", C.c_int),
+    ]
+
+
 # every symbol include/occdepth_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SYMBOLS = {
@@ -49,6 +91,13 @@ SYMBOLS = {
     "occd_sfa_lift_fwd": (C.c_int, [C.POINTER(SfaParams), _vp]),
     "occd_planar_to_cl": (C.c_int, [_vp, _vp, _i, _ll, _i, _ll, _i, _vp]),
     "occd_cl_to_planar": (C.c_int, [_vp, _i, _vp, _ll, _i, _ll, _i, _vp]),
+    "occd_conv_plan_create": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_void_p)]),
+    "occd_conv_plan_destroy": (C.c_int, [_vp]),
+    "occd_conv_run": (C.c_int, [_vp, _vp]),
+    "occd_conv_plan_info": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "occd_softmax_planar_to_cl": (C.c_int, [_vp, _vp, _ll, _i, _ll, _i, _i, _vp]),
+    "occd_cl_transpose": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _vp]),
+    "occd_copy_channels": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
 }
 
 

@@ -1,0 +1,483 @@
+// Generalised N-d convolution as implicit GEMM.
+//   TC path  : TMA (5-D tiled tensor maps, zero-filled halos, traversal strides) -> swizzled smem ->
+//              tcgen05.mma (M=128 positions x N<=256 channels, fp32 accumulators in TMEM) ->
+//              tcgen05.ld epilogue (bias + residuals + activation, bf16 channels-last / fp32 planar stores)
+//   SIMT path: CUDA-core direct convolution with identical semantics (cross-check and odd shapes)
+// See include/occdepth_b200.h for the reference call sequences this replaces.
+#include "conv_common.cuh"
+#include "conv_tc.cuh"
+#include <new>
+#include <stdio.h>
+#include <string.h>
+
+namespace {
+
+constexpr int kTcThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer (+TMEM alloc), warps 2-5: epilogue
+constexpr int kMaxStages = 8;
+
+struct TcParams {
+  ConvEpi epi;
+  int n_taps;
+  int n_kchunks[OCCD_CONV_MAX_SRC];
+  int tiles_w, tiles_h, tiles_d;
+  int TD, TH, TW;
+  int stride[3];
+  int Cout_pad, N_tile;
+  int stages;
+  int a_bytes, b_stride, b_bytes;
+  int tmem_cols;
+  signed char tap_src[OCCD_CONV_MAX_TAPS];
+  short tap_dz[OCCD_CONV_MAX_TAPS], tap_dy[OCCD_CONV_MAX_TAPS], tap_dx[OCCD_CONV_MAX_TAPS];
+};
+
+template <int KC>
+__global__ void __launch_bounds__(kTcThreads)
+conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap tmA0,
+               const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmW) {
+  constexpr int ROW_BYTES = KC * 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem is only guaranteed 16-byte aligned: round the base up to 1024 (swizzle atom alignment)
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_a + (uint32_t)p.stages * p.a_bytes;
+  const uint32_t bar_base = smem_b + (uint32_t)p.stages * p.b_stride;  // 8-byte aligned (multiples of 1024)
+  const uint32_t full_bar = bar_base;
+  const uint32_t empty_bar = bar_base + 8u * kMaxStages;
+  const uint32_t tmem_full_bar = bar_base + 16u * kMaxStages;
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile decode
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h; t /= p.tiles_h;
+  const int td = t % p.tiles_d; t /= p.tiles_d;
+  const int b = t;
+  const int od0 = td * p.TD, oh0 = th * p.TH, ow0 = tw * p.TW;
+  const int n0 = blockIdx.y * p.N_tile;
+
+  int total_iters = 0;
+  for (int i = 0; i < p.n_taps; ++i) total_iters += p.n_kchunks[p.tap_src[i]];
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA0);
+    tc::prefetch_tmap(&tmW);
+    for (int s = 0; s < p.stages; ++s) {
+      tc::mbar_init(full_bar + 8u * s, 1);
+      tc::mbar_init(empty_bar + 8u * s, 1);
+    }
+    tc::mbar_init(tmem_full_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      const CUtensorMap* maps[3] = {&tmA0, &tmA1, &tmA2};
+      int it = 0;
+      for (int tp = 0; tp < p.n_taps; ++tp) {
+        const int src = p.tap_src[tp];
+        const int cw = ow0 * p.stride[2] + p.tap_dx[tp];
+        const int ch = oh0 * p.stride[1] + p.tap_dy[tp];
+        const int cd = od0 * p.stride[0] + p.tap_dz[tp];
+        const int wrow = tp * p.Cout_pad + n0;
+        for (int kc = 0; kc < p.n_kchunks[src]; ++kc, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          tc::mbar_wait(empty_bar + 8u * s, ph ^ 1u);
+          tc::mbar_expect_tx(full_bar + 8u * s, (uint32_t)(p.a_bytes + p.b_bytes));
+          tc::tma_load_5d(smem_a + (uint32_t)s * p.a_bytes, maps[src], full_bar + 8u * s, kc * KC, cw, ch, cd, b);
+          tc::tma_load_2d(smem_b + (uint32_t)s * p.b_stride, &tmW, full_bar + 8u * s, kc * KC, wrow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = tc::make_idesc_bf16(128, p.N_tile);
+      for (int it = 0; it < total_iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        tc::mbar_wait(full_bar + 8u * s, ph);
+        tc::fence_after_sync();
+        const uint32_t a_addr = smem_a + (uint32_t)s * p.a_bytes;
+        const uint32_t b_addr = smem_b + (uint32_t)s * p.b_stride;
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k) {
+          const uint64_t da = tc::make_sdesc(a_addr + k * 32, ROW_BYTES);
+          const uint64_t db = tc::make_sdesc(b_addr + k * 32, ROW_BYTES);
+          tc::mma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        tc::mma_commit(empty_bar + 8u * s);  // frees the smem stage when these MMAs retire
+      }
+      tc::mma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int rw = row % p.TW;
+    const int rh = (row / p.TW) % p.TH;
+    const int rd = row / (p.TW * p.TH);
+    const int od = od0 + rd, oh = oh0 + rh, ow = ow0 + rw;
+    const bool valid = od < p.epi.OD && oh < p.epi.OH && ow < p.epi.OW;
+    tc::mbar_wait(tmem_full_bar, 0);
+    tc::fence_after_sync();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
+      float v[16];
+      tc::tmem_ld16(taddr + (uint32_t)c0, v);
+      if (valid) conv_epilogue_row<16>(p.epi, b, od, oh, ow, n0 + c0, v);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT direct convolution: one thread = one output position x 8 output channels
+struct SimtParams {
+  ConvEpi epi;
+  int n_src, n_taps;
+  const __nv_bfloat16* src[OCCD_CONV_MAX_SRC];
+  int src_C[OCCD_CONV_MAX_SRC], src_cstride[OCCD_CONV_MAX_SRC], src_coff[OCCD_CONV_MAX_SRC];
+  int ID, IH, IW;
+  int stride[3];
+  const __nv_bfloat16* weight;
+  int Cout_pad, Kpad;
+  signed char tap_src[OCCD_CONV_MAX_TAPS];
+  short tap_dz[OCCD_CONV_MAX_TAPS], tap_dy[OCCD_CONV_MAX_TAPS], tap_dx[OCCD_CONV_MAX_TAPS];
+};
+
+__global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ SimtParams p) {
+  const int ngroups = p.epi.Cout_store / 8;
+  const long long total = (long long)p.epi.B * p.epi.OD * p.epi.OH * p.epi.OW * ngroups;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = (int)(idx % ngroups);
+  long long pos = idx / ngroups;
+  const int ow = (int)(pos % p.epi.OW); pos /= p.epi.OW;
+  const int oh = (int)(pos % p.epi.OH); pos /= p.epi.OH;
+  const int od = (int)(pos % p.epi.OD); pos /= p.epi.OD;
+  const int b = (int)pos;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int tp = 0; tp < p.n_taps; ++tp) {
+    const int s = p.tap_src[tp];
+    const int id = od * p.stride[0] + p.tap_dz[tp];
+    const int ih = oh * p.stride[1] + p.tap_dy[tp];
+    const int iw = ow * p.stride[2] + p.tap_dx[tp];
+    if (id < 0 || id >= p.ID || ih < 0 || ih >= p.IH || iw < 0 || iw >= p.IW) continue;
+    const __nv_bfloat16* in =
+        p.src[s] + ((((long long)b * p.ID + id) * p.IH + ih) * p.IW + iw) * p.src_cstride[s] + p.src_coff[s];
+    const __nv_bfloat16* w = p.weight + ((long long)tp * p.Cout_pad + g * 8) * p.Kpad;
+    const int C = p.src_C[s];
+    for (int c = 0; c < C; c += 8) {
+      float x[8];
+      unpack8(*reinterpret_cast<const uint4*>(in + c), x);
+      if (c + 8 > C) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (c + i >= C) x[i] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float wv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(w + (long long)j * p.Kpad + c)), wv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j] = fmaf(x[i], wv[i], acc[j]);
+      }
+    }
+  }
+  conv_epilogue_row<8>(p.epi, b, od, oh, ow, g * 8, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+}  // namespace
+
+struct occd_conv_plan {
+  int impl;
+  int kc;
+  TcParams tc;
+  SimtParams simt;
+  CUtensorMap tmA[OCCD_CONV_MAX_SRC];
+  CUtensorMap tmW;
+  dim3 grid;
+  size_t smem;
+};
+
+static int fill_epi(const occd_conv_desc* d, ConvEpi* e) {
+  e->B = d->B; e->OD = d->OD; e->OH = d->OH; e->OW = d->OW;
+  for (int i = 0; i < 3; ++i) { e->omul[i] = d->omul[i]; e->oadd[i] = d->oadd[i]; }
+  e->ODf = d->ODf; e->OHf = d->OHf; e->OWf = d->OWf;
+  e->Cout = d->Cout;
+  e->Cout_store = round_up(d->Cout, 8);
+  e->bias = d->bias;
+  e->out0 = reinterpret_cast<__nv_bfloat16*>(d->out0);
+  e->out0_cstride = d->out0_cstride; e->out0_coff = d->out0_coff;
+  e->act = d->act;
+  e->res1 = reinterpret_cast<const __nv_bfloat16*>(d->res1);
+  e->res1_cstride = d->res1_cstride; e->res1_coff = d->res1_coff;
+  e->res2 = reinterpret_cast<const __nv_bfloat16*>(d->res2);
+  e->res2_cstride = d->res2_cstride; e->res2_coff = d->res2_coff; e->res2_post = d->res2_post;
+  e->out1_mode = d->out1_mode; e->out1 = d->out1;
+  e->out1_cstride = d->out1_cstride; e->out1_coff = d->out1_coff; e->out1_C = d->out1_C;
+  return 0;
+}
+
+extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** out) {
+  OCCD_CHECK_ARG(d && out, "occd_conv_plan_create: null argument");
+  OCCD_CHECK_ARG(d->n_src >= 1 && d->n_src <= OCCD_CONV_MAX_SRC, "occd_conv_plan_create: n_src");
+  OCCD_CHECK_ARG(d->n_taps >= 1 && d->n_taps <= OCCD_CONV_MAX_TAPS, "occd_conv_plan_create: n_taps");
+  OCCD_CHECK_ARG(d->B > 0 && d->ID > 0 && d->IH > 0 && d->IW > 0 && d->OD > 0 && d->OH > 0 && d->OW > 0,
+                 "occd_conv_plan_create: dims");
+  OCCD_CHECK_ARG(d->Cout > 0 && d->Cout_pad >= d->Cout && d->Cout_pad % 16 == 0, "occd_conv_plan_create: Cout_pad");
+  OCCD_CHECK_ARG(d->Kpad > 0 && d->Kpad % 8 == 0, "occd_conv_plan_create: Kpad must be a multiple of 8");
+  OCCD_CHECK_ARG(d->weight && d->bias, "occd_conv_plan_create: weight/bias");
+  OCCD_CHECK_ARG(d->out0 || d->out1_mode != OCCD_OUT1_NONE, "occd_conv_plan_create: no output");
+  const int cst = round_up(d->Cout, 8);
+  if (d->out0) OCCD_CHECK_ARG(d->out0_coff % 8 == 0 && d->out0_cstride % 8 == 0 && d->out0_coff + cst <= d->out0_cstride,
+                              "occd_conv_plan_create: out0 channel window");
+  if (d->res1) OCCD_CHECK_ARG(d->res1_coff % 8 == 0 && d->res1_cstride % 8 == 0 && d->res1_coff + cst <= d->res1_cstride,
+                              "occd_conv_plan_create: res1 channel window");
+  if (d->res2) OCCD_CHECK_ARG(d->res2_coff % 8 == 0 && d->res2_cstride % 8 == 0 && d->res2_coff + cst <= d->res2_cstride,
+                              "occd_conv_plan_create: res2 channel window");
+  if (d->out1_mode == OCCD_OUT1_BF16_CL)
+    OCCD_CHECK_ARG(d->out1 && d->out1_coff % 8 == 0 && d->out1_cstride % 8 == 0 && d->out1_coff + cst <= d->out1_cstride,
+                   "occd_conv_plan_create: out1 channel window");
+  if (d->out1_mode == OCCD_OUT1_F32_PLANAR)
+    OCCD_CHECK_ARG(d->out1 && d->out1_coff + d->Cout <= d->out1_C, "occd_conv_plan_create: out1 planar window");
+  for (int i = 0; i < 3; ++i) {
+    OCCD_CHECK_ARG(d->stride[i] >= 1 && d->stride[i] <= 8 && d->omul[i] >= 1, "occd_conv_plan_create: stride/omul");
+  }
+  OCCD_CHECK_ARG((long long)(d->OD - 1) * d->omul[0] + d->oadd[0] < d->ODf &&
+                 (long long)(d->OH - 1) * d->omul[1] + d->oadd[1] < d->OHf &&
+                 (long long)(d->OW - 1) * d->omul[2] + d->oadd[2] < d->OWf, "occd_conv_plan_create: output mapping");
+  int maxC = 0;
+  for (int s = 0; s < d->n_src; ++s) {
+    OCCD_CHECK_ARG(d->src[s] && d->src_C[s] > 0 && d->src_cstride[s] % 8 == 0 && d->src_coff[s] % 8 == 0 &&
+                   d->src_coff[s] + d->src_C[s] <= d->src_cstride[s], "occd_conv_plan_create: source channel window");
+    OCCD_CHECK_ARG(d->src_C[s] <= d->Kpad, "occd_conv_plan_create: Kpad smaller than a source");
+    maxC = d->src_C[s] > maxC ? d->src_C[s] : maxC;
+  }
+  for (int i = 0; i < d->n_taps; ++i) {
+    OCCD_CHECK_ARG(d->taps[i].src >= 0 && d->taps[i].src < d->n_src, "occd_conv_plan_create: tap source");
+    OCCD_CHECK_ARG(abs(d->taps[i].dz) < 30000 && abs(d->taps[i].dy) < 30000 && abs(d->taps[i].dx) < 30000,
+                   "occd_conv_plan_create: tap offset");
+  }
+  OCCD_CHECK_ARG(d->impl == OCCD_CONV_IMPL_TC || d->impl == OCCD_CONV_IMPL_SIMT, "occd_conv_plan_create: impl");
+
+  occd_conv_plan* pl = new (std::nothrow) occd_conv_plan;
+  OCCD_CHECK_ARG(pl != nullptr, "occd_conv_plan_create: out of memory");
+  memset(pl, 0, sizeof(*pl));
+  pl->impl = d->impl;
+
+  if (d->impl == OCCD_CONV_IMPL_SIMT) {
+    SimtParams& s = pl->simt;
+    fill_epi(d, &s.epi);
+    s.n_src = d->n_src; s.n_taps = d->n_taps;
+    for (int i = 0; i < d->n_src; ++i) {
+      s.src[i] = reinterpret_cast<const __nv_bfloat16*>(d->src[i]);
+      s.src_C[i] = d->src_C[i]; s.src_cstride[i] = d->src_cstride[i]; s.src_coff[i] = d->src_coff[i];
+    }
+    s.ID = d->ID; s.IH = d->IH; s.IW = d->IW;
+    for (int i = 0; i < 3; ++i) s.stride[i] = d->stride[i];
+    s.weight = reinterpret_cast<const __nv_bfloat16*>(d->weight);
+    s.Cout_pad = d->Cout_pad; s.Kpad = d->Kpad;
+    for (int i = 0; i < d->n_taps; ++i) {
+      s.tap_src[i] = (signed char)d->taps[i].src;
+      s.tap_dz[i] = (short)d->taps[i].dz; s.tap_dy[i] = (short)d->taps[i].dy; s.tap_dx[i] = (short)d->taps[i].dx;
+    }
+    const long long total = (long long)d->B * d->OD * d->OH * d->OW * (s.epi.Cout_store / 8);
+    pl->grid = dim3((unsigned)((total + 127) / 128));
+    *out = pl;
+    return OCCD_OK;
+  }
+
+  // ---------------- TC plan ----------------
+  TcParams& t = pl->tc;
+  fill_epi(d, &t.epi);
+  const int KC = maxC > 32 ? 64 : (maxC > 16 ? 32 : 16);
+  pl->kc = KC;
+  if (d->Kpad % KC != 0) {
+    delete pl;
+    occd_set_last_error("occd_conv_plan_create: Kpad must be a multiple of the K chunk (64/32/16)");
+    return OCCD_ERR_ARG;
+  }
+  t.n_taps = d->n_taps;
+  for (int s = 0; s < OCCD_CONV_MAX_SRC; ++s) t.n_kchunks[s] = s < d->n_src ? (d->src_C[s] + KC - 1) / KC : 0;
+  for (int i = 0; i < 3; ++i) t.stride[i] = d->stride[i];
+  for (int i = 0; i < d->n_taps; ++i) {
+    t.tap_src[i] = (signed char)d->taps[i].src;
+    t.tap_dz[i] = (short)d->taps[i].dz; t.tap_dy[i] = (short)d->taps[i].dy; t.tap_dx[i] = (short)d->taps[i].dx;
+  }
+  // tile box (TD,TH,TW), product 128, minimal padded volume; ties -> widest TW
+  {
+    long long best = -1;
+    for (int tw = 128; tw >= 1; tw >>= 1)
+      for (int th = 128 / tw; th >= 1; th >>= 1) {
+        const int tdd = 128 / (tw * th);
+        if (tw * d->stride[2] > 256 || th * d->stride[1] > 256 || tdd * d->stride[0] > 256) continue;
+        const long long vol = (long long)round_up(d->OW, tw) * round_up(d->OH, th) * round_up(d->OD, tdd);
+        if (best < 0 || vol < best) { best = vol; t.TW = tw; t.TH = th; t.TD = tdd; }
+      }
+  }
+  t.tiles_w = (d->OW + t.TW - 1) / t.TW; t.tiles_h = (d->OH + t.TH - 1) / t.TH; t.tiles_d = (d->OD + t.TD - 1) / t.TD;
+  // N tile: largest divisor of Cout_pad that is a multiple of 16 and <= 256
+  t.Cout_pad = d->Cout_pad;
+  t.N_tile = 16;
+  for (int n = 16; n <= 256 && n <= d->Cout_pad; n += 16)
+    if (d->Cout_pad % n == 0) t.N_tile = n;
+  t.tmem_cols = 32;
+  while (t.tmem_cols < t.N_tile) t.tmem_cols *= 2;
+  t.a_bytes = 128 * KC * 2;
+  t.b_bytes = t.N_tile * KC * 2;
+  t.b_stride = round_up(t.b_bytes, 1024);
+  const int stage_bytes = t.a_bytes + t.b_stride;
+  int total_iters = 0;
+  for (int i = 0; i < d->n_taps; ++i) total_iters += t.n_kchunks[d->taps[i].src];
+  int budget = (4 * stage_bytes <= 100 * 1024) ? 100 * 1024 : 200 * 1024;
+  int stages = budget / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > total_iters) stages = total_iters;
+  if (stages < 1) stages = 1;
+  t.stages = stages;
+  pl->smem = (size_t)stages * stage_bytes + 16 * kMaxStages + 16 + 1024;  // + barriers + alignment slack
+  const long long gx = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w;
+  if (gx > 2147483647LL || d->Cout_pad / t.N_tile > 65535) {
+    delete pl;
+    occd_set_last_error("occd_conv_plan_create: grid too large");
+    return OCCD_ERR_UNSUPPORTED;
+  }
+  pl->grid = dim3((unsigned)gx, (unsigned)(d->Cout_pad / t.N_tile));
+
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    delete pl;
+    occd_set_last_error("occd_conv_plan_create: cuTensorMapEncodeTiled unavailable (no CUDA driver / GPU?)");
+    return OCCD_ERR_CUDA;
+  }
+  const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                         : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  for (int s = 0; s < d->n_src; ++s) {
+    const cuuint64_t cs = (cuuint64_t)d->src_cstride[s] * 2;
+    cuuint64_t gdim[5] = {(cuuint64_t)d->src_C[s], (cuuint64_t)d->IW, (cuuint64_t)d->IH, (cuuint64_t)d->ID,
+                          (cuuint64_t)d->B};
+    cuuint64_t gstr[4] = {cs, cs * d->IW, cs * d->IW * d->IH, cs * d->IW * d->IH * d->ID};
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)(t.TW * d->stride[2]), (cuuint32_t)(t.TH * d->stride[1]),
+                         (cuuint32_t)(t.TD * d->stride[0]), 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)d->stride[2], (cuuint32_t)d->stride[1], (cuuint32_t)d->stride[0], 1};
+    void* base = (void*)((const char*)d->src[s] + (size_t)d->src_coff[s] * 2);
+    CUresult r = enc(&pl->tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      char msg[160];
+      snprintf(msg, sizeof(msg), "occd_conv_plan_create: cuTensorMapEncodeTiled(source %d) failed with %d", s, (int)r);
+      delete pl;
+      occd_set_last_error(msg);
+      return OCCD_ERR_CUDA;
+    }
+  }
+  for (int s = d->n_src; s < OCCD_CONV_MAX_SRC; ++s) pl->tmA[s] = pl->tmA[0];
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)d->Kpad, (cuuint64_t)d->n_taps * d->Cout_pad};
+    cuuint64_t gstr[1] = {(cuuint64_t)d->Kpad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)t.N_tile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&pl->tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d->weight, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      char msg[160];
+      snprintf(msg, sizeof(msg), "occd_conv_plan_create: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+      delete pl;
+      occd_set_last_error(msg);
+      return OCCD_ERR_CUDA;
+    }
+  }
+  *out = pl;
+  return OCCD_OK;
+}
+
+extern "C" int occd_conv_plan_destroy(occd_conv_plan* plan) {
+  delete plan;
+  return OCCD_OK;
+}
+
+extern "C" int occd_conv_plan_info(const occd_conv_plan* pl, int* info) {
+  OCCD_CHECK_ARG(pl && info, "occd_conv_plan_info: null");
+  if (pl->impl == OCCD_CONV_IMPL_SIMT) {
+    for (int i = 0; i < 8; ++i) info[i] = 0;
+    info[6] = (int)pl->grid.x;
+    return OCCD_OK;
+  }
+  info[0] = pl->tc.TD; info[1] = pl->tc.TH; info[2] = pl->tc.TW; info[3] = pl->tc.N_tile;
+  info[4] = pl->kc; info[5] = pl->tc.stages; info[6] = (int)pl->grid.x; info[7] = (int)pl->grid.y;
+  return OCCD_OK;
+}
+
+template <int KC>
+static int launch_tc(const occd_conv_plan* pl, cudaStream_t st) {
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
+    attr_set = true;
+  }
+  conv_tc_kernel<KC><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->tc, pl->tmA[0], pl->tmA[1], pl->tmA[2], pl->tmW);
+  OCCD_CHECK_LAUNCH();
+  return OCCD_OK;
+}
+
+extern "C" int occd_conv_run(const occd_conv_plan* pl, void* stream) {
+  OCCD_CHECK_ARG(pl != nullptr, "occd_conv_run: null plan");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (pl->impl == OCCD_CONV_IMPL_SIMT) {
+    conv_simt_kernel<<<pl->grid, 128, 0, st>>>(pl->simt);
+    OCCD_CHECK_LAUNCH();
+    return OCCD_OK;
+  }
+  switch (pl->kc) {
+    case 64: return launch_tc<64>(pl, st);
+    case 32: return launch_tc<32>(pl, st);
+    case 16: return launch_tc<16>(pl, st);
+  }
+  occd_set_last_error("occd_conv_run: bad plan");
+  return OCCD_ERR_ARG;
+}

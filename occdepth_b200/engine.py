@@ -1,0 +1,314 @@
+"""Host-side execution engine: channels-last activation buffers + planned kernel launches.
+
+PyTorch is used for device memory and streams only; every operator is a C-ABI call into libocc_b200.so
+(include/occdepth_b200.h).  A `Plan` is a static list of prepared launches over pre-allocated buffers
+(weights packed once, TMA descriptors encoded once), so a forward pass is a replay -- optionally captured
+into a CUDA graph.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+
+ACT = dict(none=_lib.ACT_NONE, relu=_lib.ACT_RELU, leaky=_lib.ACT_LEAKY, silu=_lib.ACT_SILU,
+           sigmoid=_lib.ACT_SIGMOID)
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+def default_impl():
+    v = os.environ.get("OCCDEPTH_CONV_IMPL", "tc").lower()
+    if v not in ("tc", "simt"):
+        raise ValueError("OCCDEPTH_CONV_IMPL must be 'tc' or 'simt'")
+    return _lib.CONV_IMPL_TC if v == "tc" else _lib.CONV_IMPL_SIMT
+
+
+def require_cuda(t, what):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError("%s: occdepth_b200 runs on CUDA (sm_100a) only -- there is no CPU fallback" % what)
+
+
+class CL:
+    """channels-last bf16 activation: a channel window [coff, coff+C) of a [B,D,H,W,cstride] buffer."""
+
+    def __init__(self, buf, C_, coff=0):
+        assert buf.dtype == torch.bfloat16 and buf.dim() == 5 and buf.is_contiguous()
+        self.buf, self.C, self.coff = buf, int(C_), int(coff)
+        assert self.coff % 8 == 0 and buf.shape[4] % 8 == 0 and self.coff + self.C <= buf.shape[4]
+
+    @staticmethod
+    def alloc(B, D, H, W, C_, device):
+        return CL(torch.zeros(B, D, H, W, _round_up(C_, 8), dtype=torch.bfloat16, device=device), C_)
+
+    @property
+    def dims(self):
+        return tuple(self.buf.shape[:4])
+
+    @property
+    def cstride(self):
+        return self.buf.shape[4]
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr()
+
+    def window(self, coff, C_):
+        return CL(self.buf, C_, self.coff + coff)
+
+    def spatial(self):
+        return self.buf.shape[1] * self.buf.shape[2] * self.buf.shape[3]
+
+    # ---- module-boundary conversions (reference tensors are NCHW / NCDHW fp32) ----
+    @staticmethod
+    def from_planar(x, out=None):
+        """x: fp32 [B,C,H,W] or [B,C,D,H,W] (CUDA) -> CL (bf16)."""
+        require_cuda(x, "CL.from_planar")
+        x = x.contiguous().float()
+        if x.dim() == 4:
+            B, C_, H, W = x.shape
+            D = 1
+        else:
+            B, C_, D, H, W = x.shape
+        if out is None:
+            out = CL.alloc(B, D, H, W, C_, x.device)
+        assert out.coff == 0 and out.C == C_
+        S = D * H * W
+        rc = _lib.lib().occd_planar_to_cl(x.data_ptr(), out.ptr, _lib.DTYPE_BF16, B, C_, S, out.cstride,
+                                          _lib.stream_ptr())
+        _lib.check(rc, "occd_planar_to_cl")
+        return out
+
+    def to_planar(self, squeeze_d=False):
+        """-> fp32 [B,C,D,H,W] (or [B,C,H,W] when squeeze_d)."""
+        B, D, H, W = self.dims
+        out = torch.empty(B, self.C, D, H, W, dtype=torch.float32, device=self.buf.device)
+        S = D * H * W
+        rc = _lib.lib().occd_cl_to_planar(self.ptr + 2 * self.coff, _lib.DTYPE_BF16, out.data_ptr(), B, self.C, S,
+                                          self.cstride, _lib.stream_ptr())
+        _lib.check(rc, "occd_cl_to_planar")
+        return out[:, :, 0] if squeeze_d else out
+
+
+def fold_bn(weight, bias, bn, eps=None):
+    """conv -> BatchNorm(eval) == conv with w*scale and (b-mean)*scale+beta.  Returns fp32 (w, b)."""
+    w = weight.detach().float()
+    co = w.shape[0]
+    b = bias.detach().float() if bias is not None else torch.zeros(co, device=w.device)
+    if bn is None:
+        return w, b
+    e = bn.eps if eps is None else eps
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + e)
+    shape = [co] + [1] * (w.dim() - 1)
+    return w * scale.view(shape), (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+
+
+class ConvOp:
+    """One planned implicit-GEMM launch (occd_conv_plan_create / occd_conv_run)."""
+
+    def __init__(self, srcs, taps, tap_weights, bias, out_dims, out0=None, act="none", res1=None, res2=None,
+                 stride=(1, 1, 1), omul=(1, 1, 1), oadd=(0, 0, 0), full_dims=None, out1=None, out1_mode="none",
+                 out1_coff=0, impl=None, name="", res2_post=False, weight_buf=None):
+        """srcs: list[CL] (same B,D,H,W);  taps: [(src_idx, dz, dy, dx)];  tap_weights: list of fp32 [Cout, C_src]
+        bias: fp32 [Cout];  out0/res1/res2: CL on the full output grid;  out1: CL (pre-activation bf16 copy) or
+        fp32 planar tensor [B, C1, D, H, W] (mode "planar", written at channel out1_coff)."""
+        self.name = name
+        dev = srcs[0].buf.device
+        B, ID, IH, IW = srcs[0].dims
+        for s in srcs:
+            assert s.dims == (B, ID, IH, IW)
+        Cout = int(bias.numel())
+        Cout_pad = _round_up(Cout, 16)
+        maxC = max(s.C for s in srcs)
+        KC = 64 if maxC > 32 else (32 if maxC > 16 else 16)
+        Kpad = _round_up(maxC, KC)
+        if weight_buf is not None:
+            # weights produced at run time by another launch (CRP bmm): bf16 [n_taps, Cout_pad, Kpad]
+            assert weight_buf.dtype == torch.bfloat16 and tuple(weight_buf.shape) == (len(taps), Cout_pad, Kpad)
+            self.weight = weight_buf
+        else:
+            wp = torch.zeros(len(taps), Cout_pad, Kpad, dtype=torch.float32, device=dev)
+            for i, (tp, w) in enumerate(zip(taps, tap_weights)):
+                assert w.shape == (Cout, srcs[tp[0]].C), (w.shape, Cout, srcs[tp[0]].C)
+                wp[i, :Cout, : w.shape[1]] = w
+            self.weight = wp.to(torch.bfloat16).contiguous()
+        self.bias = torch.zeros(Cout_pad, dtype=torch.float32, device=dev)
+        self.bias[:Cout] = bias.float()
+        OD, OH, OW = out_dims
+        fd = tuple(full_dims) if full_dims is not None else (OD, OH, OW)
+        d = _lib.ConvDesc()
+        d.impl = default_impl() if impl is None else impl
+        d.n_src = len(srcs)
+        for i, s in enumerate(srcs):
+            d.src[i] = s.ptr
+            d.src_C[i], d.src_cstride[i], d.src_coff[i] = s.C, s.cstride, s.coff
+        d.B, d.ID, d.IH, d.IW = B, ID, IH, IW
+        for i in range(3):
+            d.stride[i], d.omul[i], d.oadd[i] = stride[i], omul[i], oadd[i]
+        d.n_taps = len(taps)
+        for i, (si, dz, dy, dx) in enumerate(taps):
+            d.taps[i].src, d.taps[i].dz, d.taps[i].dy, d.taps[i].dx = si, dz, dy, dx
+        d.weight, d.bias = self.weight.data_ptr(), self.bias.data_ptr()
+        d.Cout, d.Cout_pad, d.Kpad = Cout, Cout_pad, Kpad
+        d.OD, d.OH, d.OW = OD, OH, OW
+        d.ODf, d.OHf, d.OWf = fd
+        d.act = ACT[act]
+        d.res2_post = 1 if res2_post else 0
+        self._keep = [srcs, out0, res1, res2, out1]
+        if out0 is not None:
+            assert out0.dims == (B,) + fd and out0.C >= Cout, (out0.dims, fd, out0.C, Cout)
+            d.out0, d.out0_cstride, d.out0_coff = out0.ptr, out0.cstride, out0.coff
+        for nm, r in (("res1", res1), ("res2", res2)):
+            if r is not None:
+                assert r.dims == (B,) + fd and r.C >= Cout
+                setattr(d, nm, r.ptr)
+                setattr(d, nm + "_cstride", r.cstride)
+                setattr(d, nm + "_coff", r.coff)
+        if out1_mode == "cl":
+            assert out1.dims == (B,) + fd
+            d.out1_mode, d.out1 = _lib.OUT1_BF16_CL, out1.ptr
+            d.out1_cstride, d.out1_coff = out1.cstride, out1.coff
+        elif out1_mode == "planar":
+            assert out1.dtype == torch.float32 and out1.is_contiguous() and tuple(out1.shape[2:]) == fd
+            d.out1_mode, d.out1 = _lib.OUT1_F32_PLANAR, out1.data_ptr()
+            d.out1_C, d.out1_coff = out1.shape[1], out1_coff
+        self.desc = d
+        self.flops = 2 * B * OD * OH * OW * Cout * sum(srcs[t[0]].C for t in taps)
+        h = C.c_void_p()
+        rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
+        _lib.check(rc, "occd_conv_plan_create(%s)" % name)
+        self.handle = h
+
+    def info(self):
+        arr = (C.c_int * 8)()
+        _lib.check(_lib.lib().occd_conv_plan_info(self.handle, arr), "occd_conv_plan_info")
+        return dict(zip(("TD", "TH", "TW", "N_tile", "KC", "stages", "grid_x", "grid_y"), list(arr)))
+
+    def run(self, stream):
+        _lib.check(_lib.lib().occd_conv_run(self.handle, stream), "occd_conv_run(%s)" % self.name)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().occd_conv_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def conv_taps(weight, dilation=(1, 1, 1), padding=(0, 0, 0), src=0):
+    """weight fp32 [Cout, Cin, kd, kh, kw] -> (taps, tap_weights) for a dense N-d convolution."""
+    co, ci, kd, kh, kw = weight.shape
+    taps, ws = [], []
+    for a in range(kd):
+        for b in range(kh):
+            for c in range(kw):
+                taps.append((src, a * dilation[0] - padding[0], b * dilation[1] - padding[1],
+                             c * dilation[2] - padding[2]))
+                ws.append(weight[:, :, a, b, c])
+    return taps, ws
+
+
+def _t3(v):
+    return (v, v, v) if isinstance(v, int) else tuple(v)
+
+
+def out_size(i, k, s, p, d):
+    return (i + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+class Plan:
+    """Ordered list of prepared launches (anything with .run(stream)) + named buffers."""
+
+    def __init__(self, device):
+        self.device = device
+        self.ops = []
+        self.flops = 0
+
+    def alloc(self, B, D, H, W, C_):
+        return CL.alloc(B, D, H, W, C_, self.device)
+
+    def add(self, op):
+        self.ops.append(op)
+        self.flops += getattr(op, "flops", 0)
+        return op
+
+    # ---- dense convolution (2-D maps have D == 1) ----
+    def conv(self, x, weight, bias, stride=1, padding=0, dilation=1, act="none", out=None, res1=None, res2=None,
+             out1=None, out1_mode="none", out1_coff=0, name="conv", impl=None, res2_post=False):
+        """x: CL; weight fp32 [Cout,Cin,kd,kh,kw] (BN already folded); returns the output CL."""
+        s, p, d = _t3(stride), _t3(padding), _t3(dilation)
+        B, ID, IH, IW = x.dims
+        co, ci, kd, kh, kw = weight.shape
+        assert ci == x.C, (ci, x.C, name)
+        od = (out_size(ID, kd, s[0], p[0], d[0]), out_size(IH, kh, s[1], p[1], d[1]),
+              out_size(IW, kw, s[2], p[2], d[2]))
+        if out is None and out1_mode != "planar":
+            out = self.alloc(B, od[0], od[1], od[2], co)
+        taps, ws = conv_taps(weight, d, p)
+        self.add(ConvOp([x], taps, ws, bias, od, out0=out, act=act, res1=res1, res2=res2, stride=s, out1=out1,
+                        out1_mode=out1_mode, out1_coff=out1_coff, name=name, impl=impl, res2_post=res2_post))
+        return out
+
+    def conv_multi(self, srcs, weights, bias, paddings, dilations, act="none", out=None, res1=None, res2=None,
+                   name="conv_multi", impl=None):
+        """sum_i conv(srcs[i], weights[i]) with one accumulator (stride 1, 'same' geometry)."""
+        B, ID, IH, IW = srcs[0].dims
+        taps, ws = [], []
+        for i, (w, p, d) in enumerate(zip(weights, paddings, dilations)):
+            t, wl = conv_taps(w, _t3(d), _t3(p), src=i)
+            taps += t
+            ws += wl
+        co = weights[0].shape[0]
+        if out is None:
+            out = self.alloc(B, ID, IH, IW, co)
+        self.add(ConvOp(srcs, taps, ws, bias, (ID, IH, IW), out0=out, act=act, res1=res1, res2=res2, name=name,
+                        impl=impl))
+        return out
+
+    def conv_transpose_k3s2(self, x, weight, bias, act="none", out=None, name="convT", impl=None, res_post=None):
+        """ConvTranspose3d(kernel 3, stride 2, padding 1, output_padding 1) as 8 sub-pixel phase convolutions.
+        weight fp32 [Cin, Cout, 3, 3, 3] (torch layout, BN folded over Cout).  out[o] += x[i] w[k], o = 2i-1+k:
+        even o=2j uses (k=1,i=j); odd o=2j+1 uses (k=2,i=j) and (k=0,i=j+1)."""
+        B, ID, IH, IW = x.dims
+        ci, co = weight.shape[:2]
+        assert ci == x.C
+        if out is None:
+            out = self.alloc(B, 2 * ID, 2 * IH, 2 * IW, co)
+        sel = {0: [(1, 0)], 1: [(2, 0), (0, 1)]}  # parity -> [(kernel index, input offset)]
+        for pd in (0, 1):
+            for ph in (0, 1):
+                for pw in (0, 1):
+                    taps, ws = [], []
+                    for (ka, oa) in sel[pd]:
+                        for (kb, ob) in sel[ph]:
+                            for (kc, oc) in sel[pw]:
+                                taps.append((0, oa, ob, oc))
+                                ws.append(weight[:, :, ka, kb, kc].t())
+                    self.add(ConvOp([x], taps, ws, bias, (ID, IH, IW), out0=out, act=act, omul=(2, 2, 2),
+                                    res2=res_post, res2_post=True,
+                                    oadd=(pd, ph, pw), full_dims=(2 * ID, 2 * IH, 2 * IW),
+                                    name="%s.p%d%d%d" % (name, pd, ph, pw), impl=impl))
+        return out
+
+    def run(self, stream=None):
+        st = _lib.stream_ptr() if stream is None else stream
+        for op in self.ops:
+            op.run(st)
+
+
+class FnOp:
+    """A prepared non-conv launch: fn(stream) -> rc."""
+
+    def __init__(self, fn, name, keep=()):
+        self.fn, self.name, self._keep = fn, name, keep
+
+    def run(self, stream):
+        _lib.check(self.fn(stream), self.name)
+
+
+def kpad_for(C_):
+    KC = 64 if C_ > 32 else (32 if C_ > 16 else 16)
+    return _round_up(C_, KC)
