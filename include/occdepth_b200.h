@@ -162,6 +162,24 @@ int occd_cl_transpose(const void* in, void* out, int B, int P, int C, int cstrid
 int occd_copy_channels(const void* in, void* out, long long positions, int C, int in_cstride, int in_coff,
                        int out_cstride, int out_coff, void* stream);
 
+/* -------------------------------------------------------------------------------------------- */
+/* EfficientNet / decoder bandwidth kernels (channels-last bf16, 2-D)                             */
+/* depthwise KxK (K = 3|5) conv + folded BN + activation; optionally accumulates the per-channel  */
+/* spatial SUM of the output into pool[B][C] (squeeze of geffnet SqueezeExcite); explicit         */
+/* top/left padding implements TF "SAME" (bottom/right implied by OH/OW). w: fp32 [K*K][C].       */
+int occd_dwconv2d_fwd(const void* in, const float* w, const float* bias, void* out, float* pool, int B, int H,
+                      int W, int OH, int OW, int C, int cs_in, int cs_out, int K, int stride, int pad_top,
+                      int pad_left, int act, void* stream);
+/* gate[b][c] = sigmoid(W2 silu(W1 (pool[b]/HW) + b1) + b2); zeroes pool. w1 [R][C], w2t [R][C]   */
+int occd_se_gate_fwd(float* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
+                     const float* b2, float* gate, int B, int C, int R, void* stream);
+/* out[row][k] = bf16(master[row][k] * gate[k]): folds x * gate into the next 1x1 conv's weights   */
+int occd_scale_weights(const float* master, const float* gate, void* out, int rows, int Kpad, int C,
+                       void* stream);
+/* F.interpolate(mode="bilinear", align_corners=True) of UpSampleBN.forward (unet2d.py:39-44)      */
+int occd_upsample_bilinear_ac(const void* in, void* out, int B, int h, int w, int OH, int OW, int C, int cs_in,
+                              int in_off, int cs_out, int out_off, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -237,7 +237,7 @@ class Plan:
 
     # ---- dense convolution (2-D maps have D == 1) ----
     def conv(self, x, weight, bias, stride=1, padding=0, dilation=1, act="none", out=None, res1=None, res2=None,
-             out1=None, out1_mode="none", out1_coff=0, name="conv", impl=None, res2_post=False):
+             out1=None, out1_mode="none", out1_coff=0, name="conv", impl=None, res2_post=False, no_out0=False):
         """x: CL; weight fp32 [Cout,Cin,kd,kh,kw] (BN already folded); returns the output CL."""
         s, p, d = _t3(stride), _t3(padding), _t3(dilation)
         B, ID, IH, IW = x.dims
@@ -245,7 +245,7 @@ class Plan:
         assert ci == x.C, (ci, x.C, name)
         od = (out_size(ID, kd, s[0], p[0], d[0]), out_size(IH, kh, s[1], p[1], d[1]),
               out_size(IW, kw, s[2], p[2], d[2]))
-        if out is None and out1_mode != "planar":
+        if out is None and not no_out0:
             out = self.alloc(B, od[0], od[1], od[2], co)
         taps, ws = conv_taps(weight, d, p)
         self.add(ConvOp([x], taps, ws, bias, od, out0=out, act=act, res1=res1, res2=res2, stride=s, out1=out1,

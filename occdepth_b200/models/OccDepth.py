@@ -1,0 +1,177 @@
+"""Drop-in for the reference `occdepth/models/OccDepth.py` (class OccDepth, forward path :31-376).
+
+Same constructor, same `forward(batch) -> dict`, same state_dict keys.  The forward is one planned sequence of
+sm_100a launches: both stereo views go through the 2D UNet as one batch, the 4-scale / 2-view Stereo-SFA lift
+is a single fused kernel writing the channels-last voxel grid the 3D UNet consumes, and the logits are written
+in the reference's NCDHW fp32 layout by the last convolution's epilogue.
+Training (`step`, losses, optimisers; OccDepth.py:378-600) is out of scope of this package.
+"""
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..engine import CL, FnOp, Plan, require_cuda
+from ._base import B200Module, _to_planar
+from .SFA import SFA, lift_multiscale
+from .unet2d import UNet2D
+from .unet3d_kitti import UNet3D as UNet3DKitti
+from .unet3d_nyu import UNet3D as UNet3DNYU
+
+try:  # the reference derives from pl.LightningModule; use it when present so Trainer-based scripts keep working
+    import pytorch_lightning as pl
+    _Base = pl.LightningModule
+except Exception:  # noqa: BLE001
+    class _Base(nn.Module):
+        def save_hyperparameters(self, *a, **k):
+            pass
+
+        def log(self, *a, **k):
+            pass
+
+
+def _get(config, name, default=None):
+    try:
+        return getattr(config, name)
+    except (AttributeError, KeyError):
+        return default
+
+
+class OccDepth(_Base, B200Module):
+    def __init__(self, class_names, class_weights, class_weights_occ=None, full_scene_size=None, project_res=[],
+                 config=None, infer_mode=False):
+        super().__init__()
+        self.project_res = project_res
+        self.full_scene_size = full_scene_size
+        self.class_names = class_names
+        self.class_weights = class_weights
+        self.class_weights_occ = class_weights_occ
+        self.dataset = config.dataset
+        self.project_scale = config.project_scale
+        self.n_relations = config.n_relations
+        self.context_prior = config.context_prior
+        self.n_classes = config.n_classes
+        self.feature = config.feature
+        self.feature_2d_oc = config.feature_2d_oc
+        self.trans_2d_to_3d = config.trans_2d_to_3d
+        self.cascade_cls = config.cascade_cls
+        self.occluded_cls = config.occluded_cls
+        self.multi_view_mode = _get(config, "multi_view_mode", True)
+        self.share_2d_backbone_gradient = _get(config, "share_2d_backbone_gradient", False)
+        print("INFO: Use cascade cls: {}".format(self.cascade_cls))
+        print("INFO: Use occluded cls: {}".format(self.occluded_cls))
+        self.infer_mode = infer_mode
+        if self.infer_mode:
+            self.context_prior = False
+        self.use_stereo_depth_gt = _get(config, "use_stereo_depth_gt", False)
+        self.use_lidar_depth_gt = _get(config, "use_lidar_depth_gt", False)
+        self.use_depth_gt = _get(config, "use_depth_gt", False)
+        assert not (self.use_stereo_depth_gt and self.use_lidar_depth_gt), "only with one depth data supported."
+        self.with_depth_gt = self.use_stereo_depth_gt or self.use_lidar_depth_gt or self.use_depth_gt
+        if self.dataset == "NYU":
+            self.net_3d_decoder = UNet3DNYU(self.n_classes, nn.BatchNorm3d, n_relations=self.n_relations,
+                                            feature=self.feature, full_scene_size=self.full_scene_size,
+                                            context_prior=self.context_prior, cascade_cls=self.cascade_cls,
+                                            infer_mode=self.infer_mode)
+        elif self.dataset == "kitti":
+            self.net_3d_decoder = UNet3DKitti(self.n_classes, nn.BatchNorm3d, project_scale=self.project_scale,
+                                              feature=self.feature, full_scene_size=self.full_scene_size,
+                                              context_prior=self.context_prior, cascade_cls=self.cascade_cls,
+                                              occluded_cls=self.occluded_cls, infer_mode=self.infer_mode)
+        self.net_rgb = UNet2D.build(out_feature=self.feature_2d_oc, use_decoder=True,
+                                    backbone_2d_name=config.backbone_2d_name,
+                                    return_up_feats=config.return_up_feats)
+        self.save_hyperparameters()
+        self.init_2d_to_3d_trans(config)
+        if self.dataset not in ("kitti", "NYU"):
+            raise NotImplementedError(self.dataset)
+
+    def init_2d_to_3d_trans(self, config):
+        print("INFO: Selected 2d->3d transformation method: {}".format(self.trans_2d_to_3d))
+        if self.trans_2d_to_3d in ("flosp", "flosp_depth"):
+            self.scale_2ds = [1, 2, 4, 8]
+            self.projects = nn.ModuleDict({
+                str(s): SFA(config.full_scene_size, project_scale=self.project_scale, dataset=self.dataset)
+                for s in self.scale_2ds})
+            if self.trans_2d_to_3d == "flosp_depth":
+                from .flosp_depth.flosp_depth import FlospDepth, flosp_depth_conf_map
+                self.flosp_depth_conf = flosp_depth_conf_map[self.dataset]
+                self.flosp_depth_conf.update({
+                    "scene_size": config.full_scene_size,
+                    "project_scale": config.project_scale,
+                    "output_channels": config.feature,
+                    "depth_net_conf": dict(in_channels=config.feature,
+                                           mid_channels=self.flosp_depth_conf["depth_net_conf"]["mid_channels"]),
+                    "return_depth": self.with_depth_gt,
+                    "infer_mode": self.infer_mode,
+                })
+                self.flosp_depth = FlospDepth(**self.flosp_depth_conf)
+        else:
+            raise NotImplementedError(f"{self.trans_2d_to_3d} is not supported yet.")
+
+    # ------------------------------------------------------------------------------------------
+    def _build(self, B, V, H, W, N, P, dev, batch):
+        plan = Plan(dev)
+        ps = self.project_scale
+        S = [int(s) // ps for s in self.full_scene_size]
+        if self.dataset == "NYU" and V == 1 and "gt_depth" in batch:
+            raise NotImplementedError("virtual right view (OccDepth.generate_virtual_img) is not built yet")
+        img = plan.alloc(B * V, 1, H, W, 3)
+        Cf = self.feature_2d_oc
+        scales = [int(s) for s in self.project_res]
+        x_rgb = self.net_rgb.emit(plan, img)                                # {"1_s": CL [B*V,1,h,w,Cf]}
+        pix = torch.zeros(B, V, N, P, 2, dtype=torch.int64, device=dev)
+        fov = torch.zeros(B, V, N, P, dtype=torch.bool, device=dev)
+        x3d = plan.alloc(B, S[0], S[1], S[2], self.feature)
+        assert Cf == self.feature, "feature_2d_oc must equal feature (the lift feeds the 3D net directly)"
+        prior = None
+        if self.trans_2d_to_3d == "flosp_depth":
+            prior = self.flosp_depth.emit(plan, x_rgb, batch, B, V)         # fp32 [B, X*Y*Z]
+        for b in range(B):
+            feats = []
+            for s in scales:
+                f = x_rgb["1_%d" % s]
+                assert f.coff == 0 and f.cstride == Cf
+                feats.append(f.buf[b * V:(b + 1) * V, 0])                   # [V, h, w, Cf] contiguous view
+            out_b = CL(x3d.buf[b:b + 1], x3d.C, 0)
+            pr = prior[b] if prior is not None else None
+            plan.add(FnOp(lambda st, feats=feats, pb=pix[b], fb=fov[b], ob=out_b, pr=pr:
+                          (lift_multiscale(feats, scales, pb, fb, ob, self.dataset, self.full_scene_size, ps,
+                                           prior=pr, scale_const=100.0, stream=st), 0)[1],
+                          "sfa_lift", keep=(feats, pix, fov, out_b)))
+        out = self.net_3d_decoder.emit(plan, x3d)
+        return plan, img, pix, fov, out
+
+    def forward(self, batch):
+        img = batch["img"]
+        if not img.is_cuda:
+            if not torch.cuda.is_available():
+                raise RuntimeError("OccDepth.forward: occdepth_b200 needs a CUDA (sm_100a) device")
+            img = img.cuda(non_blocking=True)          # the reference moves the batch in forward too (:345)
+        self._check_mode(img)
+        dev = img.device
+        if next(self.parameters()).device != dev:
+            raise RuntimeError("OccDepth.forward: model and batch are on different devices")
+        B, V, _, H, W = img.shape
+        ps = self.project_scale
+        pp = batch["projected_pix_{}".format(ps)]
+        fm = batch["fov_mask_{}".format(ps)]
+        N, P = pp[0].shape[1], pp[0].shape[2]
+        key = (B, V, H, W, N, P, str(dev))
+        ent = self._plans().get(key)
+        if ent is None:
+            with torch.no_grad():
+                ent = self._build(B, V, H, W, N, P, dev, batch)
+            self._plans()[key] = ent
+        plan, img_cl, pix, fov, out = ent
+        CL.from_planar(img.reshape(B * V, 3, H, W), out=img_cl)
+        for b in range(B):
+            pix[b].copy_(pp[b], non_blocking=True)
+            fov[b].copy_(fm[b], non_blocking=True)
+        if self.trans_2d_to_3d == "flosp_depth":
+            self.flosp_depth.stage_inputs(batch, dev)
+        plan.run()
+        res = _to_planar(out, False)
+        return res
+
+    def step(self, *a, **k):
+        raise NotImplementedError("occdepth_b200 implements OccDepth.forward only (training is out of scope)")

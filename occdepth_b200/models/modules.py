@@ -68,7 +68,7 @@ class SegmentationHead(B200Module):
         x1 = _emit_aspp(plan, self, x0, name="head.aspp")
         w, b = fold_bn(self.conv_classes.weight, self.conv_classes.bias, None)
         logits = _planar_out(plan, x1, w.shape[0])
-        plan.conv(x1, w, b, padding=1, out1=logits, out1_mode="planar", name="head.conv_classes")
+        plan.conv(x1, w, b, padding=1, out1=logits, out1_mode="planar", no_out0=True, name="head.conv_classes")
         return logits
 
     def forward(self, x_in):
@@ -94,7 +94,7 @@ class SegmentationHeadCascadeCLS(B200Module):
         x1 = _emit_aspp(plan, self, x0, out=cat.window(0, planes), name="head.aspp")
         w, b = fold_bn(self.occ_classes.weight, self.occ_classes.bias, None)
         x_occ = _planar_out(plan, x1, 2)
-        plan.conv(x1, w, b, padding=1, out1=x_occ, out1_mode="planar", name="head.occ_classes")
+        plan.conv(x1, w, b, padding=1, out1=x_occ, out1_mode="planar", no_out0=True, name="head.occ_classes")
         L = _lib.lib()
         S = D * H * W
         plan.add(FnOp(lambda st: L.occd_softmax_planar_to_cl(x_occ.data_ptr(), cat.ptr, B, 2, S, cat.cstride,
@@ -102,7 +102,7 @@ class SegmentationHeadCascadeCLS(B200Module):
                       "occd_softmax_planar_to_cl", keep=(x_occ, cat)))
         w, b = fold_bn(self.conv_classes.weight, self.conv_classes.bias, None)
         logits = _planar_out(plan, x1, w.shape[0])
-        plan.conv(cat, w, b, padding=1, out1=logits, out1_mode="planar", name="head.conv_classes")
+        plan.conv(cat, w, b, padding=1, out1=logits, out1_mode="planar", no_out0=True, name="head.conv_classes")
         return logits, x_occ
 
     def forward(self, x_in):
@@ -123,7 +123,7 @@ class SegmentationHeadOccludedCLS(B200Module):
         x1 = _emit_aspp(plan, self, x0, name="occl.aspp")
         w, b = fold_bn(self.occ_classes.weight, self.occ_classes.bias, None)
         x_occ = _planar_out(plan, x1, 2)
-        plan.conv(x1, w, b, padding=1, out1=x_occ, out1_mode="planar", name="occl.occ_classes")
+        plan.conv(x1, w, b, padding=1, out1=x_occ, out1_mode="planar", no_out0=True, name="occl.occ_classes")
         return x_occ
 
     def forward(self, x_in):

@@ -24,9 +24,11 @@ def randomize_bn_(sd_or_module, seed=1):
     return sd
 
 
-def kitti_calib(img_w, img_h):
-    """KITTI-like intrinsics / lidar->camera extrinsics for the two stereo views."""
-    K = np.array([[707.0912, 0, img_w / 2.0], [0, 707.0912, img_h / 2.0], [0, 0, 1]], dtype=np.float64)
+def kitti_calib(img_w, img_h, focal=None):
+    """KITTI-like intrinsics / lidar->camera extrinsics for the two stereo views.
+    focal defaults to 707.0912 px at the 1370-px-wide synthetic image and scales with the image width."""
+    f = 707.0912 * img_w / 1370.0 if focal is None else focal
+    K = np.array([[f, 0, img_w / 2.0], [0, f, img_h / 2.0], [0, 0, 1]], dtype=np.float64)
     T0 = np.array([[0, -1, 0, 0], [0, 0, -1, -0.08], [1, 0, 0, -0.27], [0, 0, 0, 1]], dtype=np.float32)
     T1 = T0.copy()
     T1[0, 3] -= 0.54

@@ -1,0 +1,68 @@
+"""2D UNet (EfficientNet encoder + DecoderBN) and the whole OccDepth.forward on CUDA vs the CPU fp32 oracle."""
+import pytest
+import torch
+
+from oracle import functional as OF
+from oracle import ref_import, synth
+
+pytestmark = pytest.mark.gpu
+
+# stated tolerance for the bf16-operand / fp32-accumulate pipeline, relative to max-abs of the oracle tensor
+TOL_2D = 5e-2
+TOL_E2E = 6e-2
+
+
+def _rel(g, w):
+    return float((g.float().cpu() - w).abs().max() / w.abs().max().clamp_min(1e-6))
+
+
+@pytest.mark.parametrize("backbone,hw", [("tf_efficientnet_b3_ns", (70, 93)), ("tf_efficientnet_b7_ns", (47, 85))])
+def test_unet2d(backbone, hw):
+    from occdepth_b200.models.unet2d import UNet2D
+    torch.manual_seed(0)
+    with ref_import.quiet():
+        m = UNet2D.build(out_feature=32, use_decoder=True, backbone_2d_name=backbone, return_up_feats=1).eval()
+    synth.randomize_bn_(m)
+    sd = {"net_rgb." + k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(1, 3, *hw)
+    with torch.no_grad():
+        want = OF.unet2d(sd, "net_rgb", x, backbone, 1)
+        got = m.cuda()(x.cuda())
+    assert set(got.keys()) == set(want.keys())
+    for k in want:
+        assert got[k].shape == want[k].shape, k
+        assert _rel(got[k], want[k]) <= TOL_2D, (k, _rel(got[k], want[k]))
+
+
+@pytest.mark.parametrize("dataset", ["kitti", "NYU"])
+def test_occdepth_forward_small(dataset):
+    """config-1-like plumbing case: tiny stereo pair, both decoders, CRP on; max-abs-diff of the voxel logits."""
+    from occdepth_b200.models.OccDepth import OccDepth
+    torch.manual_seed(0)
+    if dataset == "kitti":
+        full, ps, ncls, casc = (32, 32, 16), 2, 20, True
+    else:
+        full, ps, ncls, casc = (20, 12, 20), 1, 12, False
+    cfg = synth.occdepth_cfg(dataset=dataset, full_scene_size=full, project_scale=ps, feature=32, feature_2d_oc=32,
+                             n_classes=ncls, cascade_cls=casc, backbone_2d_name="tf_efficientnet_b3_ns")
+    with ref_import.quiet():
+        m = OccDepth(["c"] * ncls, torch.ones(ncls), full_scene_size=full, project_res=["1", "2", "4", "8"],
+                     config=cfg).eval()
+    synth.randomize_bn_(m)
+    H, W = 47, 85
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(1, 2, 3, H, W, generator=g)
+    N = (full[0] // ps) * (full[1] // ps) * (full[2] // ps)
+    pix, fov = synth.random_indices(N, W, H, n_views=2, P=1, seed=5, margin=(10, 6))
+    batch = {"img": img, "projected_pix_%d" % ps: [pix], "fov_mask_%d" % ps: [fov]}
+    ocfg = dict(cfg)
+    ocfg["project_res"] = ["1", "2", "4", "8"]
+    with torch.no_grad():
+        want = OF.occdepth_forward({k: v.clone() for k, v in m.state_dict().items()}, batch, ocfg)
+        got = m.cuda()({"img": img.cuda(), "projected_pix_%d" % ps: [pix], "fov_mask_%d" % ps: [fov]})
+    assert set(got.keys()) == set(want.keys())
+    for k in want:
+        assert got[k].shape == want[k].shape, k
+        assert _rel(got[k], want[k]) <= TOL_E2E, (k, _rel(got[k], want[k]))
+    agree = (got["ssc_logit"].argmax(1).cpu() == want["ssc_logit"].argmax(1)).float().mean()
+    assert agree > 0.9, float(agree)
