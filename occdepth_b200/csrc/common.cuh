@@ -41,6 +41,24 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// activation over 8 values with ONE uniform branch (keeps the epilogues free of per-element switches)
+__device__ __forceinline__ void apply_act8(float* v, int act) {
+  if (act == ACT_NONE) return;
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (act == ACT_LEAKY) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
+  } else if (act == ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
+  }
+}
+
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 // 8 x bf16 <-> 8 x float through one 16-byte vector

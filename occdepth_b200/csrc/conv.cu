@@ -9,23 +9,25 @@
 #include <new>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
 constexpr int kTcThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer (+TMEM alloc), warps 2-5: epilogue
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 24;
 
 struct TcParams {
   ConvEpi epi;
   int n_taps;
   int n_kchunks[OCCD_CONV_MAX_SRC];
-  int tiles_w, tiles_h, tiles_d;
+  int tiles_w, tiles_h, tiles_d, num_m_tiles;
   int TD, TH, TW;
   int stride[3];
   int Cout_pad, N_tile;
-  int stages;
+  int stages, group;
   int a_bytes, b_stride, b_bytes;
   int tmem_cols;
+  long long* trace;  // optional [tile][8] clock64 stamps of CTA 0 (tools/conv_trace.py)
   signed char tap_src[OCCD_CONV_MAX_TAPS];
   short tap_dz[OCCD_CONV_MAX_TAPS], tap_dy[OCCD_CONV_MAX_TAPS], tap_dx[OCCD_CONV_MAX_TAPS];
 };
@@ -35,32 +37,30 @@ __global__ void __launch_bounds__(kTcThreads)
 conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW) {
+  // Persistent, warp-specialised implicit GEMM.  Each CTA walks tiles blockIdx.x, +gridDim.x, ...:
+  //   warp 0 (one lane): TMA producer -- runs ahead across tile boundaries, the smem ring never drains
+  //   warp 1 (one lane): tcgen05.mma issuer, accumulating into one of TWO TMEM accumulators
+  //   warps 2-5        : epilogue of tile j (TMEM -> regs -> global) while the MMAs of tile j+1 run
   constexpr int ROW_BYTES = KC * 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16-byte aligned: round the base up to 1024 (swizzle atom alignment)
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
-  const uint32_t smem_b = smem_a + (uint32_t)p.stages * p.a_bytes;
-  const uint32_t bar_base = smem_b + (uint32_t)p.stages * p.b_stride;  // 8-byte aligned (multiples of 1024)
+  const uint32_t smem_b = smem_a + (uint32_t)(p.stages * p.group) * p.a_bytes;
+  const uint32_t bar_base = smem_b + (uint32_t)(p.stages * p.group) * p.b_stride;  // 8-byte aligned (multiples of 1024)
   const uint32_t full_bar = bar_base;
   const uint32_t empty_bar = bar_base + 8u * kMaxStages;
-  const uint32_t tmem_full_bar = bar_base + 16u * kMaxStages;
-  const uint32_t tmem_slot = tmem_full_bar + 8u;
+  const uint32_t tmem_full_bar = bar_base + 16u * kMaxStages;       // [2]
+  const uint32_t tmem_empty_bar = tmem_full_bar + 16u;              // [2]
+  const uint32_t tmem_slot = tmem_empty_bar + 16u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int n_tiles_n = p.Cout_pad / p.N_tile;
+  const int num_tiles = p.num_m_tiles * n_tiles_n;
 
-  // tile decode
-  int t = blockIdx.x;
-  const int tw = t % p.tiles_w; t /= p.tiles_w;
-  const int th = t % p.tiles_h; t /= p.tiles_h;
-  const int td = t % p.tiles_d; t /= p.tiles_d;
-  const int b = t;
-  const int od0 = td * p.TD, oh0 = th * p.TH, ow0 = tw * p.TW;
-  const int n0 = blockIdx.y * p.N_tile;
-
-  int total_iters = 0;
-  for (int i = 0; i < p.n_taps; ++i) total_iters += p.n_kchunks[p.tap_src[i]];
+  int iters_per_tile = 0;
+  for (int i = 0; i < p.n_taps; ++i) iters_per_tile += p.n_kchunks[p.tap_src[i]];
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA0);
@@ -69,7 +69,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       tc::mbar_init(full_bar + 8u * s, 1);
       tc::mbar_init(empty_bar + 8u * s, 1);
     }
-    tc::mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(tmem_full_bar + 8u * a, 1);
+      tc::mbar_init(tmem_empty_bar + 8u * a, 128);  // every epilogue thread arrives
+    }
     tc::fence_barrier_init();
   }
   if (warp == 1) {
@@ -81,48 +84,86 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   tc::fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t acc_stride = (uint32_t)p.tmem_cols >> 1;  // column offset of the second accumulator
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
       const CUtensorMap* maps[3] = {&tmA0, &tmA1, &tmA2};
-      int it = 0;
-      for (int tp = 0; tp < p.n_taps; ++tp) {
-        const int src = p.tap_src[tp];
-        const int cw = ow0 * p.stride[2] + p.tap_dx[tp];
-        const int ch = oh0 * p.stride[1] + p.tap_dy[tp];
-        const int cd = od0 * p.stride[0] + p.tap_dz[tp];
-        const int wrow = tp * p.Cout_pad + n0;
-        for (int kc = 0; kc < p.n_kchunks[src]; ++kc, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          tc::mbar_wait(empty_bar + 8u * s, ph ^ 1u);
-          tc::mbar_expect_tx(full_bar + 8u * s, (uint32_t)(p.a_bytes + p.b_bytes));
-          tc::tma_load_5d(smem_a + (uint32_t)s * p.a_bytes, maps[src], full_bar + 8u * s, kc * KC, cw, ch, cd, b);
-          tc::tma_load_2d(smem_b + (uint32_t)s * p.b_stride, &tmW, full_bar + 8u * s, kc * KC, wrow);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % n_tiles_n;
+        int t = tile / n_tiles_n;
+        const int tw = t % p.tiles_w; t /= p.tiles_w;
+        const int th = t % p.tiles_h; t /= p.tiles_h;
+        const int td = t % p.tiles_d; t /= p.tiles_d;
+        const int b = t;
+        const int iw0 = tw * p.TW * p.stride[2], ih0 = th * p.TH * p.stride[1], id0 = td * p.TD * p.stride[0];
+        const int n0 = nt * p.N_tile;
+        // items (tap, k-chunk) are loaded in groups of p.group per pipeline stage: one barrier hand-off per group
+        int g = 0;
+        int remaining = iters_per_tile;
+        const int jt = (tile - blockIdx.x) / gridDim.x;
+        if (p.trace && blockIdx.x == 0 && jt < 64) p.trace[jt * 8 + 0] = clock64();
+        for (int tp = 0; tp < p.n_taps; ++tp) {
+          const int src = p.tap_src[tp];
+          const int cw = iw0 + p.tap_dx[tp], ch = ih0 + p.tap_dy[tp], cd = id0 + p.tap_dz[tp];
+          const int wrow = tp * p.Cout_pad + n0;
+          const int nk = p.n_kchunks[src];
+          for (int kc = 0; kc < nk; ++kc) {
+            if (g == 0) {
+              const int cnt = remaining < p.group ? remaining : p.group;
+              tc::mbar_wait(empty_bar + 8u * s, ph ^ 1u);
+              tc::mbar_expect_tx(full_bar + 8u * s, (uint32_t)(cnt * (p.a_bytes + p.b_bytes)));
+            }
+            const uint32_t sa = smem_a + (uint32_t)(s * p.group + g) * p.a_bytes;
+            const uint32_t sb = smem_b + (uint32_t)(s * p.group + g) * p.b_stride;
+            tc::tma_load_5d(sa, maps[src], full_bar + 8u * s, kc * KC, cw, ch, cd, b);
+            tc::tma_load_2d(sb, &tmW, full_bar + 8u * s, kc * KC, wrow);
+            --remaining;
+            if (++g == p.group || remaining == 0) {
+              g = 0;
+              if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
+          }
         }
+        if (p.trace && blockIdx.x == 0 && jt < 64) p.trace[jt * 8 + 1] = clock64();
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc = tc::make_idesc_bf16(128, p.N_tile);
-      for (int it = 0; it < total_iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        tc::mbar_wait(full_bar + 8u * s, ph);
+      int s = 0;
+      uint32_t ph = 0;
+      int j = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+        const uint32_t acc = (uint32_t)j & 1u;
+        tc::mbar_wait(tmem_empty_bar + 8u * acc, (((uint32_t)j >> 1) & 1u) ^ 1u);  // epilogue drained this buffer
         tc::fence_after_sync();
-        const uint32_t a_addr = smem_a + (uint32_t)s * p.a_bytes;
-        const uint32_t b_addr = smem_b + (uint32_t)s * p.b_stride;
+        if (p.trace && blockIdx.x == 0 && j < 64) p.trace[j * 8 + 2] = clock64();
+        const uint32_t d_tmem = tmem_base + acc * acc_stride;
+        for (int it = 0; it < iters_per_tile;) {
+          tc::mbar_wait(full_bar + 8u * s, ph);
+          tc::fence_after_sync();
+          const int cnt = (iters_per_tile - it) < p.group ? (iters_per_tile - it) : p.group;
+          for (int g = 0; g < cnt; ++g, ++it) {
+            const uint32_t a_addr = smem_a + (uint32_t)(s * p.group + g) * p.a_bytes;
+            const uint32_t b_addr = smem_b + (uint32_t)(s * p.group + g) * p.b_stride;
 #pragma unroll
-        for (int k = 0; k < KC / 16; ++k) {
-          const uint64_t da = tc::make_sdesc(a_addr + k * 32, ROW_BYTES);
-          const uint64_t db = tc::make_sdesc(b_addr + k * 32, ROW_BYTES);
-          tc::mma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < KC / 16; ++k) {
+              const uint64_t da = tc::make_sdesc(a_addr + k * 32, ROW_BYTES);
+              const uint64_t db = tc::make_sdesc(b_addr + k * 32, ROW_BYTES);
+              tc::mma_bf16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          tc::mma_commit(empty_bar + 8u * s);  // frees the smem stage when these MMAs retire
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        tc::mma_commit(empty_bar + 8u * s);  // frees the smem stage when these MMAs retire
+        tc::mma_commit(tmem_full_bar + 8u * acc);  // accumulator complete
+        if (p.trace && blockIdx.x == 0 && j < 64) p.trace[j * 8 + 3] = clock64();
       }
-      tc::mma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
@@ -131,15 +172,31 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
     const int rw = row % p.TW;
     const int rh = (row / p.TW) % p.TH;
     const int rd = row / (p.TW * p.TH);
-    const int od = od0 + rd, oh = oh0 + rh, ow = ow0 + rw;
-    const bool valid = od < p.epi.OD && oh < p.epi.OH && ow < p.epi.OW;
-    tc::mbar_wait(tmem_full_bar, 0);
-    tc::fence_after_sync();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
-      float v[16];
-      tc::tmem_ld16(taddr + (uint32_t)c0, v);
-      if (valid) conv_epilogue_row<16>(p.epi, b, od, oh, ow, n0 + c0, v);
+    int j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      const int nt = tile % n_tiles_n;
+      int t = tile / n_tiles_n;
+      const int tw = t % p.tiles_w; t /= p.tiles_w;
+      const int th = t % p.tiles_h; t /= p.tiles_h;
+      const int td = t % p.tiles_d; t /= p.tiles_d;
+      const int b = t;
+      const int od = td * p.TD + rd, oh = th * p.TH + rh, ow = tw * p.TW + rw;
+      const bool valid = od < p.epi.OD && oh < p.epi.OH && ow < p.epi.OW;
+      const int n0 = nt * p.N_tile;
+      const uint32_t acc = (uint32_t)j & 1u;
+      if (p.trace && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) p.trace[j * 8 + 4] = clock64();
+      tc::mbar_wait(tmem_full_bar + 8u * acc, ((uint32_t)j >> 1) & 1u);
+      tc::fence_after_sync();
+      if (p.trace && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) p.trace[j * 8 + 5] = clock64();
+      const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(taddr + (uint32_t)c0, v);
+        if (valid) conv_epilogue_row<16>(p.epi, b, od, oh, ow, n0 + c0, v);
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive(tmem_empty_bar + 8u * acc);  // this thread's TMEM reads of the buffer are done
+      if (p.trace && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) p.trace[j * 8 + 6] = clock64();
     }
   }
   tc::fence_before_sync();
@@ -348,14 +405,22 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
   }
   // tile box (TD,TH,TW), product 128, minimal padded volume; ties -> widest TW
   {
+    // minimal padded volume, but a wide innermost extent (long contiguous TMA runs, coalesced stores) wins
+    // whenever it costs < 4% extra positions
     long long best = -1;
-    for (int tw = 128; tw >= 1; tw >>= 1)
-      for (int th = 128 / tw; th >= 1; th >>= 1) {
-        const int tdd = 128 / (tw * th);
-        if (tw * d->stride[2] > 256 || th * d->stride[1] > 256 || tdd * d->stride[0] > 256) continue;
-        const long long vol = (long long)round_up(d->OW, tw) * round_up(d->OH, th) * round_up(d->OD, tdd);
-        if (best < 0 || vol < best) { best = vol; t.TW = tw; t.TH = th; t.TD = tdd; }
-      }
+    for (int pass = 0; pass < 2; ++pass)
+      for (int tw = 128; tw >= 1; tw >>= 1)
+        for (int th = 128 / tw; th >= 1; th >>= 1) {
+          const int tdd = 128 / (tw * th);
+          if (tw * d->stride[2] > 256 || th * d->stride[1] > 256 || tdd * d->stride[0] > 256) continue;
+          const long long vol = (long long)round_up(d->OW, tw) * round_up(d->OH, th) * round_up(d->OD, tdd);
+          if (pass == 0) {
+            if (best < 0 || vol < best) best = vol;
+          } else if (vol * 100 <= best * 104) {
+            t.TW = tw; t.TH = th; t.TD = tdd;
+            pass = 2; tw = 0; break;  // first hit in (widest TW, tallest TH) order
+          }
+        }
   }
   t.tiles_w = (d->OW + t.TW - 1) / t.TW; t.tiles_h = (d->OH + t.TH - 1) / t.TH; t.tiles_d = (d->OD + t.TD - 1) / t.TD;
   // N tile: largest divisor of Cout_pad that is a multiple of 16 and <= 256
@@ -365,26 +430,50 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
     if (d->Cout_pad % n == 0) t.N_tile = n;
   t.tmem_cols = 32;
   while (t.tmem_cols < t.N_tile) t.tmem_cols *= 2;
+  { const char* e = getenv("OCCD_CONV_TRACE_PTR"); t.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
+  t.tmem_cols *= 2;  // two accumulators: the epilogue of tile j overlaps the MMAs of tile j+1
   t.a_bytes = 128 * KC * 2;
   t.b_bytes = t.N_tile * KC * 2;
   t.b_stride = round_up(t.b_bytes, 1024);
   const int stage_bytes = t.a_bytes + t.b_stride;
   int total_iters = 0;
   for (int i = 0; i < d->n_taps; ++i) total_iters += t.n_kchunks[d->taps[i].src];
-  int budget = (4 * stage_bytes <= 100 * 1024) ? 100 * 1024 : 200 * 1024;
-  int stages = budget / stage_bytes;
+  const int budget = 200 * 1024;  // persistent kernel: one CTA per SM owns the shared memory
+  // (tap, k-chunk) items per pipeline stage: the single-thread producer/MMA hand-off costs ~0.25 us, so a stage
+  // must carry >= ~512 tensor-pipe cycles of work (or up to 9 items) while leaving >= 3 stages in flight
+  const int mma_cycles_per_item = (KC / 16) * (128 * t.N_tile / 256);
+  int group = (512 + mma_cycles_per_item - 1) / mma_cycles_per_item;
+  if (group > 9) group = 9;
+  if (group > total_iters) group = total_iters;
+  while (group > 1 && 3 * group * stage_bytes > budget) --group;
+  t.group = group;
+  int stages = budget / (group * stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > total_iters) stages = total_iters;
+  const int groups_per_tile = (total_iters + group - 1) / group;
+  if (stages > 2 * groups_per_tile) stages = 2 * groups_per_tile;
   if (stages < 1) stages = 1;
   t.stages = stages;
-  pl->smem = (size_t)stages * stage_bytes + 16 * kMaxStages + 16 + 1024;  // + barriers + alignment slack
-  const long long gx = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w;
-  if (gx > 2147483647LL || d->Cout_pad / t.N_tile > 65535) {
+  pl->smem = (size_t)stages * group * stage_bytes + 16 * kMaxStages + 64 + 1024;  // + barriers + alignment slack
+  const long long m_tiles = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w;
+  const long long all_tiles = m_tiles * (d->Cout_pad / t.N_tile);
+  if (all_tiles > 2147483647LL) {
     delete pl;
-    occd_set_last_error("occd_conv_plan_create: grid too large");
+    occd_set_last_error("occd_conv_plan_create: too many tiles");
     return OCCD_ERR_UNSUPPORTED;
   }
-  pl->grid = dim3((unsigned)gx, (unsigned)(d->Cout_pad / t.N_tile));
+  t.num_m_tiles = (int)m_tiles;
+  {
+    static int n_sms = 0;
+    if (n_sms == 0) {
+      int dev = 0;
+      cudaDeviceProp prop;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
+        n_sms = prop.multiProcessorCount;
+      else
+        n_sms = 148;
+    }
+    pl->grid = dim3((unsigned)(all_tiles < n_sms ? all_tiles : n_sms));
+  }
 
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
@@ -448,7 +537,7 @@ extern "C" int occd_conv_plan_info(const occd_conv_plan* pl, int* info) {
     return OCCD_OK;
   }
   info[0] = pl->tc.TD; info[1] = pl->tc.TH; info[2] = pl->tc.TW; info[3] = pl->tc.N_tile;
-  info[4] = pl->kc; info[5] = pl->tc.stages; info[6] = (int)pl->grid.x; info[7] = (int)pl->grid.y;
+  info[4] = pl->kc; info[5] = pl->tc.stages * 100 + pl->tc.group; info[6] = (int)pl->grid.x; info[7] = pl->tc.num_m_tiles * (pl->tc.Cout_pad / pl->tc.N_tile);
   return OCCD_OK;
 }
 

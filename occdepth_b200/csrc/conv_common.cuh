@@ -66,8 +66,7 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvEpi& e, int b, int o
         if (n + i < e.Cout) o[(long long)i * S] = vv[i];
     }
     if (e.out0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) vv[i] = apply_act(vv[i], e.act);
+      apply_act8(vv, e.act);
       if (e.res2 && e.res2_post) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) vv[i] += r2[i];

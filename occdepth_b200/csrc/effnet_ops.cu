@@ -54,8 +54,7 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
           for (int i = 0; i < 8; ++i) acc[i] = fmaf(x[i], wv[i], acc[i]);
         }
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = apply_act(acc[i], act);
+      apply_act8(acc, act);
       const uint4 packed = pack8(acc);
       *reinterpret_cast<uint4*>(out + (((long long)b * OH + oy) * OW + ox) * cs_out + c0) = packed;
       if (pool) {

@@ -226,6 +226,7 @@ class Plan:
         self.device = device
         self.ops = []
         self.flops = 0
+        self.graph = None
 
     def alloc(self, B, D, H, W, C_):
         return CL.alloc(B, D, H, W, C_, self.device)
@@ -294,9 +295,38 @@ class Plan:
         return out
 
     def run(self, stream=None):
+        """Replays the launches on the current stream (through a captured CUDA graph when enabled)."""
+        if stream is None and self.graph is not None:
+            self.graph.replay()
+            return
         st = _lib.stream_ptr() if stream is None else stream
         for op in self.ops:
             op.run(st)
+
+    def capture(self):
+        """Capture the launch sequence into a CUDA graph (buffers are static, so replay is valid)."""
+        self.graph = None
+        self.run()                      # warm-up outside capture (lazy module loading, func attributes)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            st = _lib.stream_ptr()
+            for op in self.ops:
+                op.run(st)
+        self.graph = g
+        return g
+
+    def profile(self):
+        """Per-launch device times (CUDA events on the launching stream); returns [(name, ms, flops)]."""
+        st = _lib.stream_ptr()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.ops) + 1)]
+        evs[0].record()
+        for i, op in enumerate(self.ops):
+            op.run(st)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        return [(getattr(op, "name", "?"), evs[i].elapsed_time(evs[i + 1]), getattr(op, "flops", 0))
+                for i, op in enumerate(self.ops)]
 
 
 class FnOp:

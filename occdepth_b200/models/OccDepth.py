@@ -6,6 +6,8 @@ is a single fused kernel writing the channels-last voxel grid the 3D UNet consum
 in the reference's NCDHW fp32 layout by the last convolution's epilogue.
 Training (`step`, losses, optimisers; OccDepth.py:378-600) is out of scope of this package.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -139,6 +141,12 @@ class OccDepth(_Base, B200Module):
                                            prior=pr, scale_const=100.0, stream=st), 0)[1],
                           "sfa_lift", keep=(feats, pix, fov, out_b)))
         out = self.net_3d_decoder.emit(plan, x3d)
+        if os.environ.get("OCCDEPTH_CUDA_GRAPH", "1") == "1":
+            try:
+                plan.capture()
+            except Exception as e:  # noqa: BLE001 -- same kernels either way; only the launch mechanism differs
+                print("WARNING: CUDA graph capture failed (%r); launching kernels individually" % (e,))
+                plan.graph = None
         return plan, img, pix, fov, out
 
     def forward(self, batch):
@@ -171,7 +179,8 @@ class OccDepth(_Base, B200Module):
             self.flosp_depth.stage_inputs(batch, dev)
         plan.run()
         res = _to_planar(out, False)
-        return res
+        # tensors written directly by kernels live in plan-owned static buffers: hand out copies
+        return {k: (v.clone() if isinstance(out[k], torch.Tensor) else v) for k, v in res.items()}
 
     def step(self, *a, **k):
         raise NotImplementedError("occdepth_b200 implements OccDepth.forward only (training is out of scope)")
