@@ -170,9 +170,15 @@ int occd_copy_channels(const void* in, void* out, long long positions, int C, in
 int occd_dwconv2d_fwd(const void* in, const float* w, const float* bias, void* out, float* pool, int B, int H,
                       int W, int OH, int OW, int C, int cs_in, int cs_out, int K, int stride, int pad_top,
                       int pad_left, int act, void* stream);
-/* gate[b][c] = sigmoid(W2 silu(W1 (pool[b]/HW) + b1) + b2); zeroes pool. w1 [R][C], w2t [R][C]   */
+/* gate[b][c] = sigmoid(W2 silu(W1 (pool[b]/HW) + b1) + b2); zeroes pool. w1 [R][C], w2t [R][C];  */
+/* `gate` must hold B*C + B*R floats (the hidden layer is staged behind the gates)               */
 int occd_se_gate_fwd(float* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
                      const float* b2, float* gate, int B, int C, int R, void* stream);
+/* fused single-image path: squeeze-excite MLP + gate folded into the projection weights          */
+/* wout[row][k] = bf16(master[row][k] * gate[k]); hidden: R floats of scratch; zeroes pool        */
+int occd_se_gate_fold_fwd(float* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
+                          const float* b2, float* hidden, const float* master, void* wout, int C, int R,
+                          int rows, int Kpad, void* stream);
 /* out[row][k] = bf16(master[row][k] * gate[k]): folds x * gate into the next 1x1 conv's weights   */
 int occd_scale_weights(const float* master, const float* gate, void* out, int rows, int Kpad, int C,
                        void* stream);

@@ -13,7 +13,7 @@
 
 namespace {
 
-constexpr int kTcThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer (+TMEM alloc), warps 2-5: epilogue
+constexpr int kTcThreads = 320;  // warp 0: TMA producer, warp 1: MMA issuer (+TMEM alloc), warps 2-5 / 6-9: epilogue groups
 constexpr int kMaxStages = 24;
 
 struct TcParams {
@@ -40,7 +40,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   // Persistent, warp-specialised implicit GEMM.  Each CTA walks tiles blockIdx.x, +gridDim.x, ...:
   //   warp 0 (one lane): TMA producer -- runs ahead across tile boundaries, the smem ring never drains
   //   warp 1 (one lane): tcgen05.mma issuer, accumulating into one of TWO TMEM accumulators
-  //   warps 2-5        : epilogue of tile j (TMEM -> regs -> global) while the MMAs of tile j+1 run
+  //   warps 2-5 / 6-9  : two epilogue groups (even / odd tiles, one TMEM accumulator each): TMEM -> regs ->
+  //                      global while the MMAs of the following tiles run
   constexpr int ROW_BYTES = KC * 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16-byte aligned: round the base up to 1024 (swizzle atom alignment)
@@ -167,13 +168,16 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;     // epilogue group == accumulator index
     const int row = q * 32 + lane;
     const int rw = row % p.TW;
     const int rh = (row / p.TW) % p.TH;
     const int rd = row / (p.TW * p.TH);
+    const bool tracer = p.trace && blockIdx.x == 0 && threadIdx.x == 64;
     int j = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      if ((j & 1) != grp) continue;
       const int nt = tile % n_tiles_n;
       int t = tile / n_tiles_n;
       const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -183,20 +187,40 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       const int od = td * p.TD + rd, oh = th * p.TH + rh, ow = tw * p.TW + rw;
       const bool valid = od < p.epi.OD && oh < p.epi.OH && ow < p.epi.OW;
       const int n0 = nt * p.N_tile;
-      const uint32_t acc = (uint32_t)j & 1u;
-      if (p.trace && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) p.trace[j * 8 + 4] = clock64();
+      const uint32_t acc = (uint32_t)grp;
+      if (tracer && j < 64) p.trace[j * 8 + 4] = clock64();
       tc::mbar_wait(tmem_full_bar + 8u * acc, ((uint32_t)j >> 1) & 1u);
       tc::fence_after_sync();
-      if (p.trace && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) p.trace[j * 8 + 5] = clock64();
+      if (tracer && j < 64) p.trace[j * 8 + 5] = clock64();
       const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
-        float v[16];
-        tc::tmem_ld16(taddr + (uint32_t)c0, v);
-        if (valid) conv_epilogue_row<16>(p.epi, b, od, oh, ow, n0 + c0, v);
+      // software-pipelined: the tcgen05.ld of the next 16 columns is in flight while these 16 are stored
+      uint32_t ra[16], rb[16];
+      tc::tmem_ld16_issue(taddr, ra);
+      tc::tmem_ld_wait16(ra);
+      for (int c0 = 0; c0 < p.N_tile; c0 += 32) {
+        const bool has_b = c0 + 16 < p.N_tile;
+        if (has_b) tc::tmem_ld16_issue(taddr + (uint32_t)(c0 + 16), rb);
+        if (valid) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]);
+          conv_epilogue_row<16>(p.epi, b, od, oh, ow, n0 + c0, v);
+        }
+        if (has_b) {
+          tc::tmem_ld_wait16(rb);
+          if (c0 + 32 < p.N_tile) tc::tmem_ld16_issue(taddr + (uint32_t)(c0 + 32), ra);
+          if (valid) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]);
+            conv_epilogue_row<16>(p.epi, b, od, oh, ow, n0 + c0 + 16, v);
+          }
+          if (c0 + 32 < p.N_tile) tc::tmem_ld_wait16(ra);
+        }
       }
       tc::fence_before_sync();
       tc::mbar_arrive(tmem_empty_bar + 8u * acc);  // this thread's TMEM reads of the buffer are done
-      if (p.trace && blockIdx.x == 0 && j < 64 && threadIdx.x == 64) p.trace[j * 8 + 6] = clock64();
+      if (tracer && j < 64) p.trace[j * 8 + 6] = clock64();
     }
   }
   tc::fence_before_sync();

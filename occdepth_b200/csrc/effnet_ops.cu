@@ -10,19 +10,25 @@
 
 namespace {
 
-constexpr int kPixPerThread = 8;
+constexpr int kDwThreads = 256;
+constexpr int kDwPasses = 4;  // pixels per thread
 
-template <int K>
-__global__ void __launch_bounds__(256)
+// blockDim = (CVB, 256/CVB): threadIdx.x owns one 8-channel vector (coalesced CVB*16-byte segments),
+// threadIdx.y walks output pixels of one image row.  CVB in {8,16,32} is picked per layer so that narrow
+// layers (C = 64) keep every lane busy.  The squeeze (global-average-pool sum) is accumulated in registers,
+// reduced across threadIdx.y in shared memory and flushed with one atomicAdd per channel per block.
+template <int K, int CVB>
+__global__ void __launch_bounds__(kDwThreads)
 dwconv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
               __nv_bfloat16* __restrict__ out, float* __restrict__ pool, int H, int W, int OH, int OW, int C,
               int cs_in, int cs_out, int stride, int pad_top, int pad_left, int act) {
-  __shared__ float red[8][32 * 8 + 1];
-  const int cv = blockIdx.x * 32 + threadIdx.x;  // 8-channel vector index
-  const int c0 = cv * 8;
+  constexpr int PY = kDwThreads / CVB;
+  __shared__ float red[PY][CVB * 8 + 1];
+  const int tx = threadIdx.x % CVB, ty = threadIdx.x / CVB;
+  const int c0 = (blockIdx.y * CVB + tx) * 8;
+  const bool cvalid = c0 < C;
   const int b = blockIdx.z / OH;
   const int oy = blockIdx.z % OH;
-  const bool cvalid = c0 < C;
   float psum[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) psum[i] = 0.f;
@@ -30,9 +36,11 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
     float bv[8];
     *reinterpret_cast<float4*>(bv) = __ldg(reinterpret_cast<const float4*>(bias + c0));
     *reinterpret_cast<float4*>(bv + 4) = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
-    const __nv_bfloat16* inb = in + (long long)b * H * W * cs_in;
-    for (int j = 0; j < kPixPerThread; ++j) {
-      const int ox = blockIdx.y * (8 * kPixPerThread) + j * 8 + threadIdx.y;
+    const __nv_bfloat16* inb = in + (long long)b * H * W * cs_in + c0;
+    const float* wc = w + c0;
+#pragma unroll 1
+    for (int j = 0; j < kDwPasses; ++j) {
+      const int ox = (blockIdx.x * kDwPasses + j) * PY + ty;
       if (ox >= OW) break;
       float acc[8];
 #pragma unroll
@@ -46,8 +54,8 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
           const int ix = ox * stride - pad_left + kx;
           if (ix < 0 || ix >= W) continue;
           float x[8], wv[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(inb + ((long long)iy * W + ix) * cs_in + c0)), x);
-          const float* wp = w + (long long)(ky * K + kx) * C + c0;
+          unpack8(__ldg(reinterpret_cast<const uint4*>(inb + ((long long)iy * W + ix) * cs_in)), x);
+          const float* wp = wc + (long long)(ky * K + kx) * C;
           *reinterpret_cast<float4*>(wv) = __ldg(reinterpret_cast<const float4*>(wp));
           *reinterpret_cast<float4*>(wv + 4) = __ldg(reinterpret_cast<const float4*>(wp + 4));
 #pragma unroll
@@ -68,59 +76,95 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
   }
   if (pool) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) red[threadIdx.y][threadIdx.x * 8 + i] = psum[i];
+    for (int i = 0; i < 8; ++i) red[ty][tx * 8 + i] = psum[i];
     __syncthreads();
-    if (threadIdx.y == 0 && cvalid) {
+    if (ty == 0 && cvalid) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float s = 0.f;
 #pragma unroll
-        for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x * 8 + i];
+        for (int y = 0; y < PY; ++y) s += red[y][tx * 8 + i];
         atomicAdd(pool + (long long)b * C + c0 + i, s);
       }
     }
   }
 }
 
-// one block per image: gate = sigmoid(W2 silu(W1 mean + b1) + b2); clears the pool for the next forward
-__global__ void __launch_bounds__(512)
-se_gate_kernel(float* __restrict__ pool, float inv_hw, const float* __restrict__ w1, const float* __restrict__ b1,
-               const float* __restrict__ w2t, const float* __restrict__ b2, float* __restrict__ gate, int C, int R) {
-  extern __shared__ float sm[];  // mean[C], hidden[R]
-  float* mean = sm;
-  float* hid = sm + C;
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    mean[c] = pool[(long long)b * C + c] * inv_hw;
-    pool[(long long)b * C + c] = 0.f;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int r = warp; r < R; r += nwarps) {
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(w1[(long long)r * C + c], mean[c], s);
+// squeeze-excite MLP in two wide launches (the FC weights are MBs for the late stages: one block cannot stream them)
+//   hidden[b][r] = silu(b1[r] + <w1[r], pool[b] / HW>)          grid (R, B), one block per hidden unit
+//   gate[b][c]   = sigmoid(b2[c] + sum_r w2t[r][c] hidden[b][r]) grid (ceil(C/256), B); also clears pool
+__global__ void __launch_bounds__(128)
+se_fc1_kernel(const float* __restrict__ pool, float inv_hw, const float* __restrict__ w1,
+              const float* __restrict__ b1, float* __restrict__ hidden, int C, int R) {
+  __shared__ float red[4];
+  const int r = blockIdx.x, b = blockIdx.y;
+  const float* wr = w1 + (long long)r * C;
+  const float* pb = pool + (long long)b * C;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += 128) s = fmaf(__ldg(wr + c), pb[c], s);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-      s += b1[r];
-      hid[r] = s / (1.f + __expf(-s));
-    }
-  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = b2[c];
-    for (int r = 0; r < R; ++r) s = fmaf(w2t[(long long)r * C + c], hid[r], s);
-    gate[(long long)b * C + c] = 1.f / (1.f + __expf(-s));
+  if (threadIdx.x == 0) {
+    const float v = (red[0] + red[1] + red[2] + red[3]) * inv_hw + b1[r];
+    hidden[(long long)b * R + r] = __fdividef(v, 1.f + __expf(-v));
   }
+}
+
+__global__ void __launch_bounds__(256)
+se_fc2_kernel(float* __restrict__ pool, const float* __restrict__ hidden, const float* __restrict__ w2t,
+              const float* __restrict__ b2, float* __restrict__ gate, int C, int R) {
+  extern __shared__ float hid[];
+  const int b = blockIdx.y;
+  for (int r = threadIdx.x; r < R; r += 256) hid[r] = hidden[(long long)b * R + r];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float s = b2[c];
+  for (int r = 0; r < R; ++r) s = fmaf(__ldg(w2t + (long long)r * C + c), hid[r], s);
+  gate[(long long)b * C + c] = __fdividef(1.f, 1.f + __expf(-s));
+  pool[(long long)b * C + c] = 0.f;  // ready for the next forward
+}
+
+// fused: gate for a strip of 256 input channels (second FC + sigmoid), then that strip of the projection
+// weights scaled and packed to bf16 for `rows_per_block` output rows.  grid (ceil(Kpad/256), row blocks)
+__global__ void __launch_bounds__(256)
+se_fc2_fold_kernel(float* __restrict__ pool, const float* __restrict__ hidden, const float* __restrict__ w2t,
+                   const float* __restrict__ b2, const float* __restrict__ master, __nv_bfloat16* __restrict__ out,
+                   int C, int R, int rows, int Kpad, int rows_per_block) {
+  extern __shared__ float hid[];
+  for (int r = threadIdx.x; r < R; r += 256) hid[r] = hidden[r];
+  __syncthreads();
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= Kpad) return;
+  float g = 0.f;
+  if (k < C) {
+    float s = b2[k];
+    for (int r = 0; r < R; ++r) s = fmaf(__ldg(w2t + (long long)r * C + k), hid[r], s);
+    g = __fdividef(1.f, 1.f + __expf(-s));
+    if (blockIdx.y == 0) pool[k] = 0.f;  // ready for the next forward
+  }
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  for (int r = r0; r < r1; ++r)
+    out[(long long)r * Kpad + k] = __float2bfloat16_rn(__ldg(master + (long long)r * Kpad + k) * g);
 }
 
 // out[row][k] = bf16(master[row][k] * gate[k])  (k < C), rows = Cout_pad, row length Kpad
 __global__ void scale_weights_kernel(const float* __restrict__ master, const float* __restrict__ gate,
                                      __nv_bfloat16* __restrict__ out, int rows, int Kpad, int C) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;  // Kpad % 8 == 0
   if (i >= (long long)rows * Kpad) return;
   const int k = (int)(i % Kpad);
-  out[i] = __float2bfloat16_rn(k < C ? master[i] * gate[k] : 0.f);
+  float m[8], g[8];
+  *reinterpret_cast<float4*>(m) = __ldg(reinterpret_cast<const float4*>(master + i));
+  *reinterpret_cast<float4*>(m + 4) = __ldg(reinterpret_cast<const float4*>(master + i + 4));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = (k + j < C) ? gate[k + j] : 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] *= g[j];
+  *reinterpret_cast<uint4*>(out + i) = pack8(m);
 }
 
 // bilinear, align_corners=True; in [B][h][w][cs_in] -> out [B][OH][OW][cs_out] (channel windows), C % 8 == 0 padded
@@ -161,17 +205,25 @@ extern "C" int occd_dwconv2d_fwd(const void* in, const float* w, const float* bi
   OCCD_CHECK_ARG(C > 0 && C % 8 == 0 && cs_in % 8 == 0 && cs_out % 8 == 0 && cs_in >= C && cs_out >= C,
                  "occd_dwconv2d_fwd: channels must be a multiple of 8");
   OCCD_CHECK_ARG((long long)B * OH <= 65535, "occd_dwconv2d_fwd: B*OH too large");
-  dim3 grid((C / 8 + 31) / 32, (OW + 8 * kPixPerThread - 1) / (8 * kPixPerThread), B * OH), block(32, 8);
+  OCCD_CHECK_ARG(K == 3 || K == 5, "occd_dwconv2d_fwd: kernel size must be 3 or 5");
+  const int CV = C / 8;
+  // lanes per pixel: the candidate in {8,16,32} with the least padding (ties -> widest)
+  int cvb = 32, best = -1;
+  for (int c = 32; c >= 8; c >>= 1) {
+    const int padded = (CV + c - 1) / c * c;
+    if (best < 0 || padded < best) { best = padded; cvb = c; }
+  }
+  const int py = kDwThreads / cvb;
+  dim3 grid((OW + py * kDwPasses - 1) / (py * kDwPasses), (CV + cvb - 1) / cvb, B * OH), block(kDwThreads);
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* i = (const __nv_bfloat16*)in;
   __nv_bfloat16* o = (__nv_bfloat16*)out;
-  if (K == 3)
-    dwconv_kernel<3><<<grid, block, 0, st>>>(i, w, bias, o, pool, H, W, OH, OW, C, cs_in, cs_out, stride, pad_top,
-                                              pad_left, act);
-  else if (K == 5)
-    dwconv_kernel<5><<<grid, block, 0, st>>>(i, w, bias, o, pool, H, W, OH, OW, C, cs_in, cs_out, stride, pad_top,
-                                              pad_left, act);
-  else { occd_set_last_error("occd_dwconv2d_fwd: kernel size must be 3 or 5"); return OCCD_ERR_UNSUPPORTED; }
+#define OCCD_DW(K_, CVB_)                                                                                        \
+  dwconv_kernel<K_, CVB_><<<grid, block, 0, st>>>(i, w, bias, o, pool, H, W, OH, OW, C, cs_in, cs_out, stride,   \
+                                                   pad_top, pad_left, act)
+  if (K == 3) { if (cvb == 8) OCCD_DW(3, 8); else if (cvb == 16) OCCD_DW(3, 16); else OCCD_DW(3, 32); }
+  else        { if (cvb == 8) OCCD_DW(5, 8); else if (cvb == 16) OCCD_DW(5, 16); else OCCD_DW(5, 32); }
+#undef OCCD_DW
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
@@ -179,9 +231,13 @@ extern "C" int occd_dwconv2d_fwd(const void* in, const float* w, const float* bi
 extern "C" int occd_se_gate_fwd(float* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
                                 const float* b2, float* gate, int B, int C, int R, void* stream) {
   OCCD_CHECK_ARG(pool && w1 && b1 && w2t && b2 && gate && B > 0 && C > 0 && R > 0, "occd_se_gate_fwd: args");
-  const size_t smem = (size_t)(C + R) * sizeof(float);
-  OCCD_CHECK_ARG(smem <= 48 * 1024, "occd_se_gate_fwd: C + R too large");
-  se_gate_kernel<<<B, 512, smem, (cudaStream_t)stream>>>(pool, inv_hw, w1, b1, w2t, b2, gate, C, R);
+  OCCD_CHECK_ARG(R <= 8192 && B <= 65535, "occd_se_gate_fwd: R/B too large");
+  // hidden activations live right behind the gate: gate buffer must hold B*C + B*R floats
+  float* hidden = gate + (long long)B * C;
+  se_fc1_kernel<<<dim3(R, B), 128, 0, (cudaStream_t)stream>>>(pool, inv_hw, w1, b1, hidden, C, R);
+  OCCD_CHECK_LAUNCH();
+  se_fc2_kernel<<<dim3((C + 255) / 256, B), 256, R * sizeof(float), (cudaStream_t)stream>>>(pool, hidden, w2t, b2,
+                                                                                             gate, C, R);
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
@@ -189,7 +245,8 @@ extern "C" int occd_se_gate_fwd(float* pool, float inv_hw, const float* w1, cons
 extern "C" int occd_scale_weights(const float* master, const float* gate, void* out, int rows, int Kpad, int C,
                                   void* stream) {
   OCCD_CHECK_ARG(master && gate && out && rows > 0 && Kpad > 0 && C > 0 && C <= Kpad, "occd_scale_weights: args");
-  const long long total = (long long)rows * Kpad;
+  OCCD_CHECK_ARG(Kpad % 8 == 0, "occd_scale_weights: Kpad must be a multiple of 8");
+  const long long total = (long long)rows * Kpad / 8;
   scale_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       master, gate, (__nv_bfloat16*)out, rows, Kpad, C);
   OCCD_CHECK_LAUNCH();
@@ -208,6 +265,24 @@ extern "C" int occd_upsample_bilinear_ac(const void* in, void* out, int B, int h
   const long long total = (long long)B * OH * OW * CV;
   upsample_bilinear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, h, w, OH, OW, CV, cs_in, in_off, cs_out, out_off, sy, sx);
+  OCCD_CHECK_LAUNCH();
+  return OCCD_OK;
+}
+
+extern "C" int occd_se_gate_fold_fwd(float* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
+                                     const float* b2, float* hidden, const float* master, void* wout, int C, int R,
+                                     int rows, int Kpad, void* stream) {
+  OCCD_CHECK_ARG(pool && w1 && b1 && w2t && b2 && hidden && master && wout && C > 0 && R > 0 && rows > 0 &&
+                 Kpad >= C && R <= 8192, "occd_se_gate_fold_fwd: args");
+  cudaStream_t st = (cudaStream_t)stream;
+  se_fc1_kernel<<<dim3(R, 1), 128, 0, st>>>(pool, inv_hw, w1, b1, hidden, C, R);
+  OCCD_CHECK_LAUNCH();
+  const int kblocks = (Kpad + 255) / 256;
+  int rows_per_block = rows;
+  while (rows_per_block > 16 && kblocks * ((rows + rows_per_block - 1) / rows_per_block) < 296) rows_per_block /= 2;
+  dim3 grid(kblocks, (rows + rows_per_block - 1) / rows_per_block);
+  se_fc2_fold_kernel<<<grid, 256, R * sizeof(float), st>>>(pool, hidden, w2t, b2, master,
+                                                           (__nv_bfloat16*)wout, C, R, rows, Kpad, rows_per_block);
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }

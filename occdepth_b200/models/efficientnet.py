@@ -79,10 +79,6 @@ def _emit_dw_se_project(plan, x, conv_dw, bn_dw, se, conv_proj, bn_proj, k, stri
     b1 = se.conv_reduce.bias.detach().float().contiguous()
     w2t = se.conv_expand.weight.detach().float().reshape(Cm, R).t().contiguous()
     b2 = se.conv_expand.bias.detach().float().contiguous()
-    gate = torch.empty(B, Cm, dtype=torch.float32, device=dev)
-    plan.add(FnOp(lambda st: L.occd_se_gate_fwd(pool.data_ptr(), 1.0 / (OH * OW), w1.data_ptr(), b1.data_ptr(),
-                                                w2t.data_ptr(), b2.data_ptr(), gate.data_ptr(), B, Cm, R, st),
-                  name + ".se", keep=(pool, w1, b1, w2t, b2, gate)))
     wp, bp = fold_bn(conv_proj.weight, None, bn_proj)
     Cout = wp.shape[0]
     Cout_pad, Kp = _round_up(Cout, 16), kpad_for(Cm)
@@ -90,11 +86,13 @@ def _emit_dw_se_project(plan, x, conv_dw, bn_dw, se, conv_proj, bn_proj, k, stri
     master[:Cout, :Cm] = wp.reshape(Cout, Cm)
     if out is None:
         out = plan.alloc(B, 1, OH, OW, Cout)
-    for bi in range(B):   # the gate is per image -> per-image weights
+    hidden = torch.empty(B, R, dtype=torch.float32, device=dev)
+    for bi in range(B):   # the gate is per image -> per-image projection weights
         wbuf = torch.zeros(1, Cout_pad, Kp, dtype=torch.bfloat16, device=dev)
-        plan.add(FnOp(lambda st, g=gate[bi], wb=wbuf: L.occd_scale_weights(master.data_ptr(), g.data_ptr(),
-                                                                            wb.data_ptr(), Cout_pad, Kp, Cm, st),
-                      name + ".gate_fold", keep=(master, gate, wbuf)))
+        plan.add(FnOp(lambda st, pb=pool[bi], hb=hidden[bi], wb=wbuf: L.occd_se_gate_fold_fwd(
+            pb.data_ptr(), 1.0 / (OH * OW), w1.data_ptr(), b1.data_ptr(), w2t.data_ptr(), b2.data_ptr(),
+            hb.data_ptr(), master.data_ptr(), wb.data_ptr(), Cm, R, Cout_pad, Kp, st),
+            name + ".se", keep=(pool, w1, b1, w2t, b2, hidden, master, wbuf)))
         sl = lambda c: type(c)(c.buf[bi:bi + 1], c.C, c.coff)
         plan.add(ConvOp([sl(y)], [(0, 0, 0, 0)], None, bp, (1, OH, OW), out0=sl(out),
                         res1=sl(residual) if residual is not None else None, weight_buf=wbuf, name=name + ".proj"))

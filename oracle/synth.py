@@ -109,3 +109,31 @@ def occdepth_cfg(**over):
             return_up_feats=1, batch_size_per_gpu=1, n_gpus=1, full_scene_size=(256, 256, 32))
     c.update(over)
     return c
+
+
+def seed_weights_(module, seed=0):
+    """Deterministic weights independent of module construction order / torch init code: every state_dict entry is
+    filled, in sorted key order, from one seeded CPU generator (conv/linear weights ~ N(0, 1/fan_in), biases ~
+    N(0, 0.1), BatchNorm weight/var ~ U(0.5, 1.5), mean ~ N(0, 0.1)).  The same call reproduces the same weights
+    for the reference module, the oracle and the CUDA modules (identical key sets)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = module.state_dict()
+    for k in sorted(sd.keys()):
+        t = sd[k]
+        if not t.dtype.is_floating_point:
+            continue
+        n = t.numel()
+        if k.endswith("running_var"):
+            v = torch.rand(n, generator=g) + 0.5
+        elif k.endswith("running_mean"):
+            v = torch.randn(n, generator=g) * 0.1
+        elif t.dim() <= 1:
+            is_bn_weight = k.endswith("weight") and (k[: -len("weight")] + "running_var") in sd
+            v = torch.rand(n, generator=g) + 0.5 if is_bn_weight else torch.randn(n, generator=g) * 0.1
+        else:
+            fan_in = max(1, n // t.shape[0])
+            if "ConvTranspose" in k:
+                fan_in = max(1, n // t.shape[1])
+            v = torch.randn(n, generator=g) / fan_in ** 0.5
+        t.copy_(v.view(t.shape).to(t.dtype))
+    return module

@@ -44,14 +44,14 @@ def test_unet3d(which):
     torch.manual_seed(0)
     if which == "kitti":
         from occdepth_b200.models.unet3d_kitti import UNet3D
-        full, ps, f = (64, 64, 16), 2, 32
+        full, ps, f = (32, 32, 16), 2, 32
         m = UNet3D(20, nn.BatchNorm3d, full, f, ps, context_prior=True, cascade_cls=True, occluded_cls=True).eval()
-        x = torch.randn(1, f, 32, 32, 8)
+        x = torch.randn(1, f, 16, 16, 8)
     else:
         from occdepth_b200.models.unet3d_nyu import UNet3D
-        full, f = (20, 12, 20), 40
+        full, f = (12, 8, 12), 24
         m = UNet3D(12, nn.BatchNorm3d, f, full, context_prior=True, cascade_cls=False).eval()
-        x = torch.randn(1, f, 20, 12, 20)
+        x = torch.randn(1, f, 12, 8, 12)
     synth.randomize_bn_(m)
     sd = {"n." + k: v.clone() for k, v in m.state_dict().items()}
     with torch.no_grad():

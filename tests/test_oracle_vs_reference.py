@@ -91,7 +91,7 @@ def test_unet2d(ref):
                                     return_up_feats=1).eval()
     synth.randomize_bn_(m)
     sd = {"net_rgb." + k: v for k, v in m.state_dict().items()}
-    x = torch.randn(1, 3, 70, 93)
+    x = torch.randn(1, 3, 38, 45)
     with torch.no_grad():
         want = m(x)
         got = OF.unet2d(sd, "net_rgb", x, "tf_efficientnet_b3_ns", 1)
@@ -110,7 +110,7 @@ def test_occdepth_forward_small(ref):
         m = ref.OccDepth.OccDepth(class_names=["c"] * 6, class_weights=torch.ones(6), full_scene_size=full,
                                   project_res=["1", "2", "4", "8"], config=cfg).eval()
     synth.randomize_bn_(m)
-    H, W = 47, 85
+    H, W = 33, 49
     g = torch.Generator().manual_seed(0)
     img = torch.randn(1, 2, 3, H, W, generator=g)
     N = 16 * 16 * 8
