@@ -234,6 +234,178 @@ sfa_lift_kernel(const SfaKParams p) {
   }
 }
 
+// Fast path for P == 1 (pattern_id 0, every shipped config): one (x,y,fov) record per (view, voxel).
+// All V x n_scales gathers of a voxel are issued before the first use (memory-level parallelism), index math is
+// 32-bit (h*w < 2^31), the records are read once per view instead of once per scale.
+template <typename T, int V, int NV>
+__global__ void __launch_bounds__(kThreads)
+sfa_lift_p1_kernel(const SfaKParams p) {
+  constexpr int VEC = FeatTraits<T>::VEC;
+  constexpr int G = FeatTraits<T>::G;
+  constexpr int VPB = kThreads / G;
+  constexpr int CPL = NV * VEC;
+  constexpr int NS = OCCD_SFA_MAX_SCALES;
+  __shared__ longlong2 s_pix[V][VPB * kIters];
+  __shared__ unsigned char s_fov[V][VPB * kIters];
+  const long long block_n0 = (long long)blockIdx.x * (VPB * kIters);
+  const int n_block = (int)min((long long)(VPB * kIters), p.N - block_n0);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const longlong2* gp = reinterpret_cast<const longlong2*>(p.pix) + (long long)v * p.N + block_n0;
+    const unsigned char* gf = p.fov + (long long)v * p.N + block_n0;
+    for (int i = threadIdx.x; i < n_block; i += kThreads) {
+      s_pix[v][i] = gp[i];
+      s_fov[v][i] = gf[i];
+    }
+  }
+  __syncthreads();
+  const int lane_g = threadIdx.x % G;
+  const int grp = threadIdx.x / G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  const int ns = p.n_scales;
+
+#pragma unroll 1
+  for (int it = 0; it < kIters; ++it) {
+    const int ln = it * VPB + grp;
+    const bool active = ln < n_block;
+    float m[V];
+    int off[V][NS];  // element offset of the gathered pixel's channel vector, or -1
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      bool in = active && s_fov[v][active ? ln : 0];
+      longlong2 xy = s_pix[v][active ? ln : 0];
+      // 32-bit fast math is valid for |x|,|y| < 2^30; anything else cannot address a feature map anyway
+      if (xy.x < -(1LL << 30) || xy.x > (1LL << 30) || xy.y < -(1LL << 30) || xy.y > (1LL << 30)) {
+        xy.x = -1; xy.y = 0;  // flat index negative -> treated as the zero column, mask stays as given
+      }
+      const int x = (int)xy.x, y = (int)xy.y;
+      m[v] = in ? 1.f : 0.f;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        int o = -1;
+        if (in && s < ns) {
+          int xs, ys;
+          if (p.shift[s] >= 0) { xs = x >> p.shift[s]; ys = y >> p.shift[s]; }
+          else { xs = (int)floordiv64(x, p.div[s], -1); ys = (int)floordiv64(y, p.div[s], -1); }
+          const long long idx = (long long)ys * p.w[s] + xs;
+          const int hw = p.h[s] * p.w[s];
+          if (idx >= 0 && idx < hw) o = (v * hw + (int)idx);
+        }
+        off[v][s] = o;
+      }
+    }
+    // per scale: both views' gathers are issued back to back, then reduced (keeping all V x scales loads in
+    // flight costs 93 registers and measured slower than the extra occupancy this 60-register form gets)
+    float acc[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (s >= ns) break;
+      const T* feat = reinterpret_cast<const T*>(p.feat[s]);
+      float f[V][CPL];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int c0 = (j * G + lane_g) * VEC;
+          if (off[v][s] >= 0 && c0 < p.C) {
+            FeatTraits<T>::load(feat + (long long)off[v][s] * p.C + c0, &f[v][j * VEC]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) f[v][j * VEC + e] = 0.f;
+          }
+        }
+      }
+      if (V == 1) {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) acc[i] += f[0][i];
+      } else {
+        float pair_acc[CPL];
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) pair_acc[i] = 0.f;
+#pragma unroll
+        for (int a = 0; a < V; ++a) {
+#pragma unroll
+          for (int b = a + 1; b < V; ++b) {
+            float dot = 0.f, na = 0.f, nb = 0.f;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+              dot = fmaf(f[a][i], f[b][i], dot);
+              na = fmaf(f[a][i], f[a][i], na);
+              nb = fmaf(f[b][i], f[b][i], nb);
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+              dot += __shfl_xor_sync(gmask, dot, o);
+              na += __shfl_xor_sync(gmask, na, o);
+              nb += __shfl_xor_sync(gmask, nb, o);
+            }
+            const float eps = 1e-8f;
+            const float cosv = dot / (fmaxf(sqrtf(na), eps) * fmaxf(sqrtf(nb), eps));
+            const float c = cosv * (m[a] * m[b]);
+            const float wa = c + ((m[a] > m[b]) ? 1.f : 0.f);
+            const float wb = c + ((m[b] > m[a]) ? 1.f : 0.f);
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) pair_acc[i] += wa * f[a][i] + wb * f[b][i];
+          }
+        }
+        const float inv = 1.f / (float)(V * (V - 1));
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) acc[i] += pair_acc[i] * inv;
+      }
+    }
+    if (!active) continue;
+    const long long n = block_n0 + ln;
+    long long no = n;
+    if (p.perm_nyu) {
+      const long long i0 = n / ((long long)p.S1 * p.S2);
+      const int k = (int)((n / p.S1) % p.S2);
+      const int j = (int)(n % p.S1);
+      no = (i0 * p.S1 + j) * p.S2 + k;
+    }
+    if (p.prior) {
+      const float pr = p.prior[no];
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) acc[i] = acc[i] * pr * p.scale_const;
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c0 = (j * G + lane_g) * VEC;
+      if (c0 >= p.C) continue;
+      if (p.out_mode == OCCD_SFA_OUT_BF16_CL) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + no * p.out_cstride + c0;
+        if (VEC == 8) {
+          *reinterpret_cast<uint4*>(o) = pack8(&acc[j * VEC]);
+        } else {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(acc[j * VEC], acc[j * VEC + 1]);
+          __nv_bfloat162 hi = __floats2bfloat162_rn(acc[j * VEC + 2], acc[j * VEC + 3]);
+          uint2 u;
+          u.x = *reinterpret_cast<unsigned*>(&lo);
+          u.y = *reinterpret_cast<unsigned*>(&hi);
+          *reinterpret_cast<uint2*>(o) = u;
+        }
+      } else if (p.out_mode == OCCD_SFA_OUT_F32_CL) {
+        float* o = reinterpret_cast<float*>(p.out) + no * p.out_cstride + c0;
+#pragma unroll
+        for (int e = 0; e < VEC; e += 4)
+          *reinterpret_cast<float4*>(o + e) =
+              make_float4(acc[j * VEC + e], acc[j * VEC + e + 1], acc[j * VEC + e + 2], acc[j * VEC + e + 3]);
+      } else {
+        float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) o[(long long)(c0 + e) * p.out_n + no] = acc[j * VEC + e];
+      }
+    }
+  }
+}
+
+static bool sfa_fits_int32(const SfaKParams& kp, int n_views) {
+  for (int s = 0; s < kp.n_scales; ++s)
+    if ((long long)n_views * kp.h[s] * kp.w[s] * kp.C >= (1LL << 31) || kp.n_scales > OCCD_SFA_MAX_SCALES) return false;
+  return true;
+}
+
 template <typename T, int V>
 int launch_nv(const SfaKParams& kp, int nv, cudaStream_t st) {
   constexpr int G = FeatTraits<T>::G;
@@ -246,7 +418,9 @@ int launch_nv(const SfaKParams& kp, int nv, cudaStream_t st) {
     return OCCD_ERR_UNSUPPORTED;
   }
 #define OCCD_SFA_LAUNCH(NV_)                                                                           \
-  {                                                                                                    \
+  if (kp.P == 1 && sfa_fits_int32(kp, V)) {                    \
+    sfa_lift_p1_kernel<T, V, NV_><<<(unsigned)blocks, kThreads, 0, st>>>(kp);                          \
+  } else {                                                                                             \
     if (smem > 48 * 1024)                                                                              \
       cudaFuncSetAttribute(sfa_lift_kernel<T, V, NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                            (int)smem);                                                                 \
