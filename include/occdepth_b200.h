@@ -92,6 +92,9 @@ int occd_cl_to_planar(const void* in, int in_dtype, float* out, long long B, int
 #define OCCD_ACT_SIGMOID 4
 #define OCCD_CONV_IMPL_TC 0   /* tcgen05 + TMA implicit GEMM                                       */
 #define OCCD_CONV_IMPL_SIMT 1 /* CUDA-core direct convolution (cross-check / odd shapes)           */
+#define OCCD_CONV_IMPL_HALO 2 /* tcgen05, halo tile loaded once + row-shifted smem views per tap:    */
+                              /* stride-1 {-d,0,d}-tap convs, Cin <= 64, resident weights; returns  */
+                              /* OCCD_ERR_UNSUPPORTED from plan_create when the shape does not fit   */
 #define OCCD_OUT1_NONE 0
 #define OCCD_OUT1_BF16_CL 1    /* pre-activation copy, channels-last bf16                          */
 #define OCCD_OUT1_F32_PLANAR 2 /* pre-activation copy, fp32 [B][C][positions] (reference layout)   */
@@ -185,6 +188,25 @@ int occd_scale_weights(const float* master, const float* gate, void* out, int ro
 /* F.interpolate(mode="bilinear", align_corners=True) of UpSampleBN.forward (unet2d.py:39-44)      */
 int occd_upsample_bilinear_ac(const void* in, void* out, int B, int h, int w, int OH, int OW, int C, int cs_in,
                               int in_off, int cs_out, int out_off, void* stream);
+
+/* -------------------------------------------------------------------------------------------- */
+/* FlospDepth (the "OAD" depth branch, configs with trans_2d_to_3d: "flosp_depth")                */
+/* frustum grid generation fused with the trilinear sampling of the depth distribution and of the */
+/* all-ones mask volume + per-camera masked mean: FrustumGridGenerator (f2v/frustum_grid_         */
+/* generator.py:70-152), bin_depths LID (f2v/utils/depth_utils.py:24-26), normalize_coords        */
+/* (f2v/utils/grid_utils.py:4-19), F.grid_sample (f2v/sampler.py:49-65), flosp_depth.py:563-602.   */
+/* depth: [V][Dn][h][w] fp32 probabilities; cams: V x 40 floats {T[12], K[12], ida[16]} where T =  */
+/* rows 0..2 of lidar_to_cam @ grid_to_lidar; out: [X*Y*Z] fp32 (perm_xzy: written as [X][Z][Y])  */
+int occd_frustum_sample_fwd(const float* depth, const float* cams, int V, int Dn, int h, int w, int X, int Y,
+                            int Z, float img_w, float img_h, float dmin, float dmax, int mean_mode, float* out,
+                            int perm_xzy, void* stream);
+/* softmax over the C planar channels of [B][C][S] fp32 (depth_feature.softmax(1), flosp_depth.py:548) */
+int occd_softmax_planar(const float* in, float* out, long long B, int C, long long S, void* stream);
+/* out[b] = act(W in[b] + bias): the Linear / 1x1-on-a-vector layers of DepthNet.mlp and SELayer    */
+int occd_fc_fwd(const float* in, const float* w, const float* bias, float* out, int B, int n_in, int n_out,
+                int act, void* stream);
+/* x[b][pos][c] *= gate[b][c] in place (SELayer: x * gate(x_se), flosp_depth.py:195-199)            */
+int occd_channel_scale(void* x, const float* gate, long long B, long long S, int C, int cstride, void* stream);
 
 #ifdef __cplusplus
 }

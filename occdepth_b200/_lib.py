@@ -42,7 +42,7 @@ class SfaParams(C.Structure):
 
 
 CONV_MAX_TAPS, CONV_MAX_SRC = 81, 3
-CONV_IMPL_TC, CONV_IMPL_SIMT = 0, 1
+CONV_IMPL_TC, CONV_IMPL_SIMT, CONV_IMPL_HALO = 0, 1, 2
 OUT1_NONE, OUT1_BF16_CL, OUT1_F32_PLANAR = 0, 1, 2
 
 
@@ -102,6 +102,10 @@ SYMBOLS = {
     "occd_se_gate_fwd": (C.c_int, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "occd_se_gate_fold_fwd": (C.c_int, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "occd_scale_weights": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "occd_frustum_sample_fwd": (C.c_int, [_vp, _vp] + [_i] * 7 + [_f] * 4 + [_i, _vp, _i, _vp]),
+    "occd_softmax_planar": (C.c_int, [_vp, _vp, _ll, _i, _ll, _vp]),
+    "occd_fc_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "occd_channel_scale": (C.c_int, [_vp, _vp, _ll, _ll, _i, _i, _vp]),
     "occd_upsample_bilinear_ac": (C.c_int, [_vp, _vp] + [_i] * 10 + [_vp]),
 }
 

@@ -136,6 +136,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc = tc::make_idesc_bf16(128, p.N_tile);
+      const uint64_t da0 = tc::make_sdesc(smem_a, ROW_BYTES);
+      const uint64_t db0 = tc::make_sdesc(smem_b, ROW_BYTES);
       int s = 0;
       uint32_t ph = 0;
       int j = 0;
@@ -150,14 +152,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           tc::fence_after_sync();
           const int cnt = (iters_per_tile - it) < p.group ? (iters_per_tile - it) : p.group;
           for (int g = 0; g < cnt; ++g, ++it) {
-            const uint32_t a_addr = smem_a + (uint32_t)(s * p.group + g) * p.a_bytes;
-            const uint32_t b_addr = smem_b + (uint32_t)(s * p.group + g) * p.b_stride;
+            const uint64_t da = da0 + (uint64_t)((s * p.group + g) * (p.a_bytes >> 4));
+            const uint64_t db = db0 + (uint64_t)((s * p.group + g) * (p.b_stride >> 4));
+            if (it == 0) tc::mma_bf16_imm<0>(d_tmem, da, db, idesc);
+            else tc::mma_bf16_imm<1>(d_tmem, da, db, idesc);
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k) {
-              const uint64_t da = tc::make_sdesc(a_addr + k * 32, ROW_BYTES);
-              const uint64_t db = tc::make_sdesc(b_addr + k * 32, ROW_BYTES);
-              tc::mma_bf16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 1; k < KC / 16; ++k) tc::mma_bf16_imm<1>(d_tmem, da + 2 * k, db + 2 * k, idesc);
           }
           tc::mma_commit(empty_bar + 8u * s);  // frees the smem stage when these MMAs retire
           if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -220,6 +220,201 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       }
       tc::fence_before_sync();
       tc::mbar_arrive(tmem_empty_bar + 8u * acc);  // this thread's TMEM reads of the buffer are done
+      if (tracer && j < 64) p.trace[j * 8 + 6] = clock64();
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Halo-tile variant for stride-1 3x3x3 convolutions with few channels (the full-resolution head):
+// the per-tap TMA boxes of conv_tc_kernel re-load every input row 27 times and the TMA unit (~1.5 cycles per
+// box row) becomes the limiter.  Here each CTA tile loads ONE zero-filled halo box (PD x PH x PW positions,
+// rows of KC channels) per k-chunk and feeds all 27 taps from row-shifted views of that box: with smem rows
+// linearised as r = (pd*PH + ph)*PW + pw, the A operand of tap (a,b,c) for output rows [R, R+128) is simply
+// rows [R + (a*PH + b)*PW + c, ...) -- a different UMMA start address, same data.  Rows that fall in the
+// halo produce garbage accumulator rows that the epilogue never stores.  Dilation d runs the same scheme on
+// the d^3 sub-sampled grids (TMA traversal stride d), so the halo is always one position.  Weights for all
+// taps stay resident in shared memory.
+struct HaloParams {
+  ConvEpi epi;
+  int d;                      // dilation (== padding)
+  int D, H, W;                // full grid (== output grid)
+  int BD, BH, BW, PD, PH, PW;  // valid box / halo box (sub-sampled coordinates)
+  int hd, hh, hw;             // 1 where the taps reach into that dimension (halo of one sub-sampled position)
+  int tilesD, tilesH, tilesW;
+  int nM, R0;                 // M tiles per CTA tile, first valid row
+  int box_bytes;              // bytes one TMA box delivers
+  int a_stage_bytes;          // allocated per stage (box + slack rows read by garbage outputs)
+  int stages;
+  int n_taps;
+  int N_tile, tmem_cols, set_stride;
+  int bo_mode;                // UMMA descriptor base-offset convention for row-shifted swizzled views
+  int b_stride, w_bytes;
+  int tap_off16[27];          // (R0 + (a*PH + b)*PW + c) * row_bytes / 16: A-descriptor advance per tap
+  long long* trace;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(kTcThreads)
+conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ CUtensorMap tmA,
+                 const __grid_constant__ CUtensorMap tmW) {
+  constexpr int ROW_BYTES = KC * 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_w = smem_base;                                   // [n_taps][b_stride] resident weights
+  const uint32_t smem_a = smem_w + (uint32_t)p.w_bytes;                 // [stages][a_stage_bytes]
+  const uint32_t bar_base = smem_a + (uint32_t)p.stages * p.a_stage_bytes;
+  const uint32_t full_bar = bar_base;            // [4]
+  const uint32_t empty_bar = bar_base + 32u;     // [4]
+  const uint32_t tfull_bar = bar_base + 64u;     // [2]
+  const uint32_t tempty_bar = bar_base + 80u;    // [2]
+  const uint32_t w_bar = bar_base + 96u;
+  const uint32_t tmem_slot = bar_base + 104u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int d = p.d;
+  const int per_res = p.tilesD * p.tilesH * p.tilesW;
+  const int num_tiles = p.epi.B * d * d * d * per_res;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmW);
+    for (int s = 0; s < p.stages; ++s) {
+      tc::mbar_init(full_bar + 8u * s, 1);
+      tc::mbar_init(empty_bar + 8u * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(tfull_bar + 8u * a, 1);
+      tc::mbar_init(tempty_bar + 8u * a, 128);
+    }
+    tc::mbar_init(w_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // tile -> (batch, residue class, sub-grid tile origin)
+  auto decode = [&](int tile, int& b, int& ra, int& rb, int& rc, int& td, int& th, int& tw) {
+    int t = tile;
+    tw = t % p.tilesW; t /= p.tilesW;
+    th = t % p.tilesH; t /= p.tilesH;
+    td = t % p.tilesD; t /= p.tilesD;
+    rc = t % d; t /= d;
+    rb = t % d; t /= d;
+    ra = t % d; t /= d;
+    b = t;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: resident weights once, then one halo box per tile =====
+      tc::mbar_expect_tx(w_bar, (uint32_t)(p.n_taps * p.N_tile * ROW_BYTES));
+      for (int tp = 0; tp < p.n_taps; ++tp)
+        tc::tma_load_2d(smem_w + (uint32_t)tp * p.b_stride, &tmW, w_bar, 0, tp * p.N_tile);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int b, ra, rb, rc, td, th, tw;
+        decode(tile, b, ra, rb, rc, td, th, tw);
+        tc::mbar_wait(empty_bar + 8u * s, ph ^ 1u);
+        tc::mbar_expect_tx(full_bar + 8u * s, (uint32_t)p.box_bytes);
+        tc::tma_load_5d(smem_a + (uint32_t)s * p.a_stage_bytes, &tmA, full_bar + 8u * s, 0,
+                        (tw * p.BW - p.hw) * d + rc, (th * p.BH - p.hh) * d + rb, (td * p.BD - p.hd) * d + ra, b);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = tc::make_idesc_bf16(128, p.N_tile);
+      const uint64_t db_w = tc::make_sdesc(smem_w, ROW_BYTES);
+      const int w_step16 = p.b_stride / 16;
+      tc::mbar_wait(w_bar, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int j = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+        const uint32_t set = (uint32_t)j & 1u;
+        const uint32_t use = (uint32_t)j >> 1;
+        tc::mbar_wait(tempty_bar + 8u * set, (use & 1u) ^ 1u);
+        tc::mbar_wait(full_bar + 8u * s, ph);
+        tc::fence_after_sync();
+        if (p.trace && blockIdx.x == 0 && j < 64) p.trace[j * 8 + 2] = clock64();
+        // descriptors advance by plain 64-bit adds on the 16-byte-unit address field (smem < 256 KB: no carry out
+        // of the 14-bit field), so the issue loop is ~4 instructions per tcgen05.mma
+        const uint64_t da_stage = tc::make_sdesc(smem_a + (uint32_t)s * p.a_stage_bytes, ROW_BYTES);
+        for (int m = 0; m < p.nM; ++m) {
+          const uint32_t d_tmem = tmem_base + set * (uint32_t)p.set_stride + (uint32_t)(m * p.N_tile);
+          const uint64_t da_m = da_stage + (uint64_t)(m * (128 * ROW_BYTES / 16));
+          {
+            const uint64_t da = da_m + (uint64_t)p.tap_off16[0];
+            tc::mma_bf16_imm<0>(d_tmem, da, db_w, idesc);
+#pragma unroll
+            for (int k = 1; k < KC / 16; ++k) tc::mma_bf16_imm<1>(d_tmem, da + 2 * k, db_w + 2 * k, idesc);
+          }
+#pragma unroll 3
+          for (int tp = 1; tp < p.n_taps; ++tp) {
+            const uint64_t da = da_m + (uint64_t)p.tap_off16[tp];
+            const uint64_t db = db_w + (uint64_t)(tp * w_step16);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) tc::mma_bf16_imm<1>(d_tmem, da + 2 * k, db + 2 * k, idesc);
+          }
+        }
+        tc::mma_commit(empty_bar + 8u * s);
+        tc::mma_commit(tfull_bar + 8u * set);
+        if (p.trace && blockIdx.x == 0 && j < 64) p.trace[j * 8 + 3] = clock64();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const bool tracer = p.trace && blockIdx.x == 0 && threadIdx.x == 64;
+    int j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      const uint32_t set = (uint32_t)j & 1u;   // accumulator set == epilogue group
+      const uint32_t use = (uint32_t)j >> 1;
+      if ((int)set != grp) continue;
+      int b, ra, rb, rc, td, th, tw;
+      decode(tile, b, ra, rb, rc, td, th, tw);
+      if (tracer && j < 64) p.trace[j * 8 + 4] = clock64();
+      tc::mbar_wait(tfull_bar + 8u * set, use & 1u);
+      tc::fence_after_sync();
+      if (tracer && j < 64) p.trace[j * 8 + 5] = clock64();
+      for (int m = 0; m < p.nM; ++m) {
+        const int R = p.R0 + m * 128 + q * 32 + lane;
+        const int pw = R % p.PW;
+        const int phh = (R / p.PW) % p.PH;
+        const int pd = R / (p.PW * p.PH);
+        const int od = (td * p.BD + pd - p.hd) * d + ra, oh = (th * p.BH + phh - p.hh) * d + rb,
+                  ow = (tw * p.BW + pw - p.hw) * d + rc;
+        const bool valid = pd >= p.hd && pd < p.hd + p.BD && phh >= p.hh && phh < p.hh + p.BH && pw >= p.hw &&
+                           pw < p.hw + p.BW && od < p.D && oh < p.H && ow < p.W;
+        const uint32_t taddr = tmem_base + set * (uint32_t)p.set_stride + (uint32_t)(m * p.N_tile) +
+                               ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(taddr + (uint32_t)c0, v);
+          if (valid) conv_epilogue_row<16>(p.epi, b, od, oh, ow, c0, v);
+        }
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive(tempty_bar + 8u * set);
       if (tracer && j < 64) p.trace[j * 8 + 6] = clock64();
     }
   }
@@ -315,6 +510,7 @@ struct occd_conv_plan {
   int impl;
   int kc;
   TcParams tc;
+  HaloParams halo;
   SimtParams simt;
   CUtensorMap tmA[OCCD_CONV_MAX_SRC];
   CUtensorMap tmW;
@@ -339,6 +535,137 @@ static int fill_epi(const occd_conv_desc* d, ConvEpi* e) {
   e->out1_mode = d->out1_mode; e->out1 = d->out1;
   e->out1_cstride = d->out1_cstride; e->out1_coff = d->out1_coff; e->out1_C = d->out1_C;
   return 0;
+}
+
+
+static int n_sms_cached() {
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
+      n_sms = prop.multiProcessorCount;
+    else
+      n_sms = 148;
+  }
+  return n_sms;
+}
+
+// Halo-tile plan: stride-1 "same" convolution whose taps are {-d,0,d} offsets, one source, one k-chunk, one N tile.
+static int build_halo_plan(const occd_conv_desc* d, occd_conv_plan* pl) {
+#define HALO_REQUIRE(cond, msg) do { if (!(cond)) { occd_set_last_error("occd_conv_plan_create(halo): " msg); return OCCD_ERR_UNSUPPORTED; } } while (0)
+  HALO_REQUIRE(d->n_src == 1, "one source only");
+  HALO_REQUIRE(d->stride[0] == 1 && d->stride[1] == 1 && d->stride[2] == 1, "stride must be 1");
+  HALO_REQUIRE(d->omul[0] == 1 && d->omul[1] == 1 && d->omul[2] == 1 && d->oadd[0] == 0 && d->oadd[1] == 0 &&
+               d->oadd[2] == 0, "identity output mapping only");
+  HALO_REQUIRE(d->OD == d->ID && d->OH == d->IH && d->OW == d->IW, "output grid must equal the input grid");
+  HALO_REQUIRE(d->n_taps <= 27, "at most 27 taps");
+  HALO_REQUIRE(d->src_C[0] <= 64 && d->Cout_pad <= 128, "channel counts too large for the resident-weight scheme");
+  int dil = 0;
+  for (int i = 0; i < d->n_taps; ++i) {
+    const int o[3] = {abs(d->taps[i].dz), abs(d->taps[i].dy), abs(d->taps[i].dx)};
+    for (int k = 0; k < 3; ++k)
+      if (o[k]) { if (!dil) dil = o[k]; HALO_REQUIRE(o[k] == dil, "taps must be {-d,0,d} offsets"); }
+  }
+  HALO_REQUIRE(dil >= 1 && dil <= 8, "dilation must be 1..8");
+  int hal[3] = {0, 0, 0};
+  for (int i = 0; i < d->n_taps; ++i) {
+    if (d->taps[i].dz) hal[0] = 1;
+    if (d->taps[i].dy) hal[1] = 1;
+    if (d->taps[i].dx) hal[2] = 1;
+  }
+  HaloParams& h = pl->halo;
+  fill_epi(d, &h.epi);
+  const int C = d->src_C[0];
+  const int KC = C > 32 ? 64 : (C > 16 ? 32 : 16);
+  HALO_REQUIRE(d->Kpad == KC, "Kpad must equal the k-chunk");
+  pl->kc = KC;
+  const int row_bytes = KC * 2;
+  h.d = dil; h.D = d->ID; h.H = d->IH; h.W = d->IW;
+  h.hd = hal[0]; h.hh = hal[1]; h.hw = hal[2];
+  h.n_taps = d->n_taps;
+  h.N_tile = d->Cout_pad;
+  h.b_stride = round_up(h.N_tile * row_bytes, 1024);
+  h.w_bytes = h.n_taps * h.b_stride;
+  HALO_REQUIRE(h.w_bytes <= 112 * 1024, "weights do not fit in shared memory");
+  const int sD = (d->ID + dil - 1) / dil, sH = (d->IH + dil - 1) / dil, sW = (d->IW + dil - 1) / dil;
+  const int smem_total = 224 * 1024 - h.w_bytes - 2048;
+  // W extent of the box: the whole sub-sampled line when it fits, else equal splits of at most 62
+  const int nW = (sW + 61) / 62;
+  const int BW = (sW + nW - 1) / nW;
+  long long best_cost = -1;
+  for (int BD = 1; BD <= (hal[0] ? 4 : 1); ++BD)
+    for (int BH = 1; BH <= sH && BH <= 96; ++BH) {
+      const int PD = BD + 2 * hal[0], PH = BH + 2 * hal[1], PW = BW + 2 * hal[2];
+      if ((PW - 1) * dil + 1 > 256 || (PH - 1) * dil + 1 > 256 || (PD - 1) * dil + 1 > 256) continue;
+      const int R0 = (hal[0] * PH + hal[1]) * PW + hal[2];
+      const int Rend = ((BD - 1 + hal[0]) * PH + (BH - 1 + hal[1])) * PW + (BW - 1 + hal[2]);
+      const int nM = (Rend - R0 + 1 + 127) / 128;
+      if (nM * h.N_tile > 256) continue;
+      int rows_alloc = PD * PH * PW;
+      if (R0 + nM * 128 + R0 > rows_alloc) rows_alloc = R0 + nM * 128 + R0;
+      const int stage = round_up(rows_alloc * row_bytes, 1024);
+      if (2 * stage > smem_total) continue;
+      if (2 * BD * BH * BW < nM * 128) continue;  // < 50 % useful MMA rows: the per-tap kernel is the better choice
+      const long long tiles = (long long)((sD + BD - 1) / BD) * ((sH + BH - 1) / BH) * nW;
+      const long long cost = tiles * nM * 1000 + tiles;  // MMA work first, then tile count
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        h.BD = BD; h.BH = BH; h.BW = BW; h.PD = PD; h.PH = PH; h.PW = PW;
+        h.R0 = R0; h.nM = nM; h.a_stage_bytes = stage;
+      }
+    }
+  HALO_REQUIRE(best_cost >= 0, "no tile shape fits");
+  h.tilesD = (sD + h.BD - 1) / h.BD; h.tilesH = (sH + h.BH - 1) / h.BH; h.tilesW = nW;
+  h.box_bytes = h.PD * h.PH * h.PW * row_bytes;
+  h.stages = smem_total / h.a_stage_bytes;
+  if (h.stages > 4) h.stages = 4;
+  h.set_stride = 32;
+  while (h.set_stride < h.nM * h.N_tile) h.set_stride *= 2;
+  h.tmem_cols = 2 * h.set_stride;
+  for (int i = 0; i < d->n_taps; ++i)
+    h.tap_off16[i] = (h.R0 + ((d->taps[i].dz / dil) * h.PH + d->taps[i].dy / dil) * h.PW + d->taps[i].dx / dil) *
+                     row_bytes / 16;
+  { const char* e = getenv("OCCD_HALO_BO"); h.bo_mode = e ? atoi(e) : 0; }  // measured on B200: absolute address bits
+  { const char* e = getenv("OCCD_CONV_TRACE_PTR"); h.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
+  pl->smem = (size_t)h.w_bytes + (size_t)h.stages * h.a_stage_bytes + 128 + 1024;
+  const long long num_tiles = (long long)d->B * dil * dil * dil * h.tilesD * h.tilesH * h.tilesW;
+  HALO_REQUIRE(num_tiles < 2147483647LL, "too many tiles");
+  const int n_sms = n_sms_cached();
+  pl->grid = dim3((unsigned)(num_tiles < n_sms ? num_tiles : n_sms));
+
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    occd_set_last_error("occd_conv_plan_create: cuTensorMapEncodeTiled unavailable (no CUDA driver / GPU?)");
+    return OCCD_ERR_CUDA;
+  }
+  const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                         : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  {
+    const cuuint64_t cs = (cuuint64_t)d->src_cstride[0] * 2;
+    cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)d->IW, (cuuint64_t)d->IH, (cuuint64_t)d->ID, (cuuint64_t)d->B};
+    cuuint64_t gstr[4] = {cs, cs * d->IW, cs * d->IW * d->IH, cs * d->IW * d->IH * d->ID};
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)((h.PW - 1) * dil + 1), (cuuint32_t)((h.PH - 1) * dil + 1),
+                         (cuuint32_t)((h.PD - 1) * dil + 1), 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)dil, (cuuint32_t)dil, (cuuint32_t)dil, 1};
+    void* base = (void*)((const char*)d->src[0] + (size_t)d->src_coff[0] * 2);
+    CUresult r = enc(&pl->tmA[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { occd_set_last_error("occd_conv_plan_create(halo): cuTensorMapEncodeTiled(source) failed"); return OCCD_ERR_CUDA; }
+  }
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)d->Kpad, (cuuint64_t)d->n_taps * d->Cout_pad};
+    cuuint64_t gstr[1] = {(cuuint64_t)d->Kpad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)h.N_tile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&pl->tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d->weight, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { occd_set_last_error("occd_conv_plan_create(halo): cuTensorMapEncodeTiled(weights) failed"); return OCCD_ERR_CUDA; }
+  }
+#undef HALO_REQUIRE
+  return OCCD_OK;
 }
 
 extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** out) {
@@ -381,7 +708,8 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
     OCCD_CHECK_ARG(abs(d->taps[i].dz) < 30000 && abs(d->taps[i].dy) < 30000 && abs(d->taps[i].dx) < 30000,
                    "occd_conv_plan_create: tap offset");
   }
-  OCCD_CHECK_ARG(d->impl == OCCD_CONV_IMPL_TC || d->impl == OCCD_CONV_IMPL_SIMT, "occd_conv_plan_create: impl");
+  OCCD_CHECK_ARG(d->impl == OCCD_CONV_IMPL_TC || d->impl == OCCD_CONV_IMPL_SIMT || d->impl == OCCD_CONV_IMPL_HALO,
+                 "occd_conv_plan_create: impl");
 
   occd_conv_plan* pl = new (std::nothrow) occd_conv_plan;
   OCCD_CHECK_ARG(pl != nullptr, "occd_conv_plan_create: out of memory");
@@ -406,6 +734,13 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
     }
     const long long total = (long long)d->B * d->OD * d->OH * d->OW * (s.epi.Cout_store / 8);
     pl->grid = dim3((unsigned)((total + 127) / 128));
+    *out = pl;
+    return OCCD_OK;
+  }
+
+  if (d->impl == OCCD_CONV_IMPL_HALO) {
+    const int rc = build_halo_plan(d, pl);
+    if (rc != OCCD_OK) { delete pl; return rc; }
     *out = pl;
     return OCCD_OK;
   }
@@ -452,6 +787,19 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
   t.N_tile = 16;
   for (int n = 16; n <= 256 && n <= d->Cout_pad; n += 16)
     if (d->Cout_pad % n == 0) t.N_tile = n;
+  {
+    // small-M layers (late encoder stages): a narrower N tile that still keeps >= 64 columns trades some A
+    // re-reads for enough tiles to occupy every SM
+    const long long m_tiles0 = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w;
+    const int n_sms = n_sms_cached();
+    int best = t.N_tile;
+    for (int n = t.N_tile; n >= 64; n -= 16) {
+      if (d->Cout_pad % n) continue;
+      best = n;
+      if (m_tiles0 * (d->Cout_pad / n) >= n_sms) break;
+    }
+    if (m_tiles0 * (d->Cout_pad / t.N_tile) < n_sms) t.N_tile = best;
+  }
   t.tmem_cols = 32;
   while (t.tmem_cols < t.N_tile) t.tmem_cols *= 2;
   { const char* e = getenv("OCCD_CONV_TRACE_PTR"); t.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
@@ -487,15 +835,7 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
   }
   t.num_m_tiles = (int)m_tiles;
   {
-    static int n_sms = 0;
-    if (n_sms == 0) {
-      int dev = 0;
-      cudaDeviceProp prop;
-      if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
-        n_sms = prop.multiProcessorCount;
-      else
-        n_sms = 148;
-    }
+    const int n_sms = n_sms_cached();
     pl->grid = dim3((unsigned)(all_tiles < n_sms ? all_tiles : n_sms));
   }
 
@@ -560,6 +900,13 @@ extern "C" int occd_conv_plan_info(const occd_conv_plan* pl, int* info) {
     info[6] = (int)pl->grid.x;
     return OCCD_OK;
   }
+  if (pl->impl == OCCD_CONV_IMPL_HALO) {
+    const HaloParams& h = pl->halo;
+    info[0] = h.BD; info[1] = h.BH; info[2] = h.BW; info[3] = h.N_tile; info[4] = pl->kc;
+    info[5] = h.stages * 100 + h.nM; info[6] = (int)pl->grid.x;
+    info[7] = h.epi.B * h.d * h.d * h.d * h.tilesD * h.tilesH * h.tilesW;
+    return OCCD_OK;
+  }
   info[0] = pl->tc.TD; info[1] = pl->tc.TH; info[2] = pl->tc.TW; info[3] = pl->tc.N_tile;
   info[4] = pl->kc; info[5] = pl->tc.stages * 100 + pl->tc.group; info[6] = (int)pl->grid.x; info[7] = pl->tc.num_m_tiles * (pl->tc.Cout_pad / pl->tc.N_tile);
   return OCCD_OK;
@@ -578,6 +925,19 @@ static int launch_tc(const occd_conv_plan* pl, cudaStream_t st) {
   return OCCD_OK;
 }
 
+template <int KC>
+static int launch_halo(const occd_conv_plan* pl, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
+    attr_set = true;
+  }
+  conv_halo_kernel<KC><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->halo, pl->tmA[0], pl->tmW);
+  OCCD_CHECK_LAUNCH();
+  return OCCD_OK;
+}
+
 extern "C" int occd_conv_run(const occd_conv_plan* pl, void* stream) {
   OCCD_CHECK_ARG(pl != nullptr, "occd_conv_run: null plan");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -585,6 +945,13 @@ extern "C" int occd_conv_run(const occd_conv_plan* pl, void* stream) {
     conv_simt_kernel<<<pl->grid, 128, 0, st>>>(pl->simt);
     OCCD_CHECK_LAUNCH();
     return OCCD_OK;
+  }
+  if (pl->impl == OCCD_CONV_IMPL_HALO) {
+    switch (pl->kc) {
+      case 64: return launch_halo<64>(pl, st);
+      case 32: return launch_halo<32>(pl, st);
+      case 16: return launch_halo<16>(pl, st);
+    }
   }
   switch (pl->kc) {
     case 64: return launch_tc<64>(pl, st);

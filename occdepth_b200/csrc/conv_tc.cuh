@@ -104,6 +104,17 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t row_byte
   return d;
 }
 
+// descriptor for a start address that is NOT aligned to the swizzle repeat (8 rows): bits [49,52) "base offset"
+// would tell the hardware where in the 8-row pattern the first row sits.  Measured on B200 (tools/gpu_diag.py halo):
+// with TMA-written tiles whose stage base is 1024-byte aligned the XOR swizzle is a function of the ABSOLUTE shared
+// address bits on both the TMA and the UMMA side, so a row-shifted start address needs base offset 0 (mode 0,
+// bit-exact); mode 1 = (addr >> 7) & 7 produced wrong results and is kept only for experiments.
+__device__ __forceinline__ uint64_t make_sdesc_shifted(uint32_t saddr, uint32_t row_bytes, int mode) {
+  uint64_t d = make_sdesc(saddr, row_bytes);
+  if (mode == 1) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  return d;
+}
+
 // instruction descriptor for kind::f16, BF16 x BF16 -> F32, both operands K-major
 //   bits [4,6) D format (1 = F32)  [7,10) A format (1 = BF16)  [10,13) B format  [15] A major  [16] B major
 //   bits [17,23) N >> 3            [24,29) M >> 4
@@ -120,6 +131,19 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// same, with the accumulate flag as an immediate (no per-instruction setp in the issue loop)
+template <int ACC>
+__device__ __forceinline__ void mma_bf16_imm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(ACC)
       : "memory");
 }
 

@@ -1,0 +1,177 @@
+// FlospDepth occupancy prior: frustum grid generation fused with trilinear sampling of the depth distribution.
+// replaces FrustumGridGenerator.forward/transform_grid (occdepth/models/f2v/frustum_grid_generator.py:70-152),
+// bin_depths LID (f2v/utils/depth_utils.py:24-26), normalize_coords (f2v/utils/grid_utils.py:4-19),
+// Sampler / F.grid_sample 5-D bilinear zeros align_corners=False (f2v/sampler.py:49-65) for the depth volume AND
+// the all-ones mask volume, and the per-camera masked mean of FlospDepth.forward (flosp_depth.py:563-602).
+// The grid is never materialised: each thread computes its voxel's sampling coordinate on the fly.
+// Also: channel softmax (flosp_depth.py:548), small FC layers of DepthNet's Mlp/SELayer (:159-199), channel gate.
+#include "common.cuh"
+#include "../../include/occdepth_b200.h"
+
+namespace {
+
+struct FrustumCam {
+  float T[12];    // rows 0..2 of lidar_to_cam @ grid_to_lidar (voxel index+0.5 -> camera)
+  float K[12];    // cam_to_img 3x4
+  float ida[16];  // 4x4
+};
+
+__device__ __forceinline__ float dehom(float z) {  // kornia 0.5.0 convert_points_from_homogeneous scale
+  return fabsf(z) > 1e-8f ? 1.f / (z + 1e-8f) : 1.f;
+}
+
+__global__ void frustum_sample_kernel(const float* __restrict__ depth, const FrustumCam* __restrict__ cams, int V,
+                                      int Dn, int h, int w, int X, int Y, int Z, float img_w, float img_h,
+                                      float dmin, float bin_size, int mean_mode, float* __restrict__ out,
+                                      int perm_xzy) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long N = (long long)X * Y * Z;
+  if (n >= N) return;
+  const int k = (int)(n % Z), j = (int)((n / Z) % Y), i = (int)(n / ((long long)Z * Y));
+  const float px = i + 0.5f, py = j + 0.5f, pz = k + 0.5f;
+  float fsum = 0.f, msum = 0.f;
+  for (int v = 0; v < V; ++v) {
+    const FrustumCam& c = cams[v];
+    // camera point (homogeneous w == 1 -> scale 1/(1+1e-8) == 1 in fp32)
+    const float cx = c.T[0] * px + c.T[1] * py + c.T[2] * pz + c.T[3];
+    const float cy = c.T[4] * px + c.T[5] * py + c.T[6] * pz + c.T[7];
+    const float cz = c.T[8] * px + c.T[9] * py + c.T[10] * pz + c.T[11];
+    const float ix = c.K[0] * cx + c.K[1] * cy + c.K[2] * cz + c.K[3];
+    const float iy = c.K[4] * cx + c.K[5] * cy + c.K[6] * cz + c.K[7];
+    const float iz = c.K[8] * cx + c.K[9] * cy + c.K[10] * cz + c.K[11];
+    const float sc = dehom(iz);
+    const float u = ix * sc, vv = iy * sc;
+    const float dep = iz - c.K[11];
+    const float bin = -0.5f + 0.5f * sqrtf(1.f + 8.f * (dep - dmin) / bin_size);
+    // ida (4x4) on (u, v, bin, 1), de-homogenised
+    const float gx = c.ida[0] * u + c.ida[1] * vv + c.ida[2] * bin + c.ida[3];
+    const float gy = c.ida[4] * u + c.ida[5] * vv + c.ida[6] * bin + c.ida[7];
+    const float gz = c.ida[8] * u + c.ida[9] * vv + c.ida[10] * bin + c.ida[11];
+    const float gw = c.ida[12] * u + c.ida[13] * vv + c.ida[14] * bin + c.ida[15];
+    const float s2 = dehom(gw);
+    float nx = gx * s2 / (img_w - 1.f) * 2.f - 1.f;
+    float ny = gy * s2 / (img_h - 1.f) * 2.f - 1.f;
+    float nz = gz * s2 / ((float)Dn - 1.f) * 2.f - 1.f;
+    if (!isfinite(nx)) nx = -2.f;
+    if (!isfinite(ny)) ny = -2.f;
+    if (!isfinite(nz)) nz = -2.f;
+    // grid_sample, align_corners=False: pixel = ((g + 1) * size - 1) / 2
+    const float fx = ((nx + 1.f) * w - 1.f) * 0.5f;
+    const float fy = ((ny + 1.f) * h - 1.f) * 0.5f;
+    const float fz = ((nz + 1.f) * Dn - 1.f) * 0.5f;
+    const float x0f = floorf(fx), y0f = floorf(fy), z0f = floorf(fz);
+    const int x0 = (int)x0f, y0 = (int)y0f, z0 = (int)z0f;
+    const float tx = fx - x0f, ty = fy - y0f, tz = fz - z0f;
+    const float* vol = depth + (long long)v * Dn * h * w;
+    float f = 0.f, m = 0.f;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
+          if (xx >= 0 && xx < w && yy >= 0 && yy < h && zz >= 0 && zz < Dn) {
+            const float wgt = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
+            f += wgt * __ldg(vol + ((long long)zz * h + yy) * w + xx);
+            m += wgt;
+          }
+        }
+    fsum += f;
+    msum += m;
+  }
+  float r = fsum;
+  if (V > 1 && mean_mode && msum > 0.f) r = fsum / msum;
+  long long no = n;
+  if (perm_xzy) no = ((long long)i * Z + k) * Y + j;  // x3ds_depth.permute(0,1,2,4,3) (OccDepth.py:337)
+  out[no] = r;
+}
+
+// softmax over C planar channels per position: in/out [B][C][S] fp32
+__global__ void softmax_planar_kernel(const float* __restrict__ in, float* __restrict__ out, int C, long long S,
+                                      long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long b = i / S, s = i % S;
+  const float* p = in + b * C * S + s;
+  float* o = out + b * C * S + s;
+  float m = -INFINITY;
+  for (int c = 0; c < C; ++c) m = fmaxf(m, p[(long long)c * S]);
+  float sum = 0.f;
+  for (int c = 0; c < C; ++c) sum += expf(p[(long long)c * S] - m);
+  const float inv = 1.f / sum;
+  for (int c = 0; c < C; ++c) o[(long long)c * S] = expf(p[(long long)c * S] - m) * inv;
+}
+
+// out[b][o] = act(bias[o] + sum_i w[o][i] * in[b][i]); one warp per output
+__global__ void fc_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                          float* __restrict__ out, int n_in, int n_out, int act) {
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  if (o >= n_out) return;
+  float s = 0.f;
+  for (int i = lane; i < n_in; i += 32) s = fmaf(w[(long long)o * n_in + i], in[(long long)b * n_in + i], s);
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+  if (lane == 0) out[(long long)b * n_out + o] = apply_act(s + bias[o], act);
+}
+
+// x[b][pos][c] *= gate[b][c]  (channels-last bf16, C % 8 == 0)
+__global__ void channel_scale_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ gate, long long S, int C,
+                                     int cstride, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = (int)(i % (C / 8));
+  const long long pos = i / (C / 8);
+  const long long b = pos / S;
+  __nv_bfloat16* p = x + pos * cstride + cv * 8;
+  float v[8];
+  unpack8(*reinterpret_cast<const uint4*>(p), v);
+  const float* g = gate + b * C + cv * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] *= g[k];
+  *reinterpret_cast<uint4*>(p) = pack8(v);
+}
+
+}  // namespace
+
+extern "C" int occd_frustum_sample_fwd(const float* depth, const float* cams, int V, int Dn, int h, int w, int X, int Y,
+                                       int Z, float img_w, float img_h, float dmin, float dmax, int mean_mode,
+                                       float* out, int perm_xzy, void* stream) {
+  OCCD_CHECK_ARG(depth && cams && out && V >= 1 && Dn > 1 && h > 0 && w > 0 && X > 0 && Y > 0 && Z > 0,
+                 "occd_frustum_sample_fwd: args");
+  const float bin_size = 2.f * (dmax - dmin) / ((float)Dn * (1.f + (float)Dn));
+  const long long N = (long long)X * Y * Z;
+  frustum_sample_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      depth, reinterpret_cast<const FrustumCam*>(cams), V, Dn, h, w, X, Y, Z, img_w, img_h, dmin, bin_size, mean_mode,
+      out, perm_xzy);
+  OCCD_CHECK_LAUNCH();
+  return OCCD_OK;
+}
+
+extern "C" int occd_softmax_planar(const float* in, float* out, long long B, int C, long long S, void* stream) {
+  OCCD_CHECK_ARG(in && out && B > 0 && C > 0 && S > 0, "occd_softmax_planar: args");
+  const long long total = B * S;
+  softmax_planar_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, out, C, S, total);
+  OCCD_CHECK_LAUNCH();
+  return OCCD_OK;
+}
+
+extern "C" int occd_fc_fwd(const float* in, const float* w, const float* bias, float* out, int B, int n_in, int n_out,
+                           int act, void* stream) {
+  OCCD_CHECK_ARG(in && w && bias && out && B > 0 && n_in > 0 && n_out > 0, "occd_fc_fwd: args");
+  fc_kernel<<<dim3((n_out + 3) / 4, B), 128, 0, (cudaStream_t)stream>>>(in, w, bias, out, n_in, n_out, act);
+  OCCD_CHECK_LAUNCH();
+  return OCCD_OK;
+}
+
+extern "C" int occd_channel_scale(void* x, const float* gate, long long B, long long S, int C, int cstride,
+                                  void* stream) {
+  OCCD_CHECK_ARG(x && gate && B > 0 && S > 0 && C > 0 && C % 8 == 0 && cstride % 8 == 0 && cstride >= C,
+                 "occd_channel_scale: args");
+  const long long total = B * S * (C / 8);
+  channel_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (__nv_bfloat16*)x, gate, S, C, cstride, total);
+  OCCD_CHECK_LAUNCH();
+  return OCCD_OK;
+}

@@ -21,10 +21,24 @@ def _round_up(a, b):
 
 
 def default_impl():
-    v = os.environ.get("OCCDEPTH_CONV_IMPL", "tc").lower()
-    if v not in ("tc", "simt"):
-        raise ValueError("OCCDEPTH_CONV_IMPL must be 'tc' or 'simt'")
-    return _lib.CONV_IMPL_TC if v == "tc" else _lib.CONV_IMPL_SIMT
+    """'auto' (default): halo-tile tcgen05 kernel where the shape qualifies, else the per-tap tcgen05 kernel;
+    'tc' / 'halo' / 'simt' force one implementation (simt = CUDA-core cross-check)."""
+    v = os.environ.get("OCCDEPTH_CONV_IMPL", "auto").lower()
+    if v not in ("auto", "tc", "simt", "halo"):
+        raise ValueError("OCCDEPTH_CONV_IMPL must be 'auto', 'tc', 'halo' or 'simt'")
+    return {"auto": None, "tc": _lib.CONV_IMPL_TC, "simt": _lib.CONV_IMPL_SIMT, "halo": _lib.CONV_IMPL_HALO}[v]
+
+
+def halo_eligible(srcs, taps, stride, omul, out_dims, Cout_pad, weight_buf):
+    """shape test mirroring build_halo_plan (csrc/conv.cu): stride-1 'same' conv, {-d,0,d} taps, few channels"""
+    if len(srcs) != 1 or weight_buf is not None or len(taps) < 3 or len(taps) > 27:
+        return False
+    if tuple(stride) != (1, 1, 1) or tuple(omul) != (1, 1, 1) or tuple(out_dims) != tuple(srcs[0].dims[1:]):
+        return False
+    if srcs[0].C > 64 or Cout_pad > 64:
+        return False
+    offs = {abs(o) for t in taps for o in t[1:] if o}
+    return len(offs) == 1
 
 
 def require_cuda(t, what):
@@ -140,7 +154,13 @@ class ConvOp:
         OD, OH, OW = out_dims
         fd = tuple(full_dims) if full_dims is not None else (OD, OH, OW)
         d = _lib.ConvDesc()
-        d.impl = default_impl() if impl is None else impl
+        if impl is None:
+            impl = default_impl()
+        auto = impl is None
+        if auto:
+            impl = (_lib.CONV_IMPL_HALO if halo_eligible(srcs, taps, stride, omul, out_dims, Cout_pad, weight_buf)
+                    else _lib.CONV_IMPL_TC)
+        d.impl = impl
         d.n_src = len(srcs)
         for i, s in enumerate(srcs):
             d.src[i] = s.ptr
@@ -179,8 +199,12 @@ class ConvOp:
         self.flops = 2 * B * OD * OH * OW * Cout * sum(srcs[t[0]].C for t in taps)
         h = C.c_void_p()
         rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
+        if rc != 0 and auto and d.impl == _lib.CONV_IMPL_HALO:
+            d.impl = _lib.CONV_IMPL_TC      # shape did not fit the halo scheme: per-tap tcgen05 kernel
+            rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
         _lib.check(rc, "occd_conv_plan_create(%s)" % name)
         self.handle = h
+        self.impl = d.impl
 
     def info(self):
         arr = (C.c_int * 8)()

@@ -180,7 +180,10 @@ class OccDepth(_Base, B200Module):
         plan.run()
         res = _to_planar(out, False)
         # tensors written directly by kernels live in plan-owned static buffers: hand out copies
-        return {k: (v.clone() if isinstance(out[k], torch.Tensor) else v) for k, v in res.items()}
+        res = {k: (v.clone() if isinstance(out[k], torch.Tensor) else v) for k, v in res.items()}
+        if self.with_depth_gt and self.trans_2d_to_3d == "flosp_depth":
+            res["depth_pred"] = self.flosp_depth.depth_prob().clone()          # OccDepth.py:374-375
+        return res
 
     def step(self, *a, **k):
         raise NotImplementedError("occdepth_b200 implements OccDepth.forward only (training is out of scope)")

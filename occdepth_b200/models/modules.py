@@ -15,13 +15,25 @@ from .DDR import Bottleneck3D
 def _emit_aspp(plan, m, x, out=None, name="aspp"):
     """relu( sum_i bn2_i(conv2_i(relu(bn1_i(conv1_i(x))))) + x ): 3 launches for conv1, ONE launch for the three
     conv2 branches (81 taps, one TMEM accumulator) with the residual + ReLU in its epilogue."""
-    ts, ws, bs = [], [], None
+    ts, ws, b2s, bs = [], [], [], None
     for i, dl in enumerate(m.conv_list):
         w, b = fold_bn(m.conv1[i].weight, m.conv1[i].bias, m.bn1[i])
         ts.append(plan.conv(x, w, b, padding=dl, dilation=dl, act="relu", name="%s.conv1.%d" % (name, i)))
         w2, b2 = fold_bn(m.conv2[i].weight, m.conv2[i].bias, m.bn2[i])
         ws.append(w2)
+        b2s.append(b2)
         bs = b2 if bs is None else bs + b2
+    from ..engine import default_impl
+    if x.C <= 64 and default_impl() is None:
+        # few channels (the full-resolution head): three halo-tile launches chained through the residual input
+        # (partial sums stored as bf16) beat one 81-tap launch of the per-tap kernel by ~2.5x
+        y = None
+        n = len(ts)
+        for i, dl in enumerate(m.conv_list):
+            last = i == n - 1
+            y = plan.conv(ts[i], ws[i], b2s[i], padding=dl, dilation=dl, act="relu" if last else "none", res1=y,
+                          res2=x if last else None, out=out if last else None, name="%s.conv2.%d" % (name, i))
+        return y
     return plan.conv_multi(ts, ws, bs, list(m.conv_list), list(m.conv_list), act="relu", res1=x, out=out,
                            name=name + ".conv2")
 
@@ -90,19 +102,23 @@ class SegmentationHeadCascadeCLS(B200Module):
         w, b = fold_bn(self.conv0.weight, self.conv0.bias, None)
         x0 = plan.conv(x, w, b, padding=1, act="relu", name="head.conv0")
         B, D, H, W = x0.dims
-        cat = plan.alloc(B, D, H, W, planes + 2)             # torch.cat([x_in, softmax(x_occ)]) buffer
-        x1 = _emit_aspp(plan, self, x0, out=cat.window(0, planes), name="head.aspp")
+        x1 = _emit_aspp(plan, self, x0, name="head.aspp")
         w, b = fold_bn(self.occ_classes.weight, self.occ_classes.bias, None)
         x_occ = _planar_out(plan, x1, 2)
         plan.conv(x1, w, b, padding=1, out1=x_occ, out1_mode="planar", no_out0=True, name="head.occ_classes")
+        # torch.cat([x_in, softmax(x_occ)]) is never built: conv_classes is split along its input channels into
+        # the `planes`-channel part (k-chunk of 32/64 channels) and the 2 softmax channels (k-chunk of 16); the
+        # second launch adds the first one's result in its epilogue and writes the NCDHW fp32 logits
         L = _lib.lib()
         S = D * H * W
-        plan.add(FnOp(lambda st: L.occd_softmax_planar_to_cl(x_occ.data_ptr(), cat.ptr, B, 2, S, cat.cstride,
-                                                            cat.coff + planes, st),
-                      "occd_softmax_planar_to_cl", keep=(x_occ, cat)))
+        sm = plan.alloc(B, D, H, W, 2)
+        plan.add(FnOp(lambda st: L.occd_softmax_planar_to_cl(x_occ.data_ptr(), sm.ptr, B, 2, S, sm.cstride, sm.coff,
+                                                            st), "occd_softmax_planar_to_cl", keep=(x_occ, sm)))
         w, b = fold_bn(self.conv_classes.weight, self.conv_classes.bias, None)
+        part = plan.conv(x1, w[:, :planes].contiguous(), b, padding=1, name="head.conv_classes.a")
         logits = _planar_out(plan, x1, w.shape[0])
-        plan.conv(cat, w, b, padding=1, out1=logits, out1_mode="planar", no_out0=True, name="head.conv_classes")
+        plan.conv(sm, w[:, planes:].contiguous(), torch.zeros_like(b), padding=1, res1=part, out1=logits,
+                  out1_mode="planar", no_out0=True, name="head.conv_classes.b")
         return logits, x_occ
 
     def forward(self, x_in):

@@ -352,9 +352,113 @@ def occdepth_forward(sd, batch, cfg):
         x3ds.append(lift_flosp(xv, batch["projected_pix_%d" % ps][i], batch["fov_mask_%d" % ps][i],
                                cfg["project_res"], cfg["full_scene_size"], cfg["dataset"], ps))
     x3d = torch.stack(x3ds)
+    extra = {}
+    if cfg.get("trans_2d_to_3d", "flosp") == "flosp_depth":                      # OccDepth.py:299-339
+        conf = cfg["flosp_depth_conf"]
+        layer = "1_%d" % conf["downsample_factor"]
+        nv = 1 if cfg["dataset"] == "NYU" else n_views
+        img_feat = torch.stack([x_rgb[j][layer] for j in range(nv)], 1)
+        vox_origin = batch.get("vox_origin") if cfg["dataset"] == "NYU" else None
+        prior, depth_pred = flosp_depth(sd, "flosp_depth", img_feat, batch["cam_k"], batch["T_velo_2_cam"],
+                                        batch["ida_mats"], conf, vox_origin)
+        if cfg["dataset"] == "NYU":
+            prior = prior.permute(0, 1, 2, 4, 3)
+        x3d = x3d * prior * 100
+        if cfg.get("with_depth_gt", False):
+            extra["depth_pred"] = depth_pred
     ctx = cfg["context_prior"] and not cfg.get("infer_mode", False)             # OccDepth.py:82-84
     if cfg["dataset"] == "NYU":
-        return unet3d_nyu(sd, "net_3d_decoder", x3d, cfg["full_scene_size"], cfg.get("n_relations", 4), ctx,
-                          cfg["cascade_cls"], cfg.get("infer_mode", False))
-    return unet3d_kitti(sd, "net_3d_decoder", x3d, cfg["full_scene_size"], ps, ctx, cfg["cascade_cls"],
-                        cfg.get("occluded_cls", False), cfg.get("infer_mode", False))
+        out = unet3d_nyu(sd, "net_3d_decoder", x3d, cfg["full_scene_size"], cfg.get("n_relations", 4), ctx,
+                         cfg["cascade_cls"], cfg.get("infer_mode", False))
+    else:
+        out = unet3d_kitti(sd, "net_3d_decoder", x3d, cfg["full_scene_size"], ps, ctx, cfg["cascade_cls"],
+                           cfg.get("occluded_cls", False), cfg.get("infer_mode", False))
+    out.update(extra)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# A4/A5: FlospDepth -- flosp_depth.py:201-257 (DepthNet), :456-608 (forward); f2v/frustum_grid_generator.py:70-152
+def depth_net(sd, p, x, cam_k4):
+    """x (BV, C, h, w); cam_k4 (BV, 4, 4) intrinsics.  flosp_depth.py:232-257"""
+    inv = torch.inverse(cam_k4)
+    sps = torch.norm(torch.stack([inv[..., 0, 0], inv[..., 1, 1]], dim=-1), dim=-1).reshape(-1, 1) * 1000.0
+    x = F.relu(_bn(sd, p + ".reduce_conv.1", _conv2d(sd, p + ".reduce_conv.0", x, 1, 1)))
+    h = F.linear(F.relu(F.linear(sps, sd[p + ".mlp.fc1.weight"], sd[p + ".mlp.fc1.bias"])),
+                 sd[p + ".mlp.fc2.weight"], sd[p + ".mlp.fc2.bias"])[..., None, None]
+    g = _conv2d(sd, p + ".se.conv_expand", F.relu(_conv2d(sd, p + ".se.conv_reduce", h)))
+    x = x * torch.sigmoid(g)
+    for i in range(3):
+        q = "%s.depth_conv.%d" % (p, i)
+        y = F.relu(_bn(sd, q + ".bn1", _conv2d(sd, q + ".conv1", x, 1, 1)))
+        x = F.relu(_bn(sd, q + ".bn2", _conv2d(sd, q + ".conv2", y, 1, 1)) + x)
+    return _conv2d(sd, p + ".depth_pred", x)
+
+
+def frustum_grid(grid_size, pc_min, pc_max, lidar_to_cam, cam_k4, ida, image_hw, num_bins, dmin, dmax):
+    """frustum_grid_generator.py:20-152 for one camera: -> (1, X, Y, Z, 3) normalised sampling grid."""
+    X, Y, Z = grid_size
+    vs = (pc_max - pc_min) / torch.tensor([X, Y, Z], dtype=torch.float32)
+    i, j, k = torch.meshgrid(torch.arange(X, dtype=torch.float32), torch.arange(Y, dtype=torch.float32),
+                             torch.arange(Z, dtype=torch.float32), indexing="ij")
+    vox = torch.stack([i, j, k], -1) + 0.5                                       # :31-42
+    G = torch.eye(4)
+    G[0, 0], G[1, 1], G[2, 2] = vs
+    G[:3, 3] = pc_min
+    trans = lidar_to_cam @ G                                                     # :95
+    ph = F.pad(vox, [0, 1], value=1.0) @ trans.t()                                # kornia.transform_points :102
+    z = ph[..., 3:]
+    cam = ph[..., :3] * torch.where(z.abs() > 1e-8, 1.0 / (z + 1e-8), torch.ones_like(z))
+    I_C = cam_k4[:3, :]
+    pt = F.pad(cam, [0, 1], value=1.0) @ I_C.t()                                  # transform_utils.py:16-21
+    zz = pt[..., 2:]
+    img = pt[..., :2] * torch.where(zz.abs() > 1e-8, 1.0 / (zz + 1e-8), torch.ones_like(zz))
+    depth = pt[..., 2] - I_C[2, 3]                                                # :24
+    bin_size = 2 * (dmax - dmin) / (num_bins * (1 + num_bins))                    # depth_utils.py:24-26
+    idx = -0.5 + 0.5 * torch.sqrt(1 + 8 * (depth - dmin) / bin_size)
+    fg = torch.cat([img, idx.unsqueeze(-1)], -1)
+    fh = F.pad(fg, [0, 1], value=1.0) @ ida.t()                                   # :113-114
+    w = fh[..., 3:]
+    fg = fh[..., :3] * torch.where(w.abs() > 1e-8, 1.0 / (w + 1e-8), torch.ones_like(w))
+    shape = torch.tensor([float(image_hw[1]), float(image_hw[0]), float(num_bins)])   # flipped [D,H,W], :139-145
+    fg = fg / (shape - 1) * 2 - 1
+    fg[~torch.isfinite(fg)] = -2                                                  # :148-150
+    return fg.unsqueeze(0)
+
+
+def flosp_depth(sd, p, img_feat, cam_k, T_velo_2_cam, ida_mats, conf, vox_origin=None):
+    """FlospDepth.forward (flosp_depth.py:456-608).  img_feat (B, n_cams, C, h, w); returns (B,1,X,Y,Z), depth."""
+    B, V, C, h, w = img_feat.shape
+    ps = conf["project_scale"]
+    if vox_origin is not None:                                                    # :466-518 (NYU)
+        o = [float(vox_origin[0][k]) for k in range(3)]
+        bounds = [[o[0], o[0] + 4.8, 0.08], [o[1], o[1] + 4.8, 0.08], [o[2], o[2] + 2.88, 0.08]]
+    else:
+        bounds = [conf["x_bound"], conf["y_bound"], conf["z_bound"]]
+    vn = [int((b[1] - b[0]) / b[2] / ps) for b in bounds]
+    pc_min = torch.tensor([b[0] for b in bounds], dtype=torch.float32)
+    pc_max = torch.tensor([b[1] for b in bounds], dtype=torch.float32)
+    d_bound = conf["d_bound"]
+    Dn = int((d_bound[1] - d_bound[0]) / d_bound[2])
+    K4 = torch.zeros(B, V, 4, 4)
+    K4[:, :, :3, :3] = torch.stack(cam_k).to(torch.float32)
+    K4[:, :, 3, 3] = 1
+    T = torch.stack(T_velo_2_cam).to(torch.float32)
+    ida = torch.stack(ida_mats)
+    logits = depth_net(sd, p + ".depth_net.0", img_feat.reshape(B * V, C, h, w), K4.reshape(B * V, 4, 4))
+    depth = logits.softmax(1).reshape(B, V, 1, Dn, h, w)                          # :548-559
+    feats, masks = [], []
+    for v in range(V):
+        grids = torch.cat([frustum_grid(vn, pc_min, pc_max, T[b, v], K4[b, v], ida[b, v], conf["final_dim"], Dn,
+                                        d_bound[0], d_bound[1]) for b in range(B)], 0)
+        feats.append(F.grid_sample(depth[:, v], grids, mode="bilinear", padding_mode="zeros", align_corners=False))
+        masks.append(F.grid_sample(torch.ones_like(depth[:, v]), grids, mode="bilinear", padding_mode="zeros",
+                                   align_corners=False))
+    if V == 1:
+        agg = feats[0]
+    else:
+        agg = sum(feats)
+        if conf.get("agg_voxel_mode", "mean") == "mean":
+            m = sum(masks)
+            agg = torch.where(m > 0, agg / m, agg)                                # :594-602
+    return agg, depth.squeeze(2)

@@ -13,3 +13,5 @@ def convert_points_from_homogeneous(points, eps=1e-8):
     mask = torch.abs(z_vec) > eps
     scale = torch.where(mask, 1.0 / (z_vec + eps), torch.ones_like(z_vec))
     return scale * points[..., :-1]
+
+from .geometry.linalg import transform_points  # noqa: E402,F401  (kornia 0.5.0 re-exports it at top level)

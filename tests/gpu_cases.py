@@ -110,3 +110,16 @@ CONV_CASES = {
     "k1_sigmoid_b2": dict(B=2, k=(1, 1, 1), Cin=256, Cout=512, dims=(4, 4, 2), act="sigmoid", planar=True),
     "k3_respost": dict(res=True, res_post=True),
 }
+
+
+HALO_CASES = {
+    "h_c32_d1": dict(Cin=32, Cout=32, dims=(6, 10, 12)),
+    "h_c32_d2": dict(Cin=32, Cout=32, dims=(9, 11, 14), dil=(2, 2, 2)),
+    "h_c32_d3_res": dict(Cin=32, Cout=32, dims=(8, 13, 32), dil=(3, 3, 3), res=True),
+    "h_c16_n16": dict(Cin=16, Cout=16, dims=(5, 9, 16)),
+    "h_c64_n32_pre": dict(Cin=64, Cout=32, dims=(6, 9, 20), pre=True),
+    "h_c32_n2_planar": dict(Cin=32, Cout=2, dims=(6, 10, 32), act="none", planar=True),
+    "h_2d_c48": dict(k=(1, 3, 3), Cin=48, Cout=40, dims=(1, 21, 70), act="leaky"),
+    "h_big": dict(Cin=32, Cout=32, dims=(20, 40, 32), dil=(1, 1, 1)),
+    "h_big_d3": dict(Cin=32, Cout=32, dims=(20, 40, 32), dil=(3, 3, 3)),
+}

@@ -44,3 +44,11 @@ def test_conv_large_vs_simt():
     torch.cuda.synchronize()
     a, c = outs[0].buf.float(), outs[1].buf.float()
     assert float((a - c).abs().max()) <= TOL * float(c.abs().max())
+
+
+@pytest.mark.parametrize("case", sorted(G.HALO_CASES))
+def test_conv_halo(case):
+    """halo-tile tcgen05 kernel (row-shifted swizzled smem views, sub-sampled TMA for dilation)"""
+    from occdepth_b200 import _lib
+    e, info = G.conv_case(_lib.CONV_IMPL_HALO, **G.HALO_CASES[case])
+    assert e <= TOL, (e, info)

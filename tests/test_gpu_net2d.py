@@ -66,3 +66,34 @@ def test_occdepth_forward_small(dataset):
         assert _rel(got[k], want[k]) <= TOL_E2E, (k, _rel(got[k], want[k]))
     agree = (got["ssc_logit"].argmax(1).cpu() == want["ssc_logit"].argmax(1)).float().mean()
     assert agree > 0.9, float(agree)
+
+
+def _flosp_conf(H, W):
+    import copy
+    from occdepth_b200.models.flosp_depth import flosp_depth_conf_map
+    conf = copy.deepcopy(flosp_depth_conf_map["kitti"])
+    conf.update(scene_size=(64, 64, 8), project_scale=2, return_depth=True, final_dim=(H, W), output_channels=16,
+                x_bound=[0, 12.8, 0.2], y_bound=[-6.4, 6.4, 0.2], z_bound=[-2, -0.4, 0.2], d_bound=[2.0, 18.0, 0.5],
+                depth_net_conf=dict(in_channels=16, mid_channels=32))
+    return conf
+
+
+def test_flosp_depth_module():
+    """FlospDepth drop-in (DepthNet on tcgen05 + fused frustum sampling kernel) vs the CPU oracle"""
+    from occdepth_b200.models.flosp_depth import FlospDepth
+    torch.manual_seed(0)
+    H, W = 96, 320
+    conf = _flosp_conf(H, W)
+    m = synth.seed_weights_(FlospDepth(**conf), 5).eval()
+    K, Ts = synth.kitti_calib(W, H, focal=220.0)
+    cam_k = [torch.from_numpy(K).unsqueeze(0).repeat(2, 1, 1)]
+    T = [torch.stack([torch.from_numpy(t) for t in Ts])]
+    ida = [torch.eye(4).unsqueeze(0).repeat(2, 1, 1)]
+    feat = torch.randn(1, 2, 16, H // 8, W // 8)
+    with torch.no_grad():
+        want, want_d = OF.flosp_depth({"f." + k: v.clone() for k, v in m.state_dict().items()}, "f", feat, cam_k, T, ida,
+                                      conf)
+        got, got_d = m.cuda()(feat.cuda(), cam_k, T, ida, None)
+    assert float((want > 0).float().mean()) > 0.2
+    assert _rel(got_d, want_d) <= 3e-2, _rel(got_d, want_d)
+    assert _rel(got, want) <= 3e-2, _rel(got, want)

@@ -124,3 +124,29 @@ def test_occdepth_forward_small(ref):
     assert set(got.keys()) == set(want.keys())
     for k in want:
         _close(got[k], want[k], rtol=2e-3, atol=2e-4)
+
+
+def test_flosp_depth(ref):
+    """FlospDepth (DepthNet + frustum grid + trilinear sampling + masked mean), kitti geometry, 2 cameras"""
+    import copy
+    import occdepth.models.flosp_depth as rfd
+    torch.manual_seed(0)
+    conf = copy.deepcopy(rfd.flosp_depth_conf_map["kitti"])
+    H, W = 96, 320
+    conf.update(scene_size=(64, 64, 8), project_scale=2, return_depth=True, final_dim=(H, W), output_channels=16,
+                x_bound=[0, 12.8, 0.2], y_bound=[-6.4, 6.4, 0.2], z_bound=[-2, -0.4, 0.2], d_bound=[2.0, 18.0, 0.5],
+                depth_net_conf=dict(in_channels=16, mid_channels=32))
+    with ref_import.quiet():
+        m = ref.flosp_depth.FlospDepth(**conf).eval()
+    synth.seed_weights_(m, 5)
+    K, Ts = synth.kitti_calib(W, H, focal=220.0)
+    cam_k = [torch.from_numpy(K).unsqueeze(0).repeat(2, 1, 1)]
+    T = [torch.stack([torch.from_numpy(t) for t in Ts])]
+    ida = [torch.eye(4).unsqueeze(0).repeat(2, 1, 1)]
+    feat = torch.randn(1, 2, 16, H // 8, W // 8)
+    with torch.no_grad():
+        want, want_d = m(feat, cam_k, T, ida, None)
+        got, got_d = OF.flosp_depth({"f." + k: v for k, v in m.state_dict().items()}, "f", feat, cam_k, T, ida, conf)
+    assert float((want > 0).float().mean()) > 0.2     # the frustum actually covers part of the grid
+    _close(got_d, want_d, rtol=1e-4, atol=1e-6)
+    _close(got, want, rtol=1e-3, atol=1e-5)

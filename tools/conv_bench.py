@@ -18,6 +18,8 @@ SHAPES = {
     "up1_conv2": ((1, 376, 1370), 80, 80, (1, 3, 3), 1, "leaky"),
     "up2_conv2": ((1, 188, 685), 160, 160, (1, 3, 3), 1, "leaky"),
     "up16_conv1": ((1, 24, 86), 2784, 1280, (1, 3, 3), 1, "leaky"),
+    "head_c32_d2": ((256, 256, 32), 32, 32, (3, 3, 3), 2, "relu"),
+    "head_c32_n2": ((256, 256, 32), 32, 2, (3, 3, 3), 1, "none"),
     "x_c32_n32": ((256, 256, 16), 32, 32, (3, 3, 3), 1, "relu"),
     "x_c64_n32": ((256, 256, 16), 64, 32, (3, 3, 3), 1, "relu"),
     "x_c32_n64": ((256, 256, 16), 32, 64, (3, 3, 3), 1, "relu"),
@@ -39,7 +41,8 @@ def main():
         w = torch.randn(co, ci, *k, device=dev) / (ci * k[0] * k[1] * k[2]) ** 0.5
         b = torch.randn(co, device=dev)
         pad = tuple(dl * (kk - 1) // 2 for kk in k)
-        plan.conv(x, w, b, padding=pad, dilation=dl, act=act, name=n)
+        impl = {"tc": 0, "simt": 1, "halo": 2}.get(os.environ.get("BENCH_IMPL", ""), None)
+        plan.conv(x, w, b, padding=pad, dilation=dl, act=act, name=n, impl=impl)
         for _ in range(3):
             plan.run()
         torch.cuda.synchronize()

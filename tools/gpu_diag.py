@@ -14,8 +14,10 @@ def run_one(kind, name):
     import torch
     import gpu_cases as G
     from occdepth_b200 import _lib
-    impl = _lib.CONV_IMPL_TC if kind == "tc" else _lib.CONV_IMPL_SIMT
-    if name == "convT":
+    impl = {"tc": _lib.CONV_IMPL_TC, "simt": _lib.CONV_IMPL_SIMT, "halo": _lib.CONV_IMPL_HALO}[kind]
+    if kind == "halo":
+        e, info = G.conv_case(impl, **G.HALO_CASES[name])
+    elif name == "convT":
         e, info = G.convT_case(impl)
     elif name == "multi":
         e, info = G.multi_case(impl)
@@ -53,7 +55,7 @@ def main():
             lines.append("simt many rc=%d %s" % (r.returncode, r.stderr[-500:]))
             print(lines[-1], flush=True)
     for kind in kinds:
-        for name in list(G.CONV_CASES) + ["convT", "multi"]:
+        for name in (list(G.HALO_CASES) if kind == "halo" else list(G.CONV_CASES) + ["convT", "multi"]):
             try:
                 r = subprocess.run([sys.executable, __file__, "one", kind, name], capture_output=True, text=True,
                                    timeout=120)
