@@ -170,8 +170,8 @@ class FlospDepth(B200Module):
         h2 = fc(h1, dn.mlp.fc2.weight, dn.mlp.fc2.bias, mid, mid, _lib.ACT_NONE, "depthnet.mlp.fc2")
         g1 = fc(h2, dn.se.conv_reduce.weight, dn.se.conv_reduce.bias, mid, mid, _lib.ACT_RELU, "depthnet.se.reduce")
         gate = fc(g1, dn.se.conv_expand.weight, dn.se.conv_expand.bias, mid, mid, _lib.ACT_SIGMOID, "depthnet.se.gate")
-        plan.add(FnOp(lambda st: L.occd_channel_scale(x.ptr, gate.data_ptr(), BV, h * w, mid, x.cstride, st),
-                      "depthnet.se.scale", keep=(x, gate)))
+        plan.add(FnOp(lambda st, xg=x: L.occd_channel_scale(xg.ptr, gate.data_ptr(), BV, h * w, mid, xg.cstride, st),
+                      "depthnet.se.scale", keep=(x, gate)))      # xg bound now: `x` is rebound by the blocks below
         for i, blk in enumerate(dn.depth_conv):
             w1, b1 = fold_bn(blk.conv1.weight, None, blk.bn1)
             y = plan.conv(x, w1.unsqueeze(2), b1, padding=(0, 1, 1), act="relu", name="depthnet.block%d.conv1" % i)

@@ -120,6 +120,8 @@ HALO_CASES = {
     "h_c64_n32_pre": dict(Cin=64, Cout=32, dims=(6, 9, 20), pre=True),
     "h_c32_n2_planar": dict(Cin=32, Cout=2, dims=(6, 10, 32), act="none", planar=True),
     "h_2d_c48": dict(k=(1, 3, 3), Cin=48, Cout=40, dims=(1, 21, 70), act="leaky"),
+    "h_2d_b2_res": dict(B=2, k=(1, 3, 3), Cin=32, Cout=32, dims=(1, 12, 40), res=True),
+    "h_3d_b3": dict(B=3, Cin=16, Cout=32, dims=(4, 6, 8)),
     "h_big": dict(Cin=32, Cout=32, dims=(20, 40, 32), dil=(1, 1, 1)),
     "h_big_d3": dict(Cin=32, Cout=32, dims=(20, 40, 32), dil=(3, 3, 3)),
 }

@@ -97,3 +97,46 @@ def test_flosp_depth_module():
     assert float((want > 0).float().mean()) > 0.2
     assert _rel(got_d, want_d) <= 3e-2, _rel(got_d, want_d)
     assert _rel(got, want) <= 3e-2, _rel(got, want)
+
+
+def test_occdepth_forward_flosp_depth():
+    """OccDepth.forward with trans_2d_to_3d="flosp_depth" (the README-default configs): lift x depth prior x 100"""
+    from occdepth_b200.models.OccDepth import OccDepth
+    import occdepth_b200.models.flosp_depth.flosp_depth as fd
+    import copy
+    torch.manual_seed(0)
+    full, ps = (32, 32, 16), 2
+    H, W = 40, 96
+    saved = copy.deepcopy(fd.flosp_depth_conf_map["kitti"])
+    try:
+        fd.flosp_depth_conf_map["kitti"].update(final_dim=(H, W), x_bound=[0, 6.4, 0.2], y_bound=[-3.2, 3.2, 0.2],
+                                                z_bound=[-2, 1.2, 0.2], d_bound=[1.0, 9.0, 0.5])
+        cfg = synth.occdepth_cfg(full_scene_size=full, project_scale=ps, feature=32, feature_2d_oc=32, n_classes=8,
+                                 backbone_2d_name="tf_efficientnet_b3_ns", trans_2d_to_3d="flosp_depth",
+                                 use_stereo_depth_gt=True)
+        with ref_import.quiet():
+            m = OccDepth(["c"] * 8, torch.ones(8), full_scene_size=full, project_res=["1", "2", "4", "8"],
+                         config=cfg).eval()
+        conf = copy.deepcopy(m.flosp_depth_conf)
+    finally:
+        fd.flosp_depth_conf_map["kitti"].clear()
+        fd.flosp_depth_conf_map["kitti"].update(saved)
+    synth.seed_weights_(m, 9)
+    K, Ts = synth.kitti_calib(W, H, focal=60.0)
+    img = torch.randn(1, 2, 3, H, W)
+    N = 16 * 16 * 8
+    pix, fov = synth.random_indices(N, W, H, n_views=2, P=1, seed=5, margin=(10, 6))
+    batch = {"img": img, "projected_pix_2": [pix], "fov_mask_2": [fov],
+             "cam_k": [torch.from_numpy(K).unsqueeze(0).repeat(2, 1, 1)],
+             "T_velo_2_cam": [torch.stack([torch.from_numpy(t) for t in Ts])],
+             "ida_mats": [torch.eye(4).unsqueeze(0).repeat(2, 1, 1)]}
+    ocfg = dict(cfg)
+    ocfg.update(project_res=["1", "2", "4", "8"], flosp_depth_conf=conf, with_depth_gt=True)
+    with torch.no_grad():
+        want = OF.occdepth_forward({k: v.clone() for k, v in m.state_dict().items()}, batch, ocfg)
+        b2 = dict(batch)
+        b2["img"] = img.cuda()
+        got = m.cuda()(b2)
+    assert set(got.keys()) == set(want.keys())
+    for k in ("ssc_logit", "occ_logit", "depth_pred"):
+        assert _rel(got[k], want[k]) <= TOL_E2E, (k, _rel(got[k], want[k]))
