@@ -43,6 +43,7 @@ typedef struct {
   int h[OCCD_SFA_MAX_SCALES];
   int w[OCCD_SFA_MAX_SCALES];
   int div[OCCD_SFA_MAX_SCALES]; /* projected_pix // div (floor), OccDepth.py:286-294               */
+  long long vstride[OCCD_SFA_MAX_SCALES]; /* elements between consecutive views; 0 = dense (h*w*C)    */
   int n_scales;                 /* 1..4                                                            */
   int n_views;                  /* V, 1..4                                                         */
   int C;                        /* channels, multiple of 4 (f32) / 8 (bf16), <= 256                */
@@ -207,6 +208,11 @@ int occd_fc_fwd(const float* in, const float* w, const float* bias, float* out, 
                 int act, void* stream);
 /* x[b][pos][c] *= gate[b][c] in place (SELayer: x * gate(x_se), flosp_depth.py:195-199)            */
 int occd_channel_scale(void* x, const float* gate, long long B, long long S, int C, int cstride, void* stream);
+
+/* virtual right view for single-view RGB-D inputs: OccDepth.generate_virtual_img (OccDepth.py:233-260). */
+/* in/out: channels-last bf16 [B][h][w][cs]; depth: fp32 [dh][dw] of batch item 0; bf_scale = bf / scale_2d  */
+int occd_virtual_view_fwd(const void* in, void* out, const float* depth, int B, int h, int w, int C, int cs_in,
+                          int cs_out, int dh, int dw, float bf_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,7 @@ class SfaParams(C.Structure):
         ("h", C.c_int * MAX_SCALES),
         ("w", C.c_int * MAX_SCALES),
         ("div", C.c_int * MAX_SCALES),
+        ("vstride", C.c_longlong * MAX_SCALES),
         ("n_scales", C.c_int),
         ("n_views", C.c_int),
         ("C", C.c_int),
@@ -106,6 +107,7 @@ SYMBOLS = {
     "occd_softmax_planar": (C.c_int, [_vp, _vp, _ll, _i, _ll, _vp]),
     "occd_fc_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "occd_channel_scale": (C.c_int, [_vp, _vp, _ll, _ll, _i, _i, _vp]),
+    "occd_virtual_view_fwd": (C.c_int, [_vp, _vp, _vp] + [_i] * 8 + [_f, _vp]),
     "occd_upsample_bilinear_ac": (C.c_int, [_vp, _vp] + [_i] * 10 + [_vp]),
 }
 

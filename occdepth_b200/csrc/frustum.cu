@@ -175,3 +175,66 @@ extern "C" int occd_channel_scale(void* x, const float* gate, long long B, long 
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
+
+namespace {
+// Virtual right view from the left features and a depth map (NYU "virtual stereo"):
+// replaces OccDepth.generate_virtual_img (occdepth/models/OccDepth.py:233-260): F.interpolate(depth, bilinear,
+// align_corners=False) -> disparity bf/scale / depth (inf -> 0) -> base grid arange(-1,1,2/h) (pixel-CORNER
+// coordinates) shifted by disparity*2/w -> F.grid_sample(bilinear, border, align_corners=False).
+// The reference uses batch item 0's disparity for every item (:257); kept.
+__global__ void virtual_view_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                    const float* __restrict__ depth, int B, int h, int w, int CV, int cs_in,
+                                    int cs_out, int dh, int dw, float bf_scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * h * w * CV;
+  if (i >= total) return;
+  const int cv = (int)(i % CV);
+  long long p = i / CV;
+  const int x = (int)(p % w); p /= w;
+  const int y = (int)(p % h); p /= h;
+  const int b = (int)p;
+  // depth at (y, x) of the feature map: bilinear, align_corners=False (area_pixel_compute_source_index)
+  const float sy = fmaxf(((float)y + 0.5f) * ((float)dh / (float)h) - 0.5f, 0.f);
+  const float sx = fmaxf(((float)x + 0.5f) * ((float)dw / (float)w) - 0.5f, 0.f);
+  const int y0 = min((int)sy, dh - 1), x0 = min((int)sx, dw - 1);
+  const int y1 = min(y0 + 1, dh - 1), x1 = min(x0 + 1, dw - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  const float d = (1.f - ly) * ((1.f - lx) * depth[(long long)y0 * dw + x0] + lx * depth[(long long)y0 * dw + x1]) +
+                  ly * ((1.f - lx) * depth[(long long)y1 * dw + x0] + lx * depth[(long long)y1 * dw + x1]);
+  float dx = bf_scale / d;
+  if (isinf(dx)) dx = 0.f;
+  // grid = (-1 + 2x/w + dx*2/w, -1 + 2y/h); unnormalise (align_corners=False): ((g+1)*size - 1)/2
+  const float gx = -1.f + (float)x * (2.f / (float)w) + dx * 2.f / (float)w;
+  const float gy = -1.f + (float)y * (2.f / (float)h);
+  float fx = ((gx + 1.f) * (float)w - 1.f) * 0.5f;
+  float fy = ((gy + 1.f) * (float)h - 1.f) * 0.5f;
+  fx = fminf(fmaxf(fx, 0.f), (float)(w - 1));   // padding_mode="border": clip coordinates
+  fy = fminf(fmaxf(fy, 0.f), (float)(h - 1));
+  const int ix0 = (int)floorf(fx), iy0 = (int)floorf(fy);
+  const int ix1 = min(ix0 + 1, w - 1), iy1 = min(iy0 + 1, h - 1);
+  const float tx = fx - ix0, ty = fy - iy0;
+  const __nv_bfloat16* base = in + (long long)b * h * w * cs_in + cv * 8;
+  float a[8], bb[8], c[8], dd[8], o[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long long)iy0 * w + ix0) * cs_in)), a);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long long)iy0 * w + ix1) * cs_in)), bb);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long long)iy1 * w + ix0) * cs_in)), c);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long long)iy1 * w + ix1) * cs_in)), dd);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    o[k] = (1.f - ty) * ((1.f - tx) * a[k] + tx * bb[k]) + ty * ((1.f - tx) * c[k] + tx * dd[k]);
+  *reinterpret_cast<uint4*>(out + (((long long)b * h + y) * w + x) * cs_out + cv * 8) = pack8(o);
+}
+}  // namespace
+
+extern "C" int occd_virtual_view_fwd(const void* in, void* out, const float* depth, int B, int h, int w, int C,
+                                     int cs_in, int cs_out, int dh, int dw, float bf_scale, void* stream) {
+  OCCD_CHECK_ARG(in && out && depth && B > 0 && h > 0 && w > 0 && C > 0 && dh > 0 && dw > 0 && cs_in % 8 == 0 &&
+                 cs_out % 8 == 0, "occd_virtual_view_fwd: args");
+  const int CV = (C + 7) / 8;
+  OCCD_CHECK_ARG(CV * 8 <= cs_in && CV * 8 <= cs_out, "occd_virtual_view_fwd: channel window");
+  const long long total = (long long)B * h * w * CV;
+  virtual_view_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in, (__nv_bfloat16*)out, depth, B, h, w, CV, cs_in, cs_out, dh, dw, bf_scale);
+  OCCD_CHECK_LAUNCH();
+  return OCCD_OK;
+}

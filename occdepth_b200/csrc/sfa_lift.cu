@@ -46,6 +46,7 @@ struct SfaKParams {
   const void* feat[OCCD_SFA_MAX_SCALES];
   int h[OCCD_SFA_MAX_SCALES], w[OCCD_SFA_MAX_SCALES];
   int div[OCCD_SFA_MAX_SCALES], shift[OCCD_SFA_MAX_SCALES];
+  long long vstride[OCCD_SFA_MAX_SCALES];  // elements between views
   int n_scales, C, P;
   long long N;
   const long long* pix;
@@ -127,7 +128,7 @@ sfa_lift_kernel(const SfaKParams p) {
               const long long ys = floordiv64(xy.y, p.div[s], p.shift[s]);
               const long long idx = ys * ws + xs;
               if (idx >= 0 && idx < hw) {
-                const T* src = feat + ((long long)v * hw + idx) * p.C;
+                const T* src = feat + (long long)v * p.vstride[s] + idx * p.C;
 #pragma unroll
                 for (int j = 0; j < NV; ++j) {
                   const int c0 = (j * G + lane_g) * VEC;
@@ -289,7 +290,7 @@ sfa_lift_p1_kernel(const SfaKParams p) {
           else { xs = (int)floordiv64(x, p.div[s], -1); ys = (int)floordiv64(y, p.div[s], -1); }
           const long long idx = (long long)ys * p.w[s] + xs;
           const int hw = p.h[s] * p.w[s];
-          if (idx >= 0 && idx < hw) o = (v * hw + (int)idx);
+          if (idx >= 0 && idx < hw) o = (int)((long long)v * p.vstride[s] / p.C) + (int)idx;
         }
         off[v][s] = o;
       }
@@ -402,7 +403,7 @@ sfa_lift_p1_kernel(const SfaKParams p) {
 
 static bool sfa_fits_int32(const SfaKParams& kp, int n_views) {
   for (int s = 0; s < kp.n_scales; ++s)
-    if ((long long)n_views * kp.h[s] * kp.w[s] * kp.C >= (1LL << 31) || kp.n_scales > OCCD_SFA_MAX_SCALES) return false;
+    if ((long long)n_views * kp.vstride[s] >= (1LL << 31) || kp.n_scales > OCCD_SFA_MAX_SCALES) return false;
   return true;
 }
 
@@ -470,11 +471,13 @@ extern "C" int occd_sfa_lift_fwd(const occd_sfa_params* a, void* stream) {
   if (a->N == 0) return OCCD_OK;
   SfaKParams kp;
   for (int s = 0; s < OCCD_SFA_MAX_SCALES; ++s) {
-    kp.feat[s] = nullptr; kp.h[s] = kp.w[s] = 0; kp.div[s] = 1; kp.shift[s] = 0;
+    kp.feat[s] = nullptr; kp.h[s] = kp.w[s] = 0; kp.div[s] = 1; kp.shift[s] = 0; kp.vstride[s] = 0;
   }
   for (int s = 0; s < a->n_scales; ++s) {
     OCCD_CHECK_ARG(a->feat[s] != nullptr && a->h[s] > 0 && a->w[s] > 0 && a->div[s] != 0, "occd_sfa_lift_fwd: scale spec");
     kp.feat[s] = a->feat[s]; kp.h[s] = a->h[s]; kp.w[s] = a->w[s]; kp.div[s] = a->div[s];
+    kp.vstride[s] = a->vstride[s] ? a->vstride[s] : (long long)a->h[s] * a->w[s] * a->C;
+    OCCD_CHECK_ARG(kp.vstride[s] % a->C == 0, "occd_sfa_lift_fwd: view stride must be a multiple of C");
     int sh = -1;
     for (int b = 0; b < 30; ++b) if (a->div[s] == (1 << b)) sh = b;
     kp.shift[s] = sh;

@@ -31,6 +31,14 @@ except Exception:  # noqa: BLE001
             pass
 
 
+def feature_hw(img_h, img_w, scale):
+    """spatial size of the "1_scale" feature map (TF-SAME stride-2 stages: ceil division per halving)"""
+    h, w, s = img_h, img_w, 1
+    while s < scale:
+        h, w, s = (h + 1) // 2, (w + 1) // 2, s * 2
+    return h, w
+
+
 def _get(config, name, default=None):
     try:
         return getattr(config, name)
@@ -115,25 +123,51 @@ class OccDepth(_Base, B200Module):
         plan = Plan(dev)
         ps = self.project_scale
         S = [int(s) // ps for s in self.full_scene_size]
-        if self.dataset == "NYU" and V == 1 and "gt_depth" in batch:
-            raise NotImplementedError("virtual right view (OccDepth.generate_virtual_img) is not built yet")
+        virtual = V == 1 and "gt_depth" in batch                          # process_rgbs, OccDepth.py:221-229
+        VL = 2 if virtual else V                                           # views seen by the lift
         img = plan.alloc(B * V, 1, H, W, 3)
         Cf = self.feature_2d_oc
-        scales = [int(s) for s in self.project_res]
-        x_rgb = self.net_rgb.emit(plan, img)                                # {"1_s": CL [B*V,1,h,w,Cf]}
-        pix = torch.zeros(B, V, N, P, 2, dtype=torch.int64, device=dev)
-        fov = torch.zeros(B, V, N, P, dtype=torch.bool, device=dev)
-        x3d = plan.alloc(B, S[0], S[1], S[2], self.feature)
         assert Cf == self.feature, "feature_2d_oc must equal feature (the lift feeds the 3D net directly)"
+        assert Cf % 8 == 0, "feature_2d_oc must be a multiple of 8"
+        scales = [int(s) for s in self.project_res]
+        views = {}
+        outs = {}
+        if virtual:
+            # view-major buffers [2, B, h, w, C]: the 2D net writes view 0, the virtual-view kernel view 1
+            for s in scales:
+                h_s, w_s = feature_hw(H, W, s)
+                vb = torch.zeros(2, B, h_s, w_s, Cf, dtype=torch.bfloat16, device=dev)
+                views[s] = vb
+                outs["1_%d" % s] = CL(vb[0].unsqueeze(1), Cf)
+        x_rgb = self.net_rgb.emit(plan, img, outs)                          # {"1_s": CL [B*V,1,h,w,Cf]}
+        depth0 = None
+        if virtual:
+            L = _lib.lib()
+            gd = batch["gt_depth"]
+            depth0 = torch.zeros(gd.shape[2], gd.shape[3], dtype=torch.float32, device=dev)
+            bf = float(batch["virtual_bf"][0])
+            for s in scales:
+                vb = views[s]
+                _, _, h_s, w_s, _ = vb.shape
+                plan.add(FnOp(lambda st, vb=vb, h_s=h_s, w_s=w_s, s=s: L.occd_virtual_view_fwd(
+                    vb[0].data_ptr(), vb[1].data_ptr(), depth0.data_ptr(), B, h_s, w_s, Cf, Cf, Cf,
+                    depth0.shape[0], depth0.shape[1], bf / s, st), "virtual_view_1_%d" % s, keep=(vb, depth0)))
+        pix = torch.zeros(B, VL, N, P, 2, dtype=torch.int64, device=dev)
+        fov = torch.zeros(B, VL, N, P, dtype=torch.bool, device=dev)
+        x3d = plan.alloc(B, S[0], S[1], S[2], self.feature)
         prior = None
         if self.trans_2d_to_3d == "flosp_depth":
-            prior = self.flosp_depth.emit(plan, x_rgb, batch, B, V)         # fp32 [B, X*Y*Z]
+            n_cams = 1 if self.dataset == "NYU" else V                      # OccDepth.py:303-305
+            prior = self.flosp_depth.emit(plan, x_rgb, batch, B, V, n_cams)  # fp32 [B, X*Y*Z]
         for b in range(B):
             feats = []
             for s in scales:
-                f = x_rgb["1_%d" % s]
-                assert f.coff == 0 and f.cstride == Cf
-                feats.append(f.buf[b * V:(b + 1) * V, 0])                   # [V, h, w, Cf] contiguous view
+                if virtual:
+                    feats.append(views[s][:, b])                            # [2, h, w, Cf], view stride B*h*w*Cf
+                else:
+                    f = x_rgb["1_%d" % s]
+                    assert f.coff == 0 and f.cstride == Cf
+                    feats.append(f.buf[b * V:(b + 1) * V, 0])               # [V, h, w, Cf] contiguous view
             out_b = CL(x3d.buf[b:b + 1], x3d.C, 0)
             pr = prior[b] if prior is not None else None
             plan.add(FnOp(lambda st, feats=feats, pb=pix[b], fb=fov[b], ob=out_b, pr=pr:
@@ -147,7 +181,7 @@ class OccDepth(_Base, B200Module):
             except Exception as e:  # noqa: BLE001 -- same kernels either way; only the launch mechanism differs
                 print("WARNING: CUDA graph capture failed (%r); launching kernels individually" % (e,))
                 plan.graph = None
-        return plan, img, pix, fov, out
+        return plan, img, pix, fov, out, depth0
 
     def forward(self, batch):
         img = batch["img"]
@@ -164,14 +198,17 @@ class OccDepth(_Base, B200Module):
         pp = batch["projected_pix_{}".format(ps)]
         fm = batch["fov_mask_{}".format(ps)]
         N, P = pp[0].shape[1], pp[0].shape[2]
-        key = (B, V, H, W, N, P, str(dev))
+        virtual = V == 1 and "gt_depth" in batch
+        key = (B, V, H, W, N, P, str(dev), virtual, float(batch["virtual_bf"][0]) if virtual else 0.0)
         ent = self._plans().get(key)
         if ent is None:
             with torch.no_grad():
                 ent = self._build(B, V, H, W, N, P, dev, batch)
             self._plans()[key] = ent
-        plan, img_cl, pix, fov, out = ent
+        plan, img_cl, pix, fov, out, depth0 = ent
         CL.from_planar(img.reshape(B * V, 3, H, W), out=img_cl)
+        if depth0 is not None:
+            depth0.copy_(batch["gt_depth"][0, 0], non_blocking=True)
         for b in range(B):
             pix[b].copy_(pp[b], non_blocking=True)
             fov[b].copy_(fm[b], non_blocking=True)

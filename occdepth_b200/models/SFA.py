@@ -71,14 +71,17 @@ class SFA(nn.Module):
 
 def lift_multiscale(feats, divs, projected_pix, fov_mask, out, dataset, scene_size, project_scale, prior=None,
                     scale_const=1.0, stream=None):
-    """Fused lift over all 2D scales.  feats: list of channels-last bf16 tensors [V, h_s, w_s, C] (contiguous);
-    out: CL with dims (1, X, Y, Z) receiving sum_s SFA_s (x prior x scale_const)."""
+    """Fused lift over all 2D scales.  feats: list of channels-last bf16 tensors [V, h_s, w_s, C] whose views may be
+    strided (e.g. a [V, B, h, w, C] buffer sliced at one batch item); out: CL with dims (1, X, Y, Z) receiving
+    sum_s SFA_s (x prior x scale_const)."""
     p = _lib.SfaParams()
     V = feats[0].shape[0]
     Cch = feats[0].shape[3]
     for i, (f, dv) in enumerate(zip(feats, divs)):
-        assert f.is_contiguous() and f.dtype == torch.bfloat16 and f.shape[0] == V and f.shape[3] == Cch
+        assert f.dtype == torch.bfloat16 and f.shape[0] == V and f.shape[3] == Cch
+        assert f[0].is_contiguous() and f.stride(3) == 1
         p.feat[i], p.h[i], p.w[i], p.div[i] = f.data_ptr(), f.shape[1], f.shape[2], int(dv)
+        p.vstride[i] = f.stride(0) if V > 1 else 0
     p.n_scales, p.feat_dtype = len(feats), _lib.DTYPE_BF16
     _fill_common(p, projected_pix, fov_mask, V, Cch)
     assert out.coff == 0 and out.C == Cch and out.spatial() == p.N

@@ -337,6 +337,21 @@ def unet2d(sd, p, x, backbone="tf_efficientnet_b7_ns", return_up_feats=1):
 
 
 # --------------------------------------------------------------------------------------------------
+# A2c: virtual right view -- OccDepth.generate_virtual_img (OccDepth.py:233-260)
+def virtual_view(x, depth, scale_2d, bf):
+    """x (B,C,h,w) left features; depth (B,1,H,W); returns the disparity-shifted right-view features."""
+    n, c, h, w = x.shape
+    dm = F.interpolate(depth, size=(h, w), mode="bilinear", align_corners=False)        # :240-244
+    dx = (bf / int(scale_2d)) / dm                                                      # :246-247
+    dx = torch.where(torch.isinf(dx), torch.zeros_like(dx), dx).to(x.dtype)
+    hd, wd = torch.arange(-1, 1, 2 / h), torch.arange(-1, 1, 2 / w)                     # :249-250 (corner coords)
+    my, mx = torch.meshgrid(hd, wd, indexing="ij")
+    grid = torch.stack((mx, my), 2).unsqueeze(0).repeat(n, 1, 1, 1).to(x.dtype)
+    grid[..., 0] = grid[..., 0] + (dx * 2 / w)[0]                                       # item 0's disparity, :255-257
+    return F.grid_sample(x, grid, mode="bilinear", padding_mode="border", align_corners=False)
+
+
+# --------------------------------------------------------------------------------------------------
 # A1: OccDepth.forward, "flosp" transform (OccDepth.py:344-376)
 def occdepth_forward(sd, batch, cfg):
     """cfg: dict(dataset, full_scene_size, project_scale, project_res, backbone_2d_name, return_up_feats,
@@ -345,6 +360,11 @@ def occdepth_forward(sd, batch, cfg):
     bs, n_views = img.shape[:2]
     x_rgb = [unet2d(sd, "net_rgb", img[:, v], cfg["backbone_2d_name"], cfg["return_up_feats"])
              for v in range(n_views)]                                           # process_rgbs :208-219
+    if n_views == 1 and "gt_depth" in batch:                                    # process_rgbs :221-229
+        bf = batch["virtual_bf"][0]
+        x_rgb.append({"1_" + str(s): virtual_view(x_rgb[0]["1_" + str(s)], batch["gt_depth"], s, bf)
+                      for s in cfg["project_res"]})
+        n_views = 2
     ps = cfg["project_scale"]
     x3ds = []
     for i in range(bs):

@@ -140,3 +140,28 @@ def test_occdepth_forward_flosp_depth():
     assert set(got.keys()) == set(want.keys())
     for k in ("ssc_logit", "occ_logit", "depth_pred"):
         assert _rel(got[k], want[k]) <= TOL_E2E, (k, _rel(got[k], want[k]))
+
+
+def test_occdepth_forward_nyu_virtual_view():
+    """config-4-type path: single RGB view + gt_depth -> virtual right view kernel -> lift -> NYU 3D net"""
+    from occdepth_b200.models.OccDepth import OccDepth
+    from test_oracle_vs_reference import _nyu_virtual_batch
+    torch.manual_seed(0)
+    full = (12, 8, 12)
+    cfg = synth.occdepth_cfg(dataset="NYU", full_scene_size=full, project_scale=1, feature=16, feature_2d_oc=16,
+                             n_classes=6, cascade_cls=False, backbone_2d_name="tf_efficientnet_b3_ns")
+    with ref_import.quiet():
+        m = OccDepth(["c"] * 6, torch.ones(6), full_scene_size=full, project_res=["1", "2", "4", "8"],
+                     config=cfg).eval()
+    synth.seed_weights_(m, 3)
+    batch = _nyu_virtual_batch(32, 64, full)
+    ocfg = dict(cfg)
+    ocfg["project_res"] = ["1", "2", "4", "8"]
+    with torch.no_grad():
+        want = OF.occdepth_forward({k: v.clone() for k, v in m.state_dict().items()}, batch, ocfg)
+        b2 = dict(batch)
+        b2["img"] = batch["img"].cuda()
+        got = m.cuda()(b2)
+    assert set(got.keys()) == set(want.keys())
+    for k in want:
+        assert _rel(got[k], want[k]) <= TOL_E2E, (k, _rel(got[k], want[k]))

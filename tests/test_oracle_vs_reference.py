@@ -150,3 +150,35 @@ def test_flosp_depth(ref):
     assert float((want > 0).float().mean()) > 0.2     # the frustum actually covers part of the grid
     _close(got_d, want_d, rtol=1e-4, atol=1e-6)
     _close(got, want, rtol=1e-3, atol=1e-5)
+
+
+def _nyu_virtual_batch(H, W, full, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(1, 1, 3, H, W, generator=g)
+    depth = torch.rand(1, 1, H, W, generator=g) * 7.5 + 0.5
+    depth[0, 0, 3, 5] = 0.0          # exercises the inf -> 0 disparity rule (OccDepth.py:248)
+    N = full[0] * full[1] * full[2]
+    pix, fov = synth.random_indices(N, W, H, n_views=2, P=1, seed=seed + 1, margin=(8, 6))
+    return {"img": img, "gt_depth": depth, "virtual_bf": [torch.tensor(51.88579 * W / 640.0)],
+            "vox_origin": torch.zeros(1, 3, dtype=torch.float64), "projected_pix_1": [pix], "fov_mask_1": [fov]}
+
+
+def test_occdepth_forward_nyu_virtual_view(ref):
+    """NYU-type path: one real view, the right view synthesised from gt_depth (generate_virtual_img)"""
+    torch.manual_seed(0)
+    full = (12, 8, 12)
+    cfg = synth.occdepth_cfg(dataset="NYU", full_scene_size=full, project_scale=1, feature=16, feature_2d_oc=16,
+                             n_classes=6, cascade_cls=False, backbone_2d_name="tf_efficientnet_b3_ns")
+    with ref_import.quiet():
+        m = ref.OccDepth.OccDepth(["c"] * 6, torch.ones(6), full_scene_size=full, project_res=["1", "2", "4", "8"],
+                                  config=cfg).eval()
+    synth.seed_weights_(m, 3)
+    batch = _nyu_virtual_batch(32, 64, full)
+    ocfg = dict(cfg)
+    ocfg["project_res"] = ["1", "2", "4", "8"]
+    with torch.no_grad():
+        want = m(batch)
+        got = OF.occdepth_forward(m.state_dict(), batch, ocfg)
+    assert set(got.keys()) == set(want.keys())
+    for k in want:
+        _close(got[k], want[k], rtol=2e-3, atol=2e-4)
