@@ -133,13 +133,11 @@ def run_reference(args):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from occdepth_b200 import parallel
+    world, rank, local = parallel.env_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    parallel.init("nccl", dev)
     m = build_model().to(dev)
     img, pix, fov = make_inputs(seed=rank)
     # ---- device-resident arm ----
@@ -150,8 +148,7 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        parallel.barrier()
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
@@ -165,10 +162,7 @@ def run_b200(args):
             out = m(batch_dev)
     e1.record()
     barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
     sampler.stop_flag = True
 
     # ---- end-to-end arm: host buffers, H2D of the inputs and D2H of the logits inside the timed region ----
@@ -191,10 +185,7 @@ def run_b200(args):
             e2e_step()
         e1.record()
     barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    ms_e2e = float(ms2.item())
+    ms_e2e = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
 
     line = None
     if rank == 0:
