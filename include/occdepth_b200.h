@@ -114,6 +114,9 @@ typedef struct {
   int src_cstride[OCCD_CONV_MAX_SRC];
   int src_coff[OCCD_CONV_MAX_SRC];
   int B, ID, IH, IW; /* shared by all sources                                                      */
+  int src_d0;        /* plane offset added to every source D coordinate: sources that carry halo   */
+                     /* margins ([ID] = slab + 2*margin planes, X-slab multi-GPU partition) are     */
+                     /* addressed relative to their interior; 0 for ordinary tensors               */
   int stride[3];     /* (sd, sh, sw)                                                               */
   int n_taps;
   occd_conv_tap taps[OCCD_CONV_MAX_TAPS];

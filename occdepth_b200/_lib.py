@@ -60,6 +60,7 @@ class ConvDesc(C.Structure):
         ("src_cstride", C.c_int * CONV_MAX_SRC),
         ("src_coff", C.c_int * CONV_MAX_SRC),
         ("B", C.c_int), ("ID", C.c_int), ("IH", C.c_int), ("IW", C.c_int),
+        ("src_d0", C.c_int),
         ("stride", C.c_int * 3),
         ("n_taps", C.c_int),
         ("taps", ConvTap * CONV_MAX_TAPS),

@@ -13,7 +13,7 @@
 
 namespace {
 
-constexpr int kTcThreads = 320;  // warp 0: TMA producer, warp 1: MMA issuer (+TMEM alloc), warps 2-5 / 6-9: epilogue groups
+constexpr int kTcThreads = 576;  // warp 0: TMA producer, warp 1: MMA issuer (+TMEM alloc), warps 2-17: four epilogue groups
 constexpr int kMaxStages = 24;
 
 struct TcParams {
@@ -21,6 +21,7 @@ struct TcParams {
   int n_taps;
   int n_kchunks[OCCD_CONV_MAX_SRC];
   int tiles_w, tiles_h, tiles_d, num_m_tiles;
+  int src_d0;
   int TD, TH, TW;
   int stride[3];
   int Cout_pad, N_tile;
@@ -40,8 +41,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   // Persistent, warp-specialised implicit GEMM.  Each CTA walks tiles blockIdx.x, +gridDim.x, ...:
   //   warp 0 (one lane): TMA producer -- runs ahead across tile boundaries, the smem ring never drains
   //   warp 1 (one lane): tcgen05.mma issuer, accumulating into one of TWO TMEM accumulators
-  //   warps 2-5 / 6-9  : two epilogue groups (even / odd tiles, one TMEM accumulator each): TMEM -> regs ->
-  //                      global while the MMAs of the following tiles run
+  //   warps 2-17       : four epilogue groups of 4 warps: group g drains accumulator (g & 1) -- even / odd
+  //                      tiles -- and column half (g >> 1) of it: TMEM -> regs -> global while the MMAs of the
+  //                      following tiles run (the epilogue is latency bound: 16 warps keep the SM's LSU busy)
   constexpr int ROW_BYTES = KC * 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16-byte aligned: round the base up to 1024 (swizzle atom alignment)
@@ -72,7 +74,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(tmem_full_bar + 8u * a, 1);
-      tc::mbar_init(tmem_empty_bar + 8u * a, 128);  // every epilogue thread arrives
+      tc::mbar_init(tmem_empty_bar + 8u * a, 256);  // every epilogue thread of the two groups arrives
     }
     tc::fence_barrier_init();
   }
@@ -100,7 +102,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         const int th = t % p.tiles_h; t /= p.tiles_h;
         const int td = t % p.tiles_d; t /= p.tiles_d;
         const int b = t;
-        const int iw0 = tw * p.TW * p.stride[2], ih0 = th * p.TH * p.stride[1], id0 = td * p.TD * p.stride[0];
+        const int iw0 = tw * p.TW * p.stride[2], ih0 = th * p.TH * p.stride[1],
+                  id0 = td * p.TD * p.stride[0] + p.src_d0;
         const int n0 = nt * p.N_tile;
         // items (tap, k-chunk) are loaded in groups of p.group per pipeline stage: one barrier hand-off per group
         int g = 0;
@@ -169,7 +172,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
     const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int grp = (warp - 2) >> 2;     // epilogue group == accumulator index
+    const int grp = ((warp - 2) >> 2) & 1;   // accumulator index (tile parity)
+    const int half = (warp - 2) >> 3;        // which half of the accumulator's 16-column chunks
+    const int n_chunks = p.N_tile >> 4;
+    const int c_begin = half == 0 ? 0 : ((n_chunks + 1) >> 1) * 16;
+    const int c_end = half == 0 ? ((n_chunks + 1) >> 1) * 16 : p.N_tile;
     const int row = q * 32 + lane;
     const int rw = row % p.TW;
     const int rh = (row / p.TW) % p.TH;
@@ -194,28 +201,30 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       if (tracer && j < 64) p.trace[j * 8 + 5] = clock64();
       const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
       // software-pipelined: the tcgen05.ld of the next 16 columns is in flight while these 16 are stored
-      uint32_t ra[16], rb[16];
-      tc::tmem_ld16_issue(taddr, ra);
-      tc::tmem_ld_wait16(ra);
-      for (int c0 = 0; c0 < p.N_tile; c0 += 32) {
-        const bool has_b = c0 + 16 < p.N_tile;
-        if (has_b) tc::tmem_ld16_issue(taddr + (uint32_t)(c0 + 16), rb);
-        if (valid) {
-          float v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]);
-          conv_epilogue_row<16>(p.epi, b, od, oh, ow, n0 + c0, v);
-        }
-        if (has_b) {
-          tc::tmem_ld_wait16(rb);
-          if (c0 + 32 < p.N_tile) tc::tmem_ld16_issue(taddr + (uint32_t)(c0 + 32), ra);
+      if (c_begin < c_end) {
+        uint32_t ra[16], rb[16];
+        tc::tmem_ld16_issue(taddr + (uint32_t)c_begin, ra);
+        tc::tmem_ld_wait16(ra);
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+          const bool has_b = c0 + 16 < c_end;
+          if (has_b) tc::tmem_ld16_issue(taddr + (uint32_t)(c0 + 16), rb);
           if (valid) {
             float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]);
-            conv_epilogue_row<16>(p.epi, b, od, oh, ow, n0 + c0 + 16, v);
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]);
+            conv_epilogue_row<16>(p.epi, b, od, oh, ow, n0 + c0, v);
           }
-          if (c0 + 32 < p.N_tile) tc::tmem_ld_wait16(ra);
+          if (has_b) {
+            tc::tmem_ld_wait16(rb);
+            if (c0 + 32 < c_end) tc::tmem_ld16_issue(taddr + (uint32_t)(c0 + 32), ra);
+            if (valid) {
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]);
+              conv_epilogue_row<16>(p.epi, b, od, oh, ow, n0 + c0 + 16, v);
+            }
+            if (c0 + 32 < c_end) tc::tmem_ld_wait16(ra);
+          }
         }
       }
       tc::fence_before_sync();
@@ -246,6 +255,7 @@ struct HaloParams {
   int d;                      // dilation (== padding)
   int D, H, W;                // full grid (== output grid)
   int BD, BH, BW, PD, PH, PW;  // valid box / halo box (sub-sampled coordinates)
+  int src_d0;                 // plane offset of the interior inside a halo-margin source buffer
   int hd, hh, hw;             // 1 where the taps reach into that dimension (halo of one sub-sampled position)
   int tilesD, tilesH, tilesW;
   int nM, R0;                 // M tiles per CTA tile, first valid row
@@ -292,7 +302,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(tfull_bar + 8u * a, 1);
-      tc::mbar_init(tempty_bar + 8u * a, 128);
+      tc::mbar_init(tempty_bar + 8u * a, 256);
     }
     tc::mbar_init(w_bar, 1);
     tc::fence_barrier_init();
@@ -333,7 +343,8 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
         tc::mbar_wait(empty_bar + 8u * s, ph ^ 1u);
         tc::mbar_expect_tx(full_bar + 8u * s, (uint32_t)p.box_bytes);
         tc::tma_load_5d(smem_a + (uint32_t)s * p.a_stage_bytes, &tmA, full_bar + 8u * s, 0,
-                        (tw * p.BW - p.hw) * d + rc, (th * p.BH - p.hh) * d + rb, (td * p.BD - p.hd) * d + ra, b);
+                        (tw * p.BW - p.hw) * d + rc, (th * p.BH - p.hh) * d + rb,
+                        (td * p.BD - p.hd) * d + ra + p.src_d0, b);
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
@@ -383,7 +394,8 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
   } else {
     // ===== epilogue =====
     const int q = warp & 3;
-    const int grp = (warp - 2) >> 2;
+    const int grp = ((warp - 2) >> 2) & 1;   // accumulator set (tile parity)
+    const int half = (warp - 2) >> 3;        // even / odd M tiles of the set
     const bool tracer = p.trace && blockIdx.x == 0 && threadIdx.x == 64;
     int j = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
@@ -396,7 +408,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
       tc::mbar_wait(tfull_bar + 8u * set, use & 1u);
       tc::fence_after_sync();
       if (tracer && j < 64) p.trace[j * 8 + 5] = clock64();
-      for (int m = 0; m < p.nM; ++m) {
+      for (int m = half; m < p.nM; m += 2) {
         const int R = p.R0 + m * 128 + q * 32 + lane;
         const int pw = R % p.PW;
         const int phh = (R / p.PW) % p.PH;
@@ -433,7 +445,7 @@ struct SimtParams {
   int n_src, n_taps;
   const __nv_bfloat16* src[OCCD_CONV_MAX_SRC];
   int src_C[OCCD_CONV_MAX_SRC], src_cstride[OCCD_CONV_MAX_SRC], src_coff[OCCD_CONV_MAX_SRC];
-  int ID, IH, IW;
+  int ID, IH, IW, src_d0;
   int stride[3];
   const __nv_bfloat16* weight;
   int Cout_pad, Kpad;
@@ -457,7 +469,7 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ 
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   for (int tp = 0; tp < p.n_taps; ++tp) {
     const int s = p.tap_src[tp];
-    const int id = od * p.stride[0] + p.tap_dz[tp];
+    const int id = od * p.stride[0] + p.tap_dz[tp] + p.src_d0;
     const int ih = oh * p.stride[1] + p.tap_dy[tp];
     const int iw = ow * p.stride[2] + p.tap_dx[tp];
     if (id < 0 || id >= p.ID || ih < 0 || ih >= p.IH || iw < 0 || iw >= p.IW) continue;
@@ -558,7 +570,8 @@ static int build_halo_plan(const occd_conv_desc* d, occd_conv_plan* pl) {
   HALO_REQUIRE(d->stride[0] == 1 && d->stride[1] == 1 && d->stride[2] == 1, "stride must be 1");
   HALO_REQUIRE(d->omul[0] == 1 && d->omul[1] == 1 && d->omul[2] == 1 && d->oadd[0] == 0 && d->oadd[1] == 0 &&
                d->oadd[2] == 0, "identity output mapping only");
-  HALO_REQUIRE(d->OD == d->ID && d->OH == d->IH && d->OW == d->IW, "output grid must equal the input grid");
+  HALO_REQUIRE(d->OD + 2 * d->src_d0 == d->ID && d->OH == d->IH && d->OW == d->IW,
+               "output grid must equal the input grid (plus symmetric halo margins)");
   HALO_REQUIRE(d->n_taps <= 27, "at most 27 taps");
   HALO_REQUIRE(d->src_C[0] <= 64 && d->Cout_pad <= 128, "channel counts too large for the resident-weight scheme");
   int dil = 0;
@@ -581,14 +594,15 @@ static int build_halo_plan(const occd_conv_desc* d, occd_conv_plan* pl) {
   HALO_REQUIRE(d->Kpad == KC, "Kpad must equal the k-chunk");
   pl->kc = KC;
   const int row_bytes = KC * 2;
-  h.d = dil; h.D = d->ID; h.H = d->IH; h.W = d->IW;
+  h.d = dil; h.D = d->OD; h.H = d->IH; h.W = d->IW;
+  h.src_d0 = d->src_d0;
   h.hd = hal[0]; h.hh = hal[1]; h.hw = hal[2];
   h.n_taps = d->n_taps;
   h.N_tile = d->Cout_pad;
   h.b_stride = round_up(h.N_tile * row_bytes, 1024);
   h.w_bytes = h.n_taps * h.b_stride;
   HALO_REQUIRE(h.w_bytes <= 112 * 1024, "weights do not fit in shared memory");
-  const int sD = (d->ID + dil - 1) / dil, sH = (d->IH + dil - 1) / dil, sW = (d->IW + dil - 1) / dil;
+  const int sD = (d->OD + dil - 1) / dil, sH = (d->IH + dil - 1) / dil, sW = (d->IW + dil - 1) / dil;
   const int smem_total = 224 * 1024 - h.w_bytes - 2048;
   // W extent of the box: the whole sub-sampled line when it fits, else equal splits of at most 62
   const int nW = (sW + 61) / 62;
@@ -672,6 +686,7 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
   OCCD_CHECK_ARG(d && out, "occd_conv_plan_create: null argument");
   OCCD_CHECK_ARG(d->n_src >= 1 && d->n_src <= OCCD_CONV_MAX_SRC, "occd_conv_plan_create: n_src");
   OCCD_CHECK_ARG(d->n_taps >= 1 && d->n_taps <= OCCD_CONV_MAX_TAPS, "occd_conv_plan_create: n_taps");
+  OCCD_CHECK_ARG(d->src_d0 >= 0 && d->src_d0 < d->ID, "occd_conv_plan_create: src_d0");
   OCCD_CHECK_ARG(d->B > 0 && d->ID > 0 && d->IH > 0 && d->IW > 0 && d->OD > 0 && d->OH > 0 && d->OW > 0,
                  "occd_conv_plan_create: dims");
   OCCD_CHECK_ARG(d->Cout > 0 && d->Cout_pad >= d->Cout && d->Cout_pad % 16 == 0, "occd_conv_plan_create: Cout_pad");
@@ -724,7 +739,7 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
       s.src[i] = reinterpret_cast<const __nv_bfloat16*>(d->src[i]);
       s.src_C[i] = d->src_C[i]; s.src_cstride[i] = d->src_cstride[i]; s.src_coff[i] = d->src_coff[i];
     }
-    s.ID = d->ID; s.IH = d->IH; s.IW = d->IW;
+    s.ID = d->ID; s.IH = d->IH; s.IW = d->IW; s.src_d0 = d->src_d0;
     for (int i = 0; i < 3; ++i) s.stride[i] = d->stride[i];
     s.weight = reinterpret_cast<const __nv_bfloat16*>(d->weight);
     s.Cout_pad = d->Cout_pad; s.Kpad = d->Kpad;
@@ -756,6 +771,7 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
     return OCCD_ERR_ARG;
   }
   t.n_taps = d->n_taps;
+  t.src_d0 = d->src_d0;
   for (int s = 0; s < OCCD_CONV_MAX_SRC; ++s) t.n_kchunks[s] = s < d->n_src ? (d->src_C[s] + KC - 1) / KC : 0;
   for (int i = 0; i < 3; ++i) t.stride[i] = d->stride[i];
   for (int i = 0; i < d->n_taps; ++i) {

@@ -11,59 +11,83 @@
 namespace {
 
 constexpr int kDwThreads = 256;
-constexpr int kDwPasses = 4;  // pixels per thread
+constexpr int kDwPX = 4;    // consecutive output pixels per thread (register blocking along W)
+constexpr int kDwRows = 4;  // output rows per block (amortises the squeeze atomics)
 
 // blockDim = (CVB, 256/CVB): threadIdx.x owns one 8-channel vector (coalesced CVB*16-byte segments),
-// threadIdx.y walks output pixels of one image row.  CVB in {8,16,32} is picked per layer so that narrow
-// layers (C = 64) keep every lane busy.  The squeeze (global-average-pool sum) is accumulated in registers,
-// reduced across threadIdx.y in shared memory and flushed with one atomicAdd per channel per block.
-template <int K, int CVB>
+// threadIdx.y owns kDwPX consecutive output pixels of one image row.  Per filter row the thread loads the
+// (kDwPX-1)*S + K input vectors it needs ONCE and reuses them across the K taps and kDwPX outputs (2.5x fewer
+// loads/unpacks than one-pixel-per-thread for K = 5).  CVB in {8,16,32} is picked per layer so narrow layers
+// (C = 64) keep every lane busy.  The squeeze (global-average-pool sum) is accumulated in registers, reduced
+// across threadIdx.y in shared memory and flushed with one atomicAdd per channel per block.
+template <int K, int S, int CVB>
 __global__ void __launch_bounds__(kDwThreads)
 dwconv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
               __nv_bfloat16* __restrict__ out, float* __restrict__ pool, int H, int W, int OH, int OW, int C,
-              int cs_in, int cs_out, int stride, int pad_top, int pad_left, int act) {
+              int cs_in, int cs_out, int pad_top, int pad_left, int act) {
   constexpr int PY = kDwThreads / CVB;
+  constexpr int NIN = (kDwPX - 1) * S + K;
   __shared__ float red[PY][CVB * 8 + 1];
   const int tx = threadIdx.x % CVB, ty = threadIdx.x / CVB;
   const int c0 = (blockIdx.y * CVB + tx) * 8;
   const bool cvalid = c0 < C;
-  const int b = blockIdx.z / OH;
-  const int oy = blockIdx.z % OH;
+  const int row_blocks = (OH + kDwRows - 1) / kDwRows;
+  const int b = blockIdx.z / row_blocks;
+  const int ox0 = (blockIdx.x * PY + ty) * kDwPX;
   float psum[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) psum[i] = 0.f;
-  if (cvalid) {
-    float bv[8];
-    *reinterpret_cast<float4*>(bv) = __ldg(reinterpret_cast<const float4*>(bias + c0));
-    *reinterpret_cast<float4*>(bv + 4) = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+#pragma unroll 1
+  for (int ry = 0; ry < kDwRows; ++ry) {
+  const int oy = (blockIdx.z % row_blocks) * kDwRows + ry;
+  if (cvalid && ox0 < OW && oy < OH) {
+    float acc[kDwPX][8];
+    {
+      float bv[8];
+      *reinterpret_cast<float4*>(bv) = __ldg(reinterpret_cast<const float4*>(bias + c0));
+      *reinterpret_cast<float4*>(bv + 4) = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+#pragma unroll
+      for (int p = 0; p < kDwPX; ++p)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[p][i] = bv[i];
+    }
     const __nv_bfloat16* inb = in + (long long)b * H * W * cs_in + c0;
     const float* wc = w + c0;
+    const int ix0 = ox0 * S - pad_left;
 #pragma unroll 1
-    for (int j = 0; j < kDwPasses; ++j) {
-      const int ox = (blockIdx.x * kDwPasses + j) * PY + ty;
-      if (ox >= OW) break;
-      float acc[8];
+    for (int ky = 0; ky < K; ++ky) {
+      const int iy = oy * S - pad_top + ky;
+      if (iy < 0 || iy >= H) continue;
+      const __nv_bfloat16* row = inb + (long long)iy * W * cs_in;
+      float xin[NIN][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = bv[i];
+      for (int j = 0; j < NIN; ++j) {
+        const int ix = ix0 + j;
+        if (ix >= 0 && ix < W) {
+          unpack8(__ldg(reinterpret_cast<const uint4*>(row + (long long)ix * cs_in)), xin[j]);
+        } else {
 #pragma unroll
-      for (int ky = 0; ky < K; ++ky) {
-        const int iy = oy * stride - pad_top + ky;
-        if (iy < 0 || iy >= H) continue;
-#pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          const int ix = ox * stride - pad_left + kx;
-          if (ix < 0 || ix >= W) continue;
-          float x[8], wv[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(inb + ((long long)iy * W + ix) * cs_in)), x);
-          const float* wp = wc + (long long)(ky * K + kx) * C;
-          *reinterpret_cast<float4*>(wv) = __ldg(reinterpret_cast<const float4*>(wp));
-          *reinterpret_cast<float4*>(wv + 4) = __ldg(reinterpret_cast<const float4*>(wp + 4));
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = fmaf(x[i], wv[i], acc[i]);
+          for (int i = 0; i < 8; ++i) xin[j][i] = 0.f;
         }
       }
-      apply_act8(acc, act);
-      const uint4 packed = pack8(acc);
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        float wv[8];
+        const float* wp = wc + (long long)(ky * K + kx) * C;
+        *reinterpret_cast<float4*>(wv) = __ldg(reinterpret_cast<const float4*>(wp));
+        *reinterpret_cast<float4*>(wv + 4) = __ldg(reinterpret_cast<const float4*>(wp + 4));
+#pragma unroll
+        for (int p = 0; p < kDwPX; ++p)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[p][i] = fmaf(xin[p * S + kx][i], wv[i], acc[p][i]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < kDwPX; ++p) {
+      const int ox = ox0 + p;
+      if (ox >= OW) break;
+      apply_act8(acc[p], act);
+      const uint4 packed = pack8(acc[p]);
       *reinterpret_cast<uint4*>(out + (((long long)b * OH + oy) * OW + ox) * cs_out + c0) = packed;
       if (pool) {
         // pool what the next layer will actually read (the bf16-rounded activation)
@@ -73,6 +97,7 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
         for (int i = 0; i < 8; ++i) psum[i] += r[i];
       }
     }
+  }
   }
   if (pool) {
 #pragma unroll
@@ -204,7 +229,7 @@ extern "C" int occd_dwconv2d_fwd(const void* in, const float* w, const float* bi
   OCCD_CHECK_ARG(in && w && bias && out && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "occd_dwconv2d_fwd: args");
   OCCD_CHECK_ARG(C > 0 && C % 8 == 0 && cs_in % 8 == 0 && cs_out % 8 == 0 && cs_in >= C && cs_out >= C,
                  "occd_dwconv2d_fwd: channels must be a multiple of 8");
-  OCCD_CHECK_ARG((long long)B * OH <= 65535, "occd_dwconv2d_fwd: B*OH too large");
+  OCCD_CHECK_ARG((long long)B * ((OH + kDwRows - 1) / kDwRows) <= 65535, "occd_dwconv2d_fwd: B*OH too large");
   OCCD_CHECK_ARG(K == 3 || K == 5, "occd_dwconv2d_fwd: kernel size must be 3 or 5");
   const int CV = C / 8;
   // lanes per pixel: the candidate in {8,16,32} with the least padding (ties -> widest)
@@ -213,16 +238,22 @@ extern "C" int occd_dwconv2d_fwd(const void* in, const float* w, const float* bi
     const int padded = (CV + c - 1) / c * c;
     if (best < 0 || padded < best) { best = padded; cvb = c; }
   }
+  OCCD_CHECK_ARG(stride == 1 || stride == 2, "occd_dwconv2d_fwd: stride must be 1 or 2");
   const int py = kDwThreads / cvb;
-  dim3 grid((OW + py * kDwPasses - 1) / (py * kDwPasses), (CV + cvb - 1) / cvb, B * OH), block(kDwThreads);
+  dim3 grid((OW + py * kDwPX - 1) / (py * kDwPX), (CV + cvb - 1) / cvb, B * ((OH + kDwRows - 1) / kDwRows)), block(kDwThreads);
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16* i = (const __nv_bfloat16*)in;
   __nv_bfloat16* o = (__nv_bfloat16*)out;
-#define OCCD_DW(K_, CVB_)                                                                                        \
-  dwconv_kernel<K_, CVB_><<<grid, block, 0, st>>>(i, w, bias, o, pool, H, W, OH, OW, C, cs_in, cs_out, stride,   \
-                                                   pad_top, pad_left, act)
-  if (K == 3) { if (cvb == 8) OCCD_DW(3, 8); else if (cvb == 16) OCCD_DW(3, 16); else OCCD_DW(3, 32); }
-  else        { if (cvb == 8) OCCD_DW(5, 8); else if (cvb == 16) OCCD_DW(5, 16); else OCCD_DW(5, 32); }
+#define OCCD_DW(K_, S_, CVB_)                                                                                   \
+  dwconv_kernel<K_, S_, CVB_><<<grid, block, 0, st>>>(i, w, bias, o, pool, H, W, OH, OW, C, cs_in, cs_out,      \
+                                                       pad_top, pad_left, act)
+#define OCCD_DW_CVB(K_, S_)                                                                                     \
+  { if (cvb == 8) OCCD_DW(K_, S_, 8); else if (cvb == 16) OCCD_DW(K_, S_, 16); else OCCD_DW(K_, S_, 32); }
+  if (K == 3 && stride == 1) OCCD_DW_CVB(3, 1)
+  else if (K == 3) OCCD_DW_CVB(3, 2)
+  else if (stride == 1) OCCD_DW_CVB(5, 1)
+  else OCCD_DW_CVB(5, 2)
+#undef OCCD_DW_CVB
 #undef OCCD_DW
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;

@@ -47,34 +47,59 @@ def require_cuda(t, what):
 
 
 class CL:
-    """channels-last bf16 activation: a channel window [coff, coff+C) of a [B,D,H,W,cstride] buffer."""
+    """channels-last bf16 activation: a channel window [coff, coff+C) of a [B,D,H,W,cstride] buffer.
 
-    def __init__(self, buf, C_, coff=0):
+    X-slab multi-GPU partition: a buffer may carry `halo` margin planes on both sides of D; the CL then denotes the
+    INTERIOR planes [d0, d0+dlen) (what this rank owns and writes) while convolutions read the margins
+    (neighbour data put there by HaloExchangeOp, zeros at the global boundary).  Requires B == 1."""
+
+    def __init__(self, buf, C_, coff=0, d0=0, dlen=None):
         assert buf.dtype == torch.bfloat16 and buf.dim() == 5 and buf.is_contiguous()
         self.buf, self.C, self.coff = buf, int(C_), int(coff)
+        self.d0 = int(d0)
+        self.dlen = int(buf.shape[1] - 2 * d0 if dlen is None else dlen)
         assert self.coff % 8 == 0 and buf.shape[4] % 8 == 0 and self.coff + self.C <= buf.shape[4]
+        assert self.d0 == 0 or buf.shape[0] == 1
 
     @staticmethod
-    def alloc(B, D, H, W, C_, device):
-        return CL(torch.zeros(B, D, H, W, _round_up(C_, 8), dtype=torch.bfloat16, device=device), C_)
+    def alloc(B, D, H, W, C_, device, halo=0):
+        buf = torch.zeros(B, D + 2 * halo, H, W, _round_up(C_, 8), dtype=torch.bfloat16, device=device)
+        return CL(buf, C_, 0, halo, D)
+
+    @property
+    def halo(self):
+        return self.d0
 
     @property
     def dims(self):
-        return tuple(self.buf.shape[:4])
+        return (self.buf.shape[0], self.dlen, self.buf.shape[2], self.buf.shape[3])
 
     @property
     def cstride(self):
         return self.buf.shape[4]
 
     @property
+    def plane_elems(self):
+        return self.buf.shape[2] * self.buf.shape[3] * self.buf.shape[4]
+
+    @property
     def ptr(self):
+        """pointer to the first INTERIOR plane"""
+        return self.buf.data_ptr() + 2 * self.d0 * self.plane_elems
+
+    @property
+    def full_ptr(self):
         return self.buf.data_ptr()
 
     def window(self, coff, C_):
-        return CL(self.buf, C_, self.coff + coff)
+        return CL(self.buf, C_, self.coff + coff, self.d0, self.dlen)
 
     def spatial(self):
-        return self.buf.shape[1] * self.buf.shape[2] * self.buf.shape[3]
+        return self.dlen * self.buf.shape[2] * self.buf.shape[3]
+
+    def interior(self):
+        """torch view [B, dlen, H, W, cstride] of the owned planes"""
+        return self.buf[:, self.d0:self.d0 + self.dlen]
 
     # ---- module-boundary conversions (reference tensors are NCHW / NCDHW fp32) ----
     @staticmethod
@@ -163,9 +188,11 @@ class ConvOp:
         d.impl = impl
         d.n_src = len(srcs)
         for i, s in enumerate(srcs):
-            d.src[i] = s.ptr
+            assert s.d0 == srcs[0].d0 and s.buf.shape[1] == srcs[0].buf.shape[1]
+            d.src[i] = s.full_ptr
             d.src_C[i], d.src_cstride[i], d.src_coff[i] = s.C, s.cstride, s.coff
-        d.B, d.ID, d.IH, d.IW = B, ID, IH, IW
+        d.B, d.ID, d.IH, d.IW = B, srcs[0].buf.shape[1], IH, IW
+        d.src_d0 = srcs[0].d0
         for i in range(3):
             d.stride[i], d.omul[i], d.oadd[i] = stride[i], omul[i], oadd[i]
         d.n_taps = len(taps)
@@ -246,14 +273,36 @@ def out_size(i, k, s, p, d):
 class Plan:
     """Ordered list of prepared launches (anything with .run(stream)) + named buffers."""
 
-    def __init__(self, device):
+    def __init__(self, device, slab=None):
         self.device = device
         self.ops = []
         self.flops = 0
         self.graph = None
+        self.slab = slab            # parallel.SlabContext for the X-slab multi-GPU partition, else None
+        self._exchanged = set()
 
     def alloc(self, B, D, H, W, C_):
-        return CL.alloc(B, D, H, W, C_, self.device)
+        """3-D activations (D > 1) of a slab-partitioned plan get halo margins; everything else is dense."""
+        halo = self.slab.halo if (self.slab is not None and D > 1) else 0
+        return CL.alloc(B, D, H, W, C_, self.device, halo=halo)
+
+    def need_halo(self, src, taps, stride0, out_d):
+        """Insert the neighbour exchange for `src` before a conv whose taps reach across the slab boundary."""
+        if self.slab is None or src.halo == 0:
+            return
+        left = max(0, -min(t[1] for t in taps))
+        right = max(0, (out_d - 1) * stride0 + max(t[1] for t in taps) - (src.dlen - 1))
+        if left == 0 and right == 0:
+            return
+        if max(left, right) > src.halo or max(left, right) > src.dlen:
+            raise RuntimeError("slab partition: a convolution reaches %d planes across the slab boundary but the slab "
+                               "is %d planes thick (halo margin %d): use fewer ranks" % (max(left, right), src.dlen,
+                                                                                       src.halo))
+        key = src.buf.data_ptr()
+        if key in self._exchanged:
+            return
+        self._exchanged.add(key)
+        self.add(self.slab.exchange_op(src))
 
     def add(self, op):
         self.ops.append(op)
@@ -273,6 +322,7 @@ class Plan:
         if out is None and not no_out0:
             out = self.alloc(B, od[0], od[1], od[2], co)
         taps, ws = conv_taps(weight, d, p)
+        self.need_halo(x, taps, s[0], od[0])
         self.add(ConvOp([x], taps, ws, bias, od, out0=out, act=act, res1=res1, res2=res2, stride=s, out1=out1,
                         out1_mode=out1_mode, out1_coff=out1_coff, name=name, impl=impl, res2_post=res2_post))
         return out
@@ -289,6 +339,8 @@ class Plan:
         co = weights[0].shape[0]
         if out is None:
             out = self.alloc(B, ID, IH, IW, co)
+        for i, src in enumerate(srcs):
+            self.need_halo(src, [t for t in taps if t[0] == i], 1, ID)
         self.add(ConvOp(srcs, taps, ws, bias, (ID, IH, IW), out0=out, act=act, res1=res1, res2=res2, name=name,
                         impl=impl))
         return out
@@ -303,6 +355,7 @@ class Plan:
         if out is None:
             out = self.alloc(B, 2 * ID, 2 * IH, 2 * IW, co)
         sel = {0: [(1, 0)], 1: [(2, 0), (0, 1)]}  # parity -> [(kernel index, input offset)]
+        self.need_halo(x, [(0, 1, 0, 0)], 1, ID)
         for pd in (0, 1):
             for ph in (0, 1):
                 for pw in (0, 1):
@@ -344,6 +397,9 @@ class Plan:
         """Per-launch device times (CUDA events on the launching stream); returns [(name, ms, flops)]."""
         st = _lib.stream_ptr()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.ops) + 1)]
+        # park the GPU on a spin kernel while the host enqueues everything: the event deltas then measure
+        # back-to-back device execution instead of host launch latency
+        torch.cuda._sleep(int(1.9e9 * 0.04))
         evs[0].record()
         for i, op in enumerate(self.ops):
             op.run(st)

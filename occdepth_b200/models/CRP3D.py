@@ -41,11 +41,22 @@ class CPMegaVoxels(B200Module):
         B, D, H, W = x.dims
         N, M, R = self.flatten_size, self.flatten_context_size, self.n_relations
         F1, F2 = self.feature, self.context_feature
-        assert D * H * W == N
+        slab = plan.slab
+        if slab is None:
+            assert D * H * W == N
+        else:   # X-slab partition: this rank holds N / world voxels; the mega-context is all-gathered
+            assert B == 1 and D * H * W * slab.world == N
+            N = D * H * W
         x_agg = self.aspp.emit(plan, x)
         conv = self.mega_context[0]
         w, b = fold_bn(conv.weight, conv.bias, None)
         ctx = plan.conv(x_agg, w, b, stride=2, padding=conv.padding, name="crp.mega_context")   # [B, M pos, F2]
+        if slab is not None:
+            from ..engine import CL
+            _, cd, ch, cw = ctx.dims
+            full = CL.alloc(1, cd * slab.world, ch, cw, F2, plan.device)
+            plan.add(slab.all_gather_op(ctx.interior(), full.buf))
+            ctx = full
         assert ctx.spatial() == M
         # mega-context as the K-major B operand of the bmm: wbuf[b][f][m] = ctx[b][m][f]
         Kp = kpad_for(M)
@@ -65,8 +76,8 @@ class CPMegaVoxels(B200Module):
             sig = plan.conv(x_agg, w, b, act="sigmoid", out1=p_view, out1_mode="planar", out1_coff=r * M,
                             name="crp.rel%d" % r)                                   # [B, N pos, M] sigmoid
             for bi in range(B):
-                src = type(sig)(sig.buf[bi:bi + 1], sig.C, sig.coff)
-                dst = type(cat)(cat.buf[bi:bi + 1], F2, F1 + r * F2)
+                src = type(sig)(sig.buf[bi:bi + 1], sig.C, sig.coff, sig.d0, sig.dlen)
+                dst = type(cat)(cat.buf[bi:bi + 1], F2, F1 + r * F2, cat.d0, cat.dlen)
                 plan.add(ConvOp([src], [(0, 0, 0, 0)], None, zero_bias, (D, H, W), out0=dst, weight_buf=wbuf[bi],
                                 name="crp.bmm%d" % r))
         conv = self.resize[0]

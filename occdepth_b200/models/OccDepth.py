@@ -120,9 +120,19 @@ class OccDepth(_Base, B200Module):
 
     # ------------------------------------------------------------------------------------------
     def _build(self, B, V, H, W, N, P, dev, batch):
-        plan = Plan(dev)
+        slab = self.__dict__.get("slab_ctx")
+        plan = Plan(dev, slab=slab)
         ps = self.project_scale
         S = [int(s) // ps for s in self.full_scene_size]
+        n_lo = 0
+        if slab is not None:
+            # one frame, X-slab partition: this rank lifts and decodes planes [x_lo, x_hi) of the voxel grid; the
+            # 2D network is replicated (its receptive field is global: SE pooling) -- SURVEY.md section 8e
+            if B != 1 or self.dataset != "kitti":
+                raise NotImplementedError("slab partition: batch size 1, KITTI voxel order (X-major) only")
+            x_lo, x_hi = slab.slab(S[0])
+            n_lo, N = x_lo * S[1] * S[2], (x_hi - x_lo) * S[1] * S[2]
+            S = [x_hi - x_lo, S[1], S[2]]
         virtual = V == 1 and "gt_depth" in batch                          # process_rgbs, OccDepth.py:221-229
         VL = 2 if virtual else V                                           # views seen by the lift
         img = plan.alloc(B * V, 1, H, W, 3)
@@ -171,17 +181,20 @@ class OccDepth(_Base, B200Module):
             out_b = CL(x3d.buf[b:b + 1], x3d.C, 0)
             pr = prior[b] if prior is not None else None
             plan.add(FnOp(lambda st, feats=feats, pb=pix[b], fb=fov[b], ob=out_b, pr=pr:
-                          (lift_multiscale(feats, scales, pb, fb, ob, self.dataset, self.full_scene_size, ps,
+                          (lift_multiscale(feats, scales, pb, fb, ob, self.dataset,
+                                           [S[0] * ps, S[1] * ps, S[2] * ps], ps,
                                            prior=pr, scale_const=100.0, stream=st), 0)[1],
                           "sfa_lift", keep=(feats, pix, fov, out_b)))
         out = self.net_3d_decoder.emit(plan, x3d)
-        if os.environ.get("OCCDEPTH_CUDA_GRAPH", "1") == "1":
+        if slab is not None and self.trans_2d_to_3d == "flosp_depth":
+            raise NotImplementedError("slab partition with the FlospDepth prior is not built")
+        if os.environ.get("OCCDEPTH_CUDA_GRAPH", "1") == "1" and slab is None:
             try:
                 plan.capture()
             except Exception as e:  # noqa: BLE001 -- same kernels either way; only the launch mechanism differs
                 print("WARNING: CUDA graph capture failed (%r); launching kernels individually" % (e,))
                 plan.graph = None
-        return plan, img, pix, fov, out, depth0
+        return plan, img, pix, fov, out, depth0, n_lo
 
     def forward(self, batch):
         img = batch["img"]
@@ -199,19 +212,22 @@ class OccDepth(_Base, B200Module):
         fm = batch["fov_mask_{}".format(ps)]
         N, P = pp[0].shape[1], pp[0].shape[2]
         virtual = V == 1 and "gt_depth" in batch
-        key = (B, V, H, W, N, P, str(dev), virtual, float(batch["virtual_bf"][0]) if virtual else 0.0)
+        slab = self.__dict__.get("slab_ctx")
+        key = (B, V, H, W, N, P, str(dev), virtual, float(batch["virtual_bf"][0]) if virtual else 0.0,
+               None if slab is None else (slab.rank, slab.world))
         ent = self._plans().get(key)
         if ent is None:
             with torch.no_grad():
                 ent = self._build(B, V, H, W, N, P, dev, batch)
             self._plans()[key] = ent
-        plan, img_cl, pix, fov, out, depth0 = ent
+        plan, img_cl, pix, fov, out, depth0, n_lo = ent
         CL.from_planar(img.reshape(B * V, 3, H, W), out=img_cl)
         if depth0 is not None:
             depth0.copy_(batch["gt_depth"][0, 0], non_blocking=True)
+        nl = pix.shape[2]
         for b in range(B):
-            pix[b].copy_(pp[b], non_blocking=True)
-            fov[b].copy_(fm[b], non_blocking=True)
+            pix[b].copy_(pp[b][:, n_lo:n_lo + nl], non_blocking=True)
+            fov[b].copy_(fm[b][:, n_lo:n_lo + nl], non_blocking=True)
         if self.trans_2d_to_3d == "flosp_depth":
             self.flosp_depth.stage_inputs(batch, dev)
         plan.run()

@@ -20,6 +20,13 @@ class B200Module(nn.Module):
             self.__dict__["_plan_cache"] = d
         return d
 
+    def enable_slab_parallel(self, ctx):
+        """X-slab partition of one frame over the ranks of `ctx` (parallel.SlabContext): forward() then takes /
+        returns this rank's X-slab of every 3-D tensor and exchanges halo planes with its neighbours."""
+        self.__dict__["slab_ctx"] = ctx
+        self.invalidate_plans()
+        return self
+
     def invalidate_plans(self):
         for m in self.modules():
             if isinstance(m, B200Module):
@@ -39,13 +46,14 @@ class B200Module(nn.Module):
             raise RuntimeError("%s: occdepth_b200 implements the forward/inference path only; call .eval() "
                                "(BatchNorm is folded from running statistics)" % type(self).__name__)
 
-    def _run_planar(self, x, squeeze_d=False):
-        """x: planar fp32 [B,C,D,H,W] / [B,C,H,W]; returns emit()'s CL output(s) converted back to planar fp32."""
+    def _get_plan(self, x):
+        """(plan, input CL, emit() result) for planar input x, built on first use"""
         self._check_mode(x)
-        key = (tuple(x.shape), str(x.device))
+        slab = self.__dict__.get("slab_ctx")
+        key = (tuple(x.shape), str(x.device), None if slab is None else (slab.rank, slab.world))
         ent = self._plans().get(key)
         if ent is None:
-            plan = Plan(x.device)
+            plan = Plan(x.device, slab=slab)
             if x.dim() == 4:
                 B, C_, H, W = x.shape
                 D = 1
@@ -56,7 +64,11 @@ class B200Module(nn.Module):
                 y = self.emit(plan, xin)
             ent = (plan, xin, y)
             self._plans()[key] = ent
-        plan, xin, y = ent
+        return ent
+
+    def _run_planar(self, x, squeeze_d=False):
+        """x: planar fp32 [B,C,D,H,W] / [B,C,H,W]; returns emit()'s CL output(s) converted back to planar fp32."""
+        plan, xin, y = self._get_plan(x)
         CL.from_planar(x, out=xin)
         plan.run()
         return _to_planar(y, squeeze_d)
