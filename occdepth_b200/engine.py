@@ -277,7 +277,7 @@ class Plan:
         self.device = device
         self.ops = []
         self.flops = 0
-        self.graph = None
+        self.graph, self.graph_ops = None, 0
         self.slab = slab            # parallel.SlabContext for the X-slab multi-GPU partition, else None
         self._exchanged = set()
 
@@ -375,22 +375,34 @@ class Plan:
         """Replays the launches on the current stream (through a captured CUDA graph when enabled)."""
         if stream is None and self.graph is not None:
             self.graph.replay()
+            st = _lib.stream_ptr()
+            for op in self.ops[self.graph_ops:]:
+                op.run(st)
             return
         st = _lib.stream_ptr() if stream is None else stream
         for op in self.ops:
             op.run(st)
 
     def capture(self):
-        """Capture the launch sequence into a CUDA graph (buffers are static, so replay is valid)."""
+        """Capture the launch sequence into a CUDA graph (buffers are static, so replay is valid).  Communication
+        ops (NCCL halo exchange / all-gather of the slab partition) are not captured: the graph covers the ops
+        before the first of them (the replicated 2D network and the lift), the rest is launched eagerly."""
         self.graph = None
+        n = len(self.ops)
+        for i, op in enumerate(self.ops):
+            if getattr(op, "name", "") in ("halo_exchange", "all_gather"):
+                n = i
+                break
         self.run()                      # warm-up outside capture (lazy module loading, func attributes)
         torch.cuda.synchronize()
+        if n == 0:
+            return None
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             st = _lib.stream_ptr()
-            for op in self.ops:
+            for op in self.ops[:n]:
                 op.run(st)
-        self.graph = g
+        self.graph, self.graph_ops = g, n
         return g
 
     def profile(self):

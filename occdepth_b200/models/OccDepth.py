@@ -178,7 +178,7 @@ class OccDepth(_Base, B200Module):
                     f = x_rgb["1_%d" % s]
                     assert f.coff == 0 and f.cstride == Cf
                     feats.append(f.buf[b * V:(b + 1) * V, 0])               # [V, h, w, Cf] contiguous view
-            out_b = CL(x3d.buf[b:b + 1], x3d.C, 0)
+            out_b = CL(x3d.buf[b:b + 1], x3d.C, 0, x3d.d0, x3d.dlen)
             pr = prior[b] if prior is not None else None
             plan.add(FnOp(lambda st, feats=feats, pb=pix[b], fb=fov[b], ob=out_b, pr=pr:
                           (lift_multiscale(feats, scales, pb, fb, ob, self.dataset,
@@ -188,7 +188,7 @@ class OccDepth(_Base, B200Module):
         out = self.net_3d_decoder.emit(plan, x3d)
         if slab is not None and self.trans_2d_to_3d == "flosp_depth":
             raise NotImplementedError("slab partition with the FlospDepth prior is not built")
-        if os.environ.get("OCCDEPTH_CUDA_GRAPH", "1") == "1" and slab is None:
+        if os.environ.get("OCCDEPTH_CUDA_GRAPH", "1") == "1":
             try:
                 plan.capture()
             except Exception as e:  # noqa: BLE001 -- same kernels either way; only the launch mechanism differs
