@@ -171,19 +171,20 @@ int occd_copy_channels(const void* in, void* out, long long positions, int C, in
 
 /* -------------------------------------------------------------------------------------------- */
 /* EfficientNet / decoder bandwidth kernels (channels-last bf16, 2-D)                             */
-/* depthwise KxK (K = 3|5) conv + folded BN + activation; optionally accumulates the per-channel  */
-/* spatial SUM of the output into pool[B][C] (squeeze of geffnet SqueezeExcite); explicit         */
-/* top/left padding implements TF "SAME" (bottom/right implied by OH/OW). w: fp32 [K*K][C].       */
-int occd_dwconv2d_fwd(const void* in, const float* w, const float* bias, void* out, float* pool, int B, int H,
+/* depthwise KxK (K = 3|5) conv + folded BN + activation; optionally accumulates the per-channel    */
+/* spatial SUM of the output into pool[B][C] (squeeze of geffnet SqueezeExcite) as 64-bit FIXED-    */
+/* POINT integers in units of 2^-24 (integer atomics: bit-reproducible); explicit top/left padding  */
+/* implements TF "SAME" (bottom/right implied by OH/OW). w: fp32 [K*K][C].                          */
+int occd_dwconv2d_fwd(const void* in, const float* w, const float* bias, void* out, long long* pool, int B, int H,
                       int W, int OH, int OW, int C, int cs_in, int cs_out, int K, int stride, int pad_top,
                       int pad_left, int act, void* stream);
-/* gate[b][c] = sigmoid(W2 silu(W1 (pool[b]/HW) + b1) + b2); zeroes pool. w1 [R][C], w2t [R][C];  */
-/* `gate` must hold B*C + B*R floats (the hidden layer is staged behind the gates)               */
-int occd_se_gate_fwd(float* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
+/* gate[b][c] = sigmoid(W2 silu(W1 (pool[b] 2^-24 / HW) + b1) + b2); zeroes pool. w1 [R][C],       */
+/* w2t [R][C]; `gate` must hold B*C + B*R floats (the hidden layer is staged behind the gates)     */
+int occd_se_gate_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
                      const float* b2, float* gate, int B, int C, int R, void* stream);
 /* fused single-image path: squeeze-excite MLP + gate folded into the projection weights          */
 /* wout[row][k] = bf16(master[row][k] * gate[k]); hidden: R floats of scratch; zeroes pool        */
-int occd_se_gate_fold_fwd(float* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
+int occd_se_gate_fold_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
                           const float* b2, float* hidden, const float* master, void* wout, int C, int R,
                           int rows, int Kpad, void* stream);
 /* out[row][k] = bf16(master[row][k] * gate[k]): folds x * gate into the next 1x1 conv's weights   */

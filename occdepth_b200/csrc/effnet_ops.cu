@@ -19,11 +19,13 @@ constexpr int kDwRows = 4;  // output rows per block (amortises the squeeze atom
 // (kDwPX-1)*S + K input vectors it needs ONCE and reuses them across the K taps and kDwPX outputs (2.5x fewer
 // loads/unpacks than one-pixel-per-thread for K = 5).  CVB in {8,16,32} is picked per layer so narrow layers
 // (C = 64) keep every lane busy.  The squeeze (global-average-pool sum) is accumulated in registers, reduced
-// across threadIdx.y in shared memory and flushed with one atomicAdd per channel per block.
+// across threadIdx.y in shared memory and added to pool[b][c] as a 64-bit FIXED-POINT integer (2^-24 units): integer
+// atomics commute exactly, so the SE gates (and everything downstream) are bit-reproducible run to run -- float
+// atomics are not.
 template <int K, int S, int CVB>
 __global__ void __launch_bounds__(kDwThreads)
 dwconv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-              __nv_bfloat16* __restrict__ out, float* __restrict__ pool, int H, int W, int OH, int OW, int C,
+              __nv_bfloat16* __restrict__ out, long long* __restrict__ pool, int H, int W, int OH, int OW, int C,
               int cs_in, int cs_out, int pad_top, int pad_left, int act) {
   constexpr int PY = kDwThreads / CVB;
   constexpr int NIN = (kDwPX - 1) * S + K;
@@ -109,7 +111,8 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
         float s = 0.f;
 #pragma unroll
         for (int y = 0; y < PY; ++y) s += red[y][tx * 8 + i];
-        atomicAdd(pool + (long long)b * C + c0 + i, s);
+        atomicAdd(reinterpret_cast<unsigned long long*>(pool) + (long long)b * C + c0 + i,
+                  (unsigned long long)__float2ll_rn(s * 16777216.f));
       }
     }
   }
@@ -119,14 +122,15 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
 //   hidden[b][r] = silu(b1[r] + <w1[r], pool[b] / HW>)          grid (R, B), one block per hidden unit
 //   gate[b][c]   = sigmoid(b2[c] + sum_r w2t[r][c] hidden[b][r]) grid (ceil(C/256), B); also clears pool
 __global__ void __launch_bounds__(128)
-se_fc1_kernel(const float* __restrict__ pool, float inv_hw, const float* __restrict__ w1,
+se_fc1_kernel(const long long* __restrict__ pool, float inv_hw, const float* __restrict__ w1,
               const float* __restrict__ b1, float* __restrict__ hidden, int C, int R) {
   __shared__ float red[4];
   const int r = blockIdx.x, b = blockIdx.y;
   const float* wr = w1 + (long long)r * C;
-  const float* pb = pool + (long long)b * C;
+  const long long* pb = pool + (long long)b * C;
   float s = 0.f;
-  for (int c = threadIdx.x; c < C; c += 128) s = fmaf(__ldg(wr + c), pb[c], s);
+  for (int c = threadIdx.x; c < C; c += 128)
+    s = fmaf(__ldg(wr + c), (float)((double)pb[c] * (1.0 / 16777216.0)), s);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -138,7 +142,7 @@ se_fc1_kernel(const float* __restrict__ pool, float inv_hw, const float* __restr
 }
 
 __global__ void __launch_bounds__(256)
-se_fc2_kernel(float* __restrict__ pool, const float* __restrict__ hidden, const float* __restrict__ w2t,
+se_fc2_kernel(long long* __restrict__ pool, const float* __restrict__ hidden, const float* __restrict__ w2t,
               const float* __restrict__ b2, float* __restrict__ gate, int C, int R) {
   extern __shared__ float hid[];
   const int b = blockIdx.y;
@@ -149,13 +153,13 @@ se_fc2_kernel(float* __restrict__ pool, const float* __restrict__ hidden, const 
   float s = b2[c];
   for (int r = 0; r < R; ++r) s = fmaf(__ldg(w2t + (long long)r * C + c), hid[r], s);
   gate[(long long)b * C + c] = __fdividef(1.f, 1.f + __expf(-s));
-  pool[(long long)b * C + c] = 0.f;  // ready for the next forward
+  pool[(long long)b * C + c] = 0;  // ready for the next forward
 }
 
 // fused: gate for a strip of 256 input channels (second FC + sigmoid), then that strip of the projection
 // weights scaled and packed to bf16 for `rows_per_block` output rows.  grid (ceil(Kpad/256), row blocks)
 __global__ void __launch_bounds__(256)
-se_fc2_fold_kernel(float* __restrict__ pool, const float* __restrict__ hidden, const float* __restrict__ w2t,
+se_fc2_fold_kernel(long long* __restrict__ pool, const float* __restrict__ hidden, const float* __restrict__ w2t,
                    const float* __restrict__ b2, const float* __restrict__ master, __nv_bfloat16* __restrict__ out,
                    int C, int R, int rows, int Kpad, int rows_per_block) {
   extern __shared__ float hid[];
@@ -168,7 +172,7 @@ se_fc2_fold_kernel(float* __restrict__ pool, const float* __restrict__ hidden, c
     float s = b2[k];
     for (int r = 0; r < R; ++r) s = fmaf(__ldg(w2t + (long long)r * C + k), hid[r], s);
     g = __fdividef(1.f, 1.f + __expf(-s));
-    if (blockIdx.y == 0) pool[k] = 0.f;  // ready for the next forward
+    if (blockIdx.y == 0) pool[k] = 0;  // ready for the next forward
   }
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(rows, r0 + rows_per_block);
@@ -223,7 +227,7 @@ __global__ void upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, _
 
 }  // namespace
 
-extern "C" int occd_dwconv2d_fwd(const void* in, const float* w, const float* bias, void* out, float* pool, int B,
+extern "C" int occd_dwconv2d_fwd(const void* in, const float* w, const float* bias, void* out, long long* pool, int B,
                                  int H, int W, int OH, int OW, int C, int cs_in, int cs_out, int K, int stride,
                                  int pad_top, int pad_left, int act, void* stream) {
   OCCD_CHECK_ARG(in && w && bias && out && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "occd_dwconv2d_fwd: args");
@@ -259,7 +263,7 @@ extern "C" int occd_dwconv2d_fwd(const void* in, const float* w, const float* bi
   return OCCD_OK;
 }
 
-extern "C" int occd_se_gate_fwd(float* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
+extern "C" int occd_se_gate_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
                                 const float* b2, float* gate, int B, int C, int R, void* stream) {
   OCCD_CHECK_ARG(pool && w1 && b1 && w2t && b2 && gate && B > 0 && C > 0 && R > 0, "occd_se_gate_fwd: args");
   OCCD_CHECK_ARG(R <= 8192 && B <= 65535, "occd_se_gate_fwd: R/B too large");
@@ -300,7 +304,7 @@ extern "C" int occd_upsample_bilinear_ac(const void* in, void* out, int B, int h
   return OCCD_OK;
 }
 
-extern "C" int occd_se_gate_fold_fwd(float* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
+extern "C" int occd_se_gate_fold_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
                                      const float* b2, float* hidden, const float* master, void* wout, int C, int R,
                                      int rows, int Kpad, void* stream) {
   OCCD_CHECK_ARG(pool && w1 && b1 && w2t && b2 && hidden && master && wout && C > 0 && R > 0 && rows > 0 &&

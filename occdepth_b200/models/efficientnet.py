@@ -70,7 +70,7 @@ def _emit_dw_se_project(plan, x, conv_dw, bn_dw, se, conv_proj, bn_proj, k, stri
     w, b = fold_bn(conv_dw.weight, None, bn_dw)
     wdw = w.reshape(Cm, k * k).t().contiguous()                # [K*K][C] fp32
     y = plan.alloc(B, 1, OH, OW, Cm)
-    pool = torch.zeros(B, Cm, dtype=torch.float32, device=dev)
+    pool = torch.zeros(B, Cm, dtype=torch.int64, device=dev)      # squeeze sums, fixed point 2^-24 (deterministic)
     plan.add(FnOp(lambda st: L.occd_dwconv2d_fwd(x.ptr, wdw.data_ptr(), b.data_ptr(), y.ptr, pool.data_ptr(), B, H,
                                                  W, OH, OW, Cm, x.cstride, y.cstride, k, stride, pt, pl,
                                                  _lib.ACT_SILU, st), name + ".dw", keep=(x, wdw, b, y, pool)))

@@ -17,7 +17,7 @@ for n in names:
     y = torch.empty(B, OH, OW, C, device=dev, dtype=torch.bfloat16)
     w = torch.randn(K * K, C, device=dev)
     b = torch.randn(C, device=dev)
-    pool = torch.zeros(B, C, device=dev)
+    pool = torch.zeros(B, C, dtype=torch.int64, device=dev)
     pad = max((OH - 1) * S + K - H, 0) // 2
     for use_pool in (True, False):
         def run():
