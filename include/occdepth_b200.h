@@ -124,6 +124,8 @@ typedef struct {
   const void* weight;
   const float* bias;
   int Cout, Cout_pad, Kpad;
+  int weight_per_image; /* 1: weight holds B consecutive [n_taps][Cout_pad][Kpad] sets, image b uses set b   */
+                        /* (SE gate folded into the projection weights of each image); TC impl only        */
   /* iteration space of the launch and its mapping to output coordinates: o_full = o*omul + oadd    */
   int OD, OH, OW;
   int omul[3], oadd[3];
@@ -182,10 +184,10 @@ int occd_dwconv2d_fwd(const void* in, const float* w, const float* bias, void* o
 /* w2t [R][C]; `gate` must hold B*C + B*R floats (the hidden layer is staged behind the gates)     */
 int occd_se_gate_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
                      const float* b2, float* gate, int B, int C, int R, void* stream);
-/* fused single-image path: squeeze-excite MLP + gate folded into the projection weights          */
-/* wout[row][k] = bf16(master[row][k] * gate[k]); hidden: R floats of scratch; zeroes pool        */
+/* fused path: squeeze-excite MLP + gate folded into one projection-weight set per image:          */
+/* wout[b][row][k] = bf16(master[row][k] * gate[b][k]); hidden: B*R floats of scratch; zeroes pool  */
 int occd_se_gate_fold_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
-                          const float* b2, float* hidden, const float* master, void* wout, int C, int R,
+                          const float* b2, float* hidden, const float* master, void* wout, int B, int C, int R,
                           int rows, int Kpad, void* stream);
 /* out[row][k] = bf16(master[row][k] * gate[k]): folds x * gate into the next 1x1 conv's weights   */
 int occd_scale_weights(const float* master, const float* gate, void* out, int rows, int Kpad, int C,

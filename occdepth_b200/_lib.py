@@ -67,6 +67,7 @@ class ConvDesc(C.Structure):
         ("weight", C.c_void_p),
         ("bias", C.c_void_p),
         ("Cout", C.c_int), ("Cout_pad", C.c_int), ("Kpad", C.c_int),
+        ("weight_per_image", C.c_int),
         ("OD", C.c_int), ("OH", C.c_int), ("OW", C.c_int),
         ("omul", C.c_int * 3), ("oadd", C.c_int * 3),
         ("ODf", C.c_int), ("OHf", C.c_int), ("OWf", C.c_int),
@@ -102,7 +103,7 @@ SYMBOLS = {
     "occd_copy_channels": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     "occd_dwconv2d_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp] + [_i] * 13 + [_vp]),
     "occd_se_gate_fwd": (C.c_int, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "occd_se_gate_fold_fwd": (C.c_int, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "occd_se_gate_fold_fwd": (C.c_int, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "occd_scale_weights": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "occd_frustum_sample_fwd": (C.c_int, [_vp, _vp] + [_i] * 7 + [_f] * 4 + [_i, _vp, _i, _vp]),
     "occd_softmax_planar": (C.c_int, [_vp, _vp, _ll, _i, _ll, _vp]),

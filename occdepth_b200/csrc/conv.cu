@@ -22,6 +22,7 @@ struct TcParams {
   int n_kchunks[OCCD_CONV_MAX_SRC];
   int tiles_w, tiles_h, tiles_d, num_m_tiles;
   int src_d0;
+  int w_batch_rows;  // weight rows per image (0: shared weights)
   int TD, TH, TW;
   int stride[3];
   int Cout_pad, N_tile;
@@ -113,7 +114,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         for (int tp = 0; tp < p.n_taps; ++tp) {
           const int src = p.tap_src[tp];
           const int cw = iw0 + p.tap_dx[tp], ch = ih0 + p.tap_dy[tp], cd = id0 + p.tap_dz[tp];
-          const int wrow = tp * p.Cout_pad + n0;
+          const int wrow = b * p.w_batch_rows + tp * p.Cout_pad + n0;
           const int nk = p.n_kchunks[src];
           for (int kc = 0; kc < nk; ++kc) {
             if (g == 0) {
@@ -449,6 +450,7 @@ struct SimtParams {
   int stride[3];
   const __nv_bfloat16* weight;
   int Cout_pad, Kpad;
+  int w_batch_rows;
   signed char tap_src[OCCD_CONV_MAX_TAPS];
   short tap_dz[OCCD_CONV_MAX_TAPS], tap_dy[OCCD_CONV_MAX_TAPS], tap_dx[OCCD_CONV_MAX_TAPS];
 };
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ 
     if (id < 0 || id >= p.ID || ih < 0 || ih >= p.IH || iw < 0 || iw >= p.IW) continue;
     const __nv_bfloat16* in =
         p.src[s] + ((((long long)b * p.ID + id) * p.IH + ih) * p.IW + iw) * p.src_cstride[s] + p.src_coff[s];
-    const __nv_bfloat16* w = p.weight + ((long long)tp * p.Cout_pad + g * 8) * p.Kpad;
+    const __nv_bfloat16* w = p.weight + ((long long)b * p.w_batch_rows + (long long)tp * p.Cout_pad + g * 8) * p.Kpad;
     const int C = p.src_C[s];
     for (int c = 0; c < C; c += 8) {
       float x[8];
@@ -725,6 +727,7 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
   }
   OCCD_CHECK_ARG(d->impl == OCCD_CONV_IMPL_TC || d->impl == OCCD_CONV_IMPL_SIMT || d->impl == OCCD_CONV_IMPL_HALO,
                  "occd_conv_plan_create: impl");
+  OCCD_CHECK_ARG(!d->weight_per_image || d->impl != OCCD_CONV_IMPL_HALO, "occd_conv_plan_create: per-image weights: TC or SIMT impl");
 
   occd_conv_plan* pl = new (std::nothrow) occd_conv_plan;
   OCCD_CHECK_ARG(pl != nullptr, "occd_conv_plan_create: out of memory");
@@ -743,6 +746,7 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
     for (int i = 0; i < 3; ++i) s.stride[i] = d->stride[i];
     s.weight = reinterpret_cast<const __nv_bfloat16*>(d->weight);
     s.Cout_pad = d->Cout_pad; s.Kpad = d->Kpad;
+    s.w_batch_rows = d->weight_per_image ? d->n_taps * d->Cout_pad : 0;
     for (int i = 0; i < d->n_taps; ++i) {
       s.tap_src[i] = (signed char)d->taps[i].src;
       s.tap_dz[i] = (short)d->taps[i].dz; s.tap_dy[i] = (short)d->taps[i].dy; s.tap_dx[i] = (short)d->taps[i].dx;
@@ -772,6 +776,7 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
   }
   t.n_taps = d->n_taps;
   t.src_d0 = d->src_d0;
+  t.w_batch_rows = d->weight_per_image ? d->n_taps * d->Cout_pad : 0;
   for (int s = 0; s < OCCD_CONV_MAX_SRC; ++s) t.n_kchunks[s] = s < d->n_src ? (d->src_C[s] + KC - 1) / KC : 0;
   for (int i = 0; i < 3; ++i) t.stride[i] = d->stride[i];
   for (int i = 0; i < d->n_taps; ++i) {
@@ -885,7 +890,8 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
   }
   for (int s = d->n_src; s < OCCD_CONV_MAX_SRC; ++s) pl->tmA[s] = pl->tmA[0];
   {
-    cuuint64_t gdim[2] = {(cuuint64_t)d->Kpad, (cuuint64_t)d->n_taps * d->Cout_pad};
+    cuuint64_t gdim[2] = {(cuuint64_t)d->Kpad,
+                          (cuuint64_t)d->n_taps * d->Cout_pad * (d->weight_per_image ? d->B : 1)};
     cuuint64_t gstr[1] = {(cuuint64_t)d->Kpad * 2};
     cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)t.N_tile};
     cuuint32_t estr[2] = {1, 1};

@@ -163,7 +163,8 @@ se_fc2_fold_kernel(long long* __restrict__ pool, const float* __restrict__ hidde
                    const float* __restrict__ b2, const float* __restrict__ master, __nv_bfloat16* __restrict__ out,
                    int C, int R, int rows, int Kpad, int rows_per_block) {
   extern __shared__ float hid[];
-  for (int r = threadIdx.x; r < R; r += 256) hid[r] = hidden[r];
+  const int img = blockIdx.z;   // one weight set per image
+  for (int r = threadIdx.x; r < R; r += 256) hid[r] = hidden[(long long)img * R + r];
   __syncthreads();
   const int k = blockIdx.x * 256 + threadIdx.x;
   if (k >= Kpad) return;
@@ -172,12 +173,13 @@ se_fc2_fold_kernel(long long* __restrict__ pool, const float* __restrict__ hidde
     float s = b2[k];
     for (int r = 0; r < R; ++r) s = fmaf(__ldg(w2t + (long long)r * C + k), hid[r], s);
     g = __fdividef(1.f, 1.f + __expf(-s));
-    if (blockIdx.y == 0) pool[k] = 0;  // ready for the next forward
+    if (blockIdx.y == 0) pool[(long long)img * C + k] = 0;  // ready for the next forward
   }
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(rows, r0 + rows_per_block);
+  __nv_bfloat16* o = out + (long long)img * rows * Kpad;
   for (int r = r0; r < r1; ++r)
-    out[(long long)r * Kpad + k] = __float2bfloat16_rn(__ldg(master + (long long)r * Kpad + k) * g);
+    o[(long long)r * Kpad + k] = __float2bfloat16_rn(__ldg(master + (long long)r * Kpad + k) * g);
 }
 
 // out[row][k] = bf16(master[row][k] * gate[k])  (k < C), rows = Cout_pad, row length Kpad
@@ -305,17 +307,18 @@ extern "C" int occd_upsample_bilinear_ac(const void* in, void* out, int B, int h
 }
 
 extern "C" int occd_se_gate_fold_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
-                                     const float* b2, float* hidden, const float* master, void* wout, int C, int R,
-                                     int rows, int Kpad, void* stream) {
+                                     const float* b2, float* hidden, const float* master, void* wout, int B, int C,
+                                     int R, int rows, int Kpad, void* stream) {
   OCCD_CHECK_ARG(pool && w1 && b1 && w2t && b2 && hidden && master && wout && C > 0 && R > 0 && rows > 0 &&
                  Kpad >= C && R <= 8192, "occd_se_gate_fold_fwd: args");
   cudaStream_t st = (cudaStream_t)stream;
-  se_fc1_kernel<<<dim3(R, 1), 128, 0, st>>>(pool, inv_hw, w1, b1, hidden, C, R);
+  OCCD_CHECK_ARG(B >= 1 && B <= 65535, "occd_se_gate_fold_fwd: B");
+  se_fc1_kernel<<<dim3(R, B), 128, 0, st>>>(pool, inv_hw, w1, b1, hidden, C, R);
   OCCD_CHECK_LAUNCH();
   const int kblocks = (Kpad + 255) / 256;
   int rows_per_block = rows;
-  while (rows_per_block > 16 && kblocks * ((rows + rows_per_block - 1) / rows_per_block) < 296) rows_per_block /= 2;
-  dim3 grid(kblocks, (rows + rows_per_block - 1) / rows_per_block);
+  while (rows_per_block > 16 && B * kblocks * ((rows + rows_per_block - 1) / rows_per_block) < 296) rows_per_block /= 2;
+  dim3 grid(kblocks, (rows + rows_per_block - 1) / rows_per_block, B);
   se_fc2_fold_kernel<<<grid, 256, R * sizeof(float), st>>>(pool, hidden, w2t, b2, master,
                                                            (__nv_bfloat16*)wout, C, R, rows, Kpad, rows_per_block);
   OCCD_CHECK_LAUNCH();

@@ -150,7 +150,7 @@ class ConvOp:
 
     def __init__(self, srcs, taps, tap_weights, bias, out_dims, out0=None, act="none", res1=None, res2=None,
                  stride=(1, 1, 1), omul=(1, 1, 1), oadd=(0, 0, 0), full_dims=None, out1=None, out1_mode="none",
-                 out1_coff=0, impl=None, name="", res2_post=False, weight_buf=None):
+                 out1_coff=0, impl=None, name="", res2_post=False, weight_buf=None, weight_per_image=False):
         """srcs: list[CL] (same B,D,H,W);  taps: [(src_idx, dz, dy, dx)];  tap_weights: list of fp32 [Cout, C_src]
         bias: fp32 [Cout];  out0/res1/res2: CL on the full output grid;  out1: CL (pre-activation bf16 copy) or
         fp32 planar tensor [B, C1, D, H, W] (mode "planar", written at channel out1_coff)."""
@@ -166,7 +166,8 @@ class ConvOp:
         Kpad = _round_up(maxC, KC)
         if weight_buf is not None:
             # weights produced at run time by another launch (CRP bmm): bf16 [n_taps, Cout_pad, Kpad]
-            assert weight_buf.dtype == torch.bfloat16 and tuple(weight_buf.shape) == (len(taps), Cout_pad, Kpad)
+            nset = B if weight_per_image else 1
+            assert weight_buf.dtype == torch.bfloat16 and tuple(weight_buf.shape) == (nset * len(taps), Cout_pad, Kpad)
             self.weight = weight_buf
         else:
             wp = torch.zeros(len(taps), Cout_pad, Kpad, dtype=torch.float32, device=dev)
@@ -200,6 +201,7 @@ class ConvOp:
             d.taps[i].src, d.taps[i].dz, d.taps[i].dy, d.taps[i].dx = si, dz, dy, dx
         d.weight, d.bias = self.weight.data_ptr(), self.bias.data_ptr()
         d.Cout, d.Cout_pad, d.Kpad = Cout, Cout_pad, Kpad
+        d.weight_per_image = 1 if weight_per_image else 0
         d.OD, d.OH, d.OW = OD, OH, OW
         d.ODf, d.OHf, d.OWf = fd
         d.act = ACT[act]

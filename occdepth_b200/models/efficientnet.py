@@ -87,15 +87,14 @@ def _emit_dw_se_project(plan, x, conv_dw, bn_dw, se, conv_proj, bn_proj, k, stri
     if out is None:
         out = plan.alloc(B, 1, OH, OW, Cout)
     hidden = torch.empty(B, R, dtype=torch.float32, device=dev)
-    for bi in range(B):   # the gate is per image -> per-image projection weights
-        wbuf = torch.zeros(1, Cout_pad, Kp, dtype=torch.bfloat16, device=dev)
-        plan.add(FnOp(lambda st, pb=pool[bi], hb=hidden[bi], wb=wbuf: L.occd_se_gate_fold_fwd(
-            pb.data_ptr(), 1.0 / (OH * OW), w1.data_ptr(), b1.data_ptr(), w2t.data_ptr(), b2.data_ptr(),
-            hb.data_ptr(), master.data_ptr(), wb.data_ptr(), Cm, R, Cout_pad, Kp, st),
-            name + ".se", keep=(pool, w1, b1, w2t, b2, hidden, master, wbuf)))
-        sl = lambda c: type(c)(c.buf[bi:bi + 1], c.C, c.coff)
-        plan.add(ConvOp([sl(y)], [(0, 0, 0, 0)], None, bp, (1, OH, OW), out0=sl(out),
-                        res1=sl(residual) if residual is not None else None, weight_buf=wbuf, name=name + ".proj"))
+    # the gate is per image -> one projection-weight set per image, all images in ONE SE launch pair + ONE GEMM
+    wbuf = torch.zeros(B, Cout_pad, Kp, dtype=torch.bfloat16, device=dev)
+    plan.add(FnOp(lambda st: L.occd_se_gate_fold_fwd(
+        pool.data_ptr(), 1.0 / (OH * OW), w1.data_ptr(), b1.data_ptr(), w2t.data_ptr(), b2.data_ptr(),
+        hidden.data_ptr(), master.data_ptr(), wbuf.data_ptr(), B, Cm, R, Cout_pad, Kp, st),
+        name + ".se", keep=(pool, w1, b1, w2t, b2, hidden, master, wbuf)))
+    plan.add(ConvOp([y], [(0, 0, 0, 0)], None, bp, (1, OH, OW), out0=out, res1=residual, weight_buf=wbuf,
+                    weight_per_image=True, name=name + ".proj"))
     return out
 
 

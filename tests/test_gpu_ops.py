@@ -61,7 +61,7 @@ def test_se_gate_fold():
     bufs = [d(pool), d(w1), d(b1), d(w2.t()), d(b2), d(master)]
     rc = L.occd_se_gate_fold_fwd(bufs[0].data_ptr(), 1.0 / hw, bufs[1].data_ptr(), bufs[2].data_ptr(),
                                  bufs[3].data_ptr(), bufs[4].data_ptr(), hid.data_ptr(), bufs[5].data_ptr(),
-                                 out.data_ptr(), C, R, rows, Kp, _lib.stream_ptr())
+                                 out.data_ptr(), 1, C, R, rows, Kp, _lib.stream_ptr())
     assert rc == 0
     assert float((out.float().cpu() - want).abs().max()) <= 2 ** -7 * float(want.abs().max())
 
