@@ -56,7 +56,7 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
     const __nv_bfloat16* inb = in + (long long)b * H * W * cs_in + c0;
     const float* wc = w + c0;
     const int ix0 = ox0 * S - pad_left;
-#pragma unroll 1
+#pragma unroll
     for (int ky = 0; ky < K; ++ky) {
       const int iy = oy * S - pad_top + ky;
       if (iy < 0 || iy >= H) continue;
