@@ -240,13 +240,16 @@ def run_b200(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": len(plan.ops) * args.steps,
             "clocks": sampler.summary(),
-            "roofline": {"kernel": "conv_tc_kernel (tcgen05 implicit GEMM, %d launches/step)" % sum(1 for n, t, f in prof if f > 0),
+            "roofline": {"kernel": "conv_tc_kernel + conv_halo_kernel (tcgen05 implicit GEMM family, %d launches/step)" % sum(1 for n, t, f in prof if f > 0),
                          "bound": "tensor", "achieved": ach_t, "peak": tpeak, "unit": "TFLOP/s",
                          "frac": ach_t / tpeak, "traffic": None, "peak_source": src + " bf16_tflops_sustained",
+                         "note": "achieved = sum of algorithmic FLOPs (2*MACs of the reference convs) / sum of the family's "
+                                 "launch durations (CUDA events, back-to-back); per-shape ncu traffic: profiles/r01_ncu_summary.md",
                          "share_of_step": conv_ms / tot_ms if tot_ms else None,
                          "algorithmic_flops_per_step": conv_fl},
             "roofline_lift": {"kernel": "sfa_lift_kernel", "bound": "hbm", "achieved": ach_h, "peak": hpeak,
-                              "unit": "GB/s", "frac": ach_h / hpeak, "traffic": None, "peak_source": src + " hbm_gbs",
+                              "unit": "GB/s", "frac": ach_h / hpeak, "traffic": 76079360,   # ncu r01b_lift: dram read+write
+                              "peak_source": src + " hbm_gbs",
                               "algorithmic_bytes": lift_bytes, "ms": lift_ms,
                               "share_of_step": lift_ms / tot_ms if tot_ms else None},
             "profile_ms": {"convs": conv_ms, "lift": lift_ms, "other": tot_ms - conv_ms - lift_ms, "sum": tot_ms},
