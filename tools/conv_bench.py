@@ -20,6 +20,8 @@ SHAPES = {
     "up16_conv1": ((1, 24, 86), 2784, 1280, (1, 3, 3), 1, "leaky"),
     "head_c32_d2": ((256, 256, 32), 32, 32, (3, 3, 3), 2, "relu"),
     "head_c32_n2": ((256, 256, 32), 32, 2, (3, 3, 3), 1, "none"),
+    "b5_expand": ((1, 24, 43), 384, 2304, (1, 1, 1), 1, "silu"),
+    "b5_proj": ((1, 24, 43), 2304, 384, (1, 1, 1), 1, "none"),
     "x_c32_n32": ((256, 256, 16), 32, 32, (3, 3, 3), 1, "relu"),
     "x_c64_n32": ((256, 256, 16), 64, 32, (3, 3, 3), 1, "relu"),
     "x_c32_n64": ((256, 256, 16), 32, 64, (3, 3, 3), 1, "relu"),
