@@ -27,7 +27,6 @@ constexpr int kIters = 4;  // voxel batches per block
 template <typename T> struct FeatTraits;
 template <> struct FeatTraits<float> {
   static constexpr int VEC = 4;   // elements per 16-byte vector
-  static constexpr int G = 16;    // lanes cooperating on one voxel
   static __device__ __forceinline__ void load(const float* p, float* f) {
     float4 v = __ldg(reinterpret_cast<const float4*>(p));
     f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
@@ -35,7 +34,6 @@ template <> struct FeatTraits<float> {
 };
 template <> struct FeatTraits<__nv_bfloat16> {
   static constexpr int VEC = 8;
-  static constexpr int G = 8;
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* f) {
     uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
     unpack8(v, f);
@@ -66,11 +64,10 @@ __device__ __forceinline__ long long floordiv64(long long a, int d, int shift) {
   return q;
 }
 
-template <typename T, int V, int NV>
+template <typename T, int V, int NV, int G>
 __global__ void __launch_bounds__(kThreads)
 sfa_lift_kernel(const SfaKParams p) {
   constexpr int VEC = FeatTraits<T>::VEC;
-  constexpr int G = FeatTraits<T>::G;
   constexpr int VPB = kThreads / G;   // voxels per batch
   constexpr int CPL = NV * VEC;       // channels per lane
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -238,11 +235,10 @@ sfa_lift_kernel(const SfaKParams p) {
 // Fast path for P == 1 (pattern_id 0, every shipped config): one (x,y,fov) record per (view, voxel).
 // All V x n_scales gathers of a voxel are issued before the first use (memory-level parallelism), index math is
 // 32-bit (h*w < 2^31), the records are read once per view instead of once per scale.
-template <typename T, int V, int NV>
+template <typename T, int V, int NV, int G>
 __global__ void __launch_bounds__(kThreads)
 sfa_lift_p1_kernel(const SfaKParams p) {
   constexpr int VEC = FeatTraits<T>::VEC;
-  constexpr int G = FeatTraits<T>::G;
   constexpr int VPB = kThreads / G;
   constexpr int CPL = NV * VEC;
   constexpr int NS = OCCD_SFA_MAX_SCALES;
@@ -407,49 +403,50 @@ static bool sfa_fits_int32(const SfaKParams& kp, int n_views) {
   return true;
 }
 
-template <typename T, int V>
-int launch_nv(const SfaKParams& kp, int nv, cudaStream_t st) {
-  constexpr int G = FeatTraits<T>::G;
+// G lanes cooperate on one voxel, each holding NV 16-byte vectors of the C channels.  G is the smallest power of
+// two (>= 4) that keeps NV <= 2: fewer lanes per voxel = less redundant index / cosine-scalar work per voxel (the
+// kernel is issue bound), two vectors per lane = two independent 16-byte gathers in flight per lane.
+template <typename T, int V, int NV, int G>
+int launch_g(const SfaKParams& kp, cudaStream_t st) {
   constexpr int VPB = kThreads / G;
   const long long per_block = (long long)VPB * kIters;
   const long long blocks = (kp.N + per_block - 1) / per_block;
-  const size_t smem = (size_t)V * VPB * kIters * kp.P * (sizeof(longlong2) + 1);
-  if (smem > 200 * 1024) {
-    occd_set_last_error("occd_sfa_lift_fwd: pattern count too large for the index staging buffer");
-    return OCCD_ERR_UNSUPPORTED;
-  }
-#define OCCD_SFA_LAUNCH(NV_)                                                                           \
-  if (kp.P == 1 && sfa_fits_int32(kp, V)) {                    \
-    sfa_lift_p1_kernel<T, V, NV_><<<(unsigned)blocks, kThreads, 0, st>>>(kp);                          \
-  } else {                                                                                             \
-    if (smem > 48 * 1024)                                                                              \
-      cudaFuncSetAttribute(sfa_lift_kernel<T, V, NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                           (int)smem);                                                                 \
-    sfa_lift_kernel<T, V, NV_><<<(unsigned)blocks, kThreads, smem, st>>>(kp);                          \
-  }
-  switch (nv) {
-    case 1: OCCD_SFA_LAUNCH(1); break;
-    case 2: OCCD_SFA_LAUNCH(2); break;
-    case 3: OCCD_SFA_LAUNCH(3); break;
-    case 4: OCCD_SFA_LAUNCH(4); break;
-    default:
-      occd_set_last_error("occd_sfa_lift_fwd: C too large (max 256)");
+  if (kp.P == 1 && sfa_fits_int32(kp, V)) {
+    sfa_lift_p1_kernel<T, V, NV, G><<<(unsigned)blocks, kThreads, 0, st>>>(kp);
+  } else {
+    const size_t smem = (size_t)V * VPB * kIters * kp.P * (sizeof(longlong2) + 1);
+    if (smem > 200 * 1024) {
+      occd_set_last_error("occd_sfa_lift_fwd: pattern count too large for the index staging buffer");
       return OCCD_ERR_UNSUPPORTED;
+    }
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(sfa_lift_kernel<T, V, NV, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sfa_lift_kernel<T, V, NV, G><<<(unsigned)blocks, kThreads, smem, st>>>(kp);
   }
-#undef OCCD_SFA_LAUNCH
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
 
+template <typename T, int V>
+int launch_nv(const SfaKParams& kp, cudaStream_t st) {
+  constexpr int VEC = FeatTraits<T>::VEC;
+  const int vecs = (kp.C + VEC - 1) / VEC;           // 16-byte vectors per voxel
+  if (vecs <= 4) return launch_g<T, V, 1, 4>(kp, st);
+  if (vecs <= 8) return launch_g<T, V, 2, 4>(kp, st);
+  if (vecs <= 16) return launch_g<T, V, 2, 8>(kp, st);
+  if (vecs <= 32) return launch_g<T, V, 2, 16>(kp, st);
+  if (vecs <= 64) return launch_g<T, V, 2, 32>(kp, st);
+  occd_set_last_error("occd_sfa_lift_fwd: C too large (max 256 fp32 / 512 bf16 channels)");
+  return OCCD_ERR_UNSUPPORTED;
+}
+
 template <typename T>
 int launch_v(const SfaKParams& kp, int V, cudaStream_t st) {
-  constexpr int per_pass = FeatTraits<T>::G * FeatTraits<T>::VEC;
-  const int nv = (kp.C + per_pass - 1) / per_pass;
   switch (V) {
-    case 1: return launch_nv<T, 1>(kp, nv, st);
-    case 2: return launch_nv<T, 2>(kp, nv, st);
-    case 3: return launch_nv<T, 3>(kp, nv, st);
-    case 4: return launch_nv<T, 4>(kp, nv, st);
+    case 1: return launch_nv<T, 1>(kp, st);
+    case 2: return launch_nv<T, 2>(kp, st);
+    case 3: return launch_nv<T, 3>(kp, st);
+    case 4: return launch_nv<T, 4>(kp, st);
   }
   occd_set_last_error("occd_sfa_lift_fwd: n_views must be 1..4");
   return OCCD_ERR_UNSUPPORTED;
