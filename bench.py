@@ -29,14 +29,14 @@ WORKLOAD = ("configs[1]: 1370x376 stereo, tf_efficientnet_b7_ns, flosp lift to 1
 
 
 def make_cfg():
-    from oracle import synth
+    import synthetic as synth
     return synth.occdepth_cfg(full_scene_size=FULL, project_scale=2, feature=64, feature_2d_oc=64, n_classes=20,
                               backbone_2d_name="tf_efficientnet_b7_ns", cascade_cls=True, context_prior=True)
 
 
 def make_inputs(seed=0):
     import torch
-    from oracle import synth
+    import synthetic as synth
     g = torch.Generator().manual_seed(seed)
     img = torch.randn(1, 2, 3, IMG_H, IMG_W, generator=g)
     pix, fov, _, _ = synth.kitti_indices(IMG_W, IMG_H, FULL, 2, voxel=0.2)
@@ -47,7 +47,7 @@ def build_model():
     import contextlib
     import io
     import torch
-    from oracle import synth
+    import synthetic as synth
     from occdepth_b200.models.OccDepth import OccDepth
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
@@ -90,8 +90,7 @@ class ClockSampler(threading.Thread):
 def cpu_forward_seconds(steps=1, warmup=0, threads=None):
     """the reference algorithm (oracle/functional.py, pinned against /root/reference) on the host cores"""
     import torch
-    from oracle import functional as OF
-    from oracle import synth
+    from oracle import functional as OF      # the ONLY leg of bench.py that executes oracle/ code
     if threads:
         torch.set_num_threads(threads)
     m = build_model()
@@ -214,7 +213,7 @@ def run_b200(args):
         # lift algorithmic bytes (SURVEY 8d formula with the element sizes actually used: bf16 features / output)
         U = 0
         for s in (1, 2, 4, 8):
-            from oracle import synth
+            import synthetic as synth
             h, w = synth.feature_hw(IMG_H, IMG_W, s)
             for v in range(2):
                 idx = (pix[v, :, 0, 1] // s) * w + (pix[v, :, 0, 0] // s)

@@ -7,7 +7,7 @@ Nothing under `occdepth_b200/` may import this package; only `tests/`, `__graft_
                    function on the hot path, each citing the reference file:line it follows
 * `effnet.py`      geffnet-shaped `tf_efficientnet_b*_ns` definition (the reference fetches it with
                    torch.hub at run time; un-vendored, see DESIGN.md "oracle")
-* `synth.py`       seeded synthetic inputs / weights / `vox2pix` restatement
+* `synth.py`       re-export of /synthetic.py: seeded synthetic inputs / weights / `vox2pix` restatement
 * `ref_import.py`  imports the UNMODIFIED reference from /root/reference behind `shims/` (only possible in
                    the build container; used to pin `functional.py` and to generate `tests/golden/*`)
 * `gen_golden.py`  the script that generated `tests/golden/*.pt`

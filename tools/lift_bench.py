@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from oracle import synth  # noqa: E402
+import synthetic as synth  # noqa: E402
 from occdepth_b200.engine import CL  # noqa: E402
 from occdepth_b200.models.SFA import lift_multiscale  # noqa: E402
 
