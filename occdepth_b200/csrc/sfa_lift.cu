@@ -236,7 +236,7 @@ sfa_lift_kernel(const SfaKParams p) {
 // All V x n_scales gathers of a voxel are issued before the first use (memory-level parallelism), index math is
 // 32-bit (h*w < 2^31), the records are read once per view instead of once per scale.
 template <typename T, int V, int NV, int G>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads)   // (kThreads, 4) forces 64 registers + spills: measured slower
 sfa_lift_p1_kernel(const SfaKParams p) {
   constexpr int VEC = FeatTraits<T>::VEC;
   constexpr int VPB = kThreads / G;
