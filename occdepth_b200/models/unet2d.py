@@ -68,43 +68,30 @@ class DecoderBN(B200Module):
         self.use_decoder = use_decoder
         self.backbone_2d_name = backbone_2d_name
         self.return_up_feats = return_up_feats
+        # 1x1 conv WITH padding=1: a (h+2)x(w+2) map whose border is bias only (reference unet2d.py:65-67)
         self.conv2 = nn.Conv2d(bottleneck_features, features, kernel_size=1, stride=1, padding=1)
-        self.out_feature_1_1 = out_feature
-        self.out_feature_1_2 = out_feature
-        self.out_feature_1_4 = out_feature
-        self.out_feature_1_8 = out_feature
-        self.out_feature_1_16 = out_feature
-        self.feature_1_16 = features // 2
-        self.feature_1_8 = features // 4
-        self.feature_1_4 = features // 8
-        self.feature_1_2 = features // 16
-        self.feature_1_1 = features // 32
-        if self.use_decoder:
-            if self.return_up_feats <= 1:
-                self.resize_output_1_1 = nn.Conv2d(self.feature_1_1, self.out_feature_1_1, kernel_size=1)
-            if self.return_up_feats <= 2:
-                self.resize_output_1_2 = nn.Conv2d(self.feature_1_2, self.out_feature_1_2, kernel_size=1)
-            if self.return_up_feats <= 4:
-                self.resize_output_1_4 = nn.Conv2d(self.feature_1_4, self.out_feature_1_4, kernel_size=1)
-            if self.return_up_feats <= 8:
-                self.resize_output_1_8 = nn.Conv2d(self.feature_1_8, self.out_feature_1_8, kernel_size=1)
-            if self.return_up_feats <= 16:
-                self.resize_output_1_16 = nn.Conv2d(self.feature_1_16, self.out_feature_1_16, kernel_size=1)
-            ch = MODEL_CHANNELS[self.backbone_2d_name]
-            if self.return_up_feats <= 16:
-                self.up16 = UpSampleBN(skip_input=features + ch[4], output_features=self.feature_1_16)
-            if self.return_up_feats <= 8:
-                self.up8 = UpSampleBN(skip_input=self.feature_1_16 + ch[3], output_features=self.feature_1_8)
-            if self.return_up_feats <= 4:
-                self.up4 = UpSampleBN(skip_input=self.feature_1_8 + ch[2], output_features=self.feature_1_4)
-            if self.return_up_feats <= 2:
-                self.up2 = UpSampleBN(skip_input=self.feature_1_4 + ch[1], output_features=self.feature_1_2)
-            if self.return_up_feats <= 1:
-                self.up1 = UpSampleBN(skip_input=self.feature_1_2 + ch[0], output_features=self.feature_1_1)
-        else:
+        scales = (1, 2, 4, 8, 16)
+        for s in scales:                                   # decoder widths features/32 .. features/2
+            setattr(self, "out_feature_1_%d" % s, out_feature)
+        for s, div in zip(scales[::-1], (2, 4, 8, 16, 32)):
+            setattr(self, "feature_1_%d" % s, features // div)
+        if not self.use_decoder:
             self.resize_output_1_1 = nn.Conv2d(3, out_feature, kernel_size=1)
             self.resize_output_1_2 = nn.Conv2d(32, out_feature * 2, kernel_size=1)
             self.resize_output_1_4 = nn.Conv2d(48, out_feature * 4, kernel_size=1)
+            return
+        # registration order == the reference's (state_dict order): the five 1x1 heads, then up16 .. up1
+        for s in scales:
+            if self.return_up_feats <= s:
+                setattr(self, "resize_output_1_%d" % s,
+                        nn.Conv2d(getattr(self, "feature_1_%d" % s), out_feature, kernel_size=1))
+        skip_ch = MODEL_CHANNELS[self.backbone_2d_name]     # [image, blocks[0], blocks[1], blocks[2], blocks[4]]
+        below = features                                    # channels coming up from the coarser level
+        for s, skip in zip(scales[::-1], skip_ch[::-1]):
+            width = getattr(self, "feature_1_%d" % s)
+            if self.return_up_feats <= s:
+                setattr(self, "up%d" % s, UpSampleBN(skip_input=below + skip, output_features=width))
+            below = width
 
     def emit(self, plan, features, outs=None):
         """features: {0: image CL, 4,5,6,8,11: encoder CLs}; outs: optional {"1_s": CL} destinations.

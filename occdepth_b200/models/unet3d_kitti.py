@@ -19,33 +19,29 @@ class UNet3D(B200Module):
         self.cascade_cls = cascade_cls
         self.occluded_cls = occluded_cls
         self.infer_mode = infer_mode
-        size_l1 = (int(self.full_scene_size[0] / project_scale), int(self.full_scene_size[1] / project_scale),
-                   int(self.full_scene_size[2] / project_scale))
-        size_l2 = (size_l1[0] // 2, size_l1[1] // 2, size_l1[2] // 2)
-        size_l3 = (size_l2[0] // 2, size_l2[1] // 2, size_l2[2] // 2)
-        dilations = [1, 2, 3]
-        self.process_l1 = nn.Sequential(
-            Process(self.feature, norm_layer, bn_momentum, dilations=[1, 2, 3]),
-            Downsample(self.feature, norm_layer, bn_momentum))
-        self.process_l2 = nn.Sequential(
-            Process(self.feature * 2, norm_layer, bn_momentum, dilations=[1, 2, 3]),
-            Downsample(self.feature * 2, norm_layer, bn_momentum))
-        self.up_13_l2 = Upsample(self.feature * 4, self.feature * 2, norm_layer, bn_momentum)
-        self.up_12_l1 = Upsample(self.feature * 2, self.feature, norm_layer, bn_momentum)
-        if self.project_scale == 1:
-            self.up_l1_lfull = Convblock3d(self.feature, self.feature // 2, norm_layer, bn_momentum, stride=1)
-        else:
-            self.up_l1_lfull = Upsample(self.feature, self.feature // 2, norm_layer, bn_momentum)
-        if self.cascade_cls:
-            self.ssc_head = SegmentationHeadCascadeCLS(self.feature // 2, self.feature // 2, class_num, dilations)
-        else:
-            self.ssc_head = SegmentationHead(self.feature // 2, self.feature // 2, class_num, dilations)
+        f = self.feature
+        size_l3 = tuple(int(s / project_scale) // 4 for s in self.full_scene_size)      # the 1/4 grid of the lift grid
+        heads = {True: SegmentationHeadCascadeCLS, False: SegmentationHead}
+        dil = [1, 2, 3]
+
+        def level(width):
+            return nn.Sequential(Process(width, norm_layer, bn_momentum, dilations=[1, 2, 3]),
+                                 Downsample(width, norm_layer, bn_momentum))
+
+        # encoder: two (Process, Downsample) levels; decoder: transposed convs back up, skip adds in forward
+        self.process_l1 = level(f)
+        self.process_l2 = level(f * 2)
+        self.up_13_l2 = Upsample(f * 4, f * 2, norm_layer, bn_momentum)
+        self.up_12_l1 = Upsample(f * 2, f, norm_layer, bn_momentum)
+        # lift grid == full grid (project_scale 1): stride-1 block; otherwise one more x2 up-sampling to full res
+        self.up_l1_lfull = (Convblock3d(f, f // 2, norm_layer, bn_momentum, stride=1) if self.project_scale == 1
+                            else Upsample(f, f // 2, norm_layer, bn_momentum))
+        self.ssc_head = heads[bool(self.cascade_cls)](f // 2, f // 2, class_num, dil)
         if self.occluded_cls:
-            self.occluded_head = SegmentationHeadOccludedCLS(self.feature // 2, self.feature // 2, class_num,
-                                                             dilations)
+            self.occluded_head = SegmentationHeadOccludedCLS(f // 2, f // 2, class_num, dil)
         self.context_prior = context_prior
         if context_prior:
-            self.CP_mega_voxels = CPMegaVoxels(self.feature * 4, size_l3, bn_momentum=bn_momentum)
+            self.CP_mega_voxels = CPMegaVoxels(f * 4, size_l3, bn_momentum=bn_momentum)
 
     def emit(self, plan, x3d_l1):
         res = {}

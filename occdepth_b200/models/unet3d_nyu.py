@@ -15,31 +15,25 @@ class UNet3D(B200Module):
         self.business_layer = []
         self.project_res = project_res
         self.cascade_cls = cascade_cls
-        self.feature_1_4 = feature
-        self.feature_1_8 = feature * 2
-        self.feature_1_16 = feature * 4
-        self.feature_1_16_dec = self.feature_1_16
-        self.feature_1_8_dec = self.feature_1_8
-        self.feature_1_4_dec = self.feature_1_4
+        f4, f8, f16 = feature, feature * 2, feature * 4
+        self.feature_1_4, self.feature_1_8, self.feature_1_16 = f4, f8, f16
+        self.feature_1_4_dec, self.feature_1_8_dec, self.feature_1_16_dec = f4, f8, f16
         self.infer_mode = infer_mode
-        self.process_1_4 = nn.Sequential(
-            Process(self.feature_1_4, norm_layer, bn_momentum, dilations=[1, 2, 3]),
-            Downsample(self.feature_1_4, norm_layer, bn_momentum))
-        self.process_1_8 = nn.Sequential(
-            Process(self.feature_1_8, norm_layer, bn_momentum, dilations=[1, 2, 3]),
-            Downsample(self.feature_1_8, norm_layer, bn_momentum))
-        self.up_1_16_1_8 = Upsample(self.feature_1_16_dec, self.feature_1_8_dec, norm_layer, bn_momentum)
-        self.up_1_8_1_4 = Upsample(self.feature_1_8_dec, self.feature_1_4_dec, norm_layer, bn_momentum)
-        if self.cascade_cls:
-            self.ssc_head_1_4 = SegmentationHeadCascadeCLS(self.feature_1_4_dec, self.feature_1_4_dec, class_num,
-                                                           [1, 2, 3])
-        else:
-            self.ssc_head_1_4 = SegmentationHead(self.feature_1_4_dec, self.feature_1_4_dec, class_num, [1, 2, 3])
+
+        def level(width):
+            return nn.Sequential(Process(width, norm_layer, bn_momentum, dilations=[1, 2, 3]),
+                                 Downsample(width, norm_layer, bn_momentum))
+
+        self.process_1_4 = level(f4)
+        self.process_1_8 = level(f8)
+        self.up_1_16_1_8 = Upsample(f16, f8, norm_layer, bn_momentum)
+        self.up_1_8_1_4 = Upsample(f8, f4, norm_layer, bn_momentum)
+        head = SegmentationHeadCascadeCLS if self.cascade_cls else SegmentationHead
+        self.ssc_head_1_4 = head(f4, f4, class_num, [1, 2, 3])
         self.context_prior = context_prior
-        size_1_16 = tuple(np.ceil(i / 4).astype(int) for i in full_scene_size)
         if context_prior:
-            self.CP_mega_voxels = CPMegaVoxels(self.feature_1_16, size_1_16, n_relations=n_relations,
-                                               bn_momentum=bn_momentum)
+            size_1_16 = tuple(int(np.ceil(i / 4)) for i in full_scene_size)
+            self.CP_mega_voxels = CPMegaVoxels(f16, size_1_16, n_relations=n_relations, bn_momentum=bn_momentum)
 
     def emit(self, plan, x3d_1_4):
         res = {}
