@@ -138,7 +138,12 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     parallel.init("nccl", dev)
     m = build_model().to(dev)
-    img, pix, fov = make_inputs(seed=rank)
+    slab = args.partition == "slab" and world > 1
+    img, pix, fov = make_inputs(seed=0 if slab else rank)
+    if slab:
+        # BASELINE.json configs[2]: ONE frame, voxel grid split along X over the ranks, NCCL halo exchange at the
+        # 3-D conv boundaries (strong scaling); the default is one independent frame per rank (weak scaling)
+        m.enable_slab_parallel(parallel.SlabContext(halo=3))
     # ---- device-resident arm ----
     batch_dev = {"img": img.to(dev), "projected_pix_2": [pix.to(dev)], "fov_mask_2": [fov.to(dev)]}
     with torch.no_grad():
@@ -186,9 +191,13 @@ def run_b200(args):
     ms_e2e = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
     # keep the GPU under the same load a little longer so that nvidia-smi (100 ms period) sees it, then stop
     with torch.no_grad():
-        t_end = time.time() + 1.0
-        while time.time() < t_end:
-            m(batch_dev)
+        if slab:      # every rank must run the SAME number of forwards (each one is a set of NCCL exchanges)
+            for _ in range(40):
+                m(batch_dev)
+        else:
+            t_end = time.time() + 1.0
+            while time.time() < t_end:
+                m(batch_dev)
         torch.cuda.synchronize()
     sampler.stop_flag = True
 
@@ -196,8 +205,8 @@ def run_b200(args):
     if rank == 0:
         plan = list(m._plans().values())[0][0]
         # per-kernel profile pass (outside the timed regions): shares + roofline of the dominant kernel
-        prof = plan.profile()
-        prof = plan.profile()
+        # (not in slab mode: the plan contains NCCL ops that every rank would have to enter together)
+        prof = [] if slab else (plan.profile(), plan.profile())[1]
         conv_ms = sum(t for n, t, f in prof if f > 0)
         conv_fl = sum(f for n, t, f in prof if f > 0)
         lift_ms = sum(t for n, t, f in prof if n == "sfa_lift")
@@ -222,7 +231,8 @@ def run_b200(args):
         lift_bytes = U * 64 * 2 + 2 * N1 * 17 + N1 * 64 * 2
         ach_t = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         ach_h = lift_bytes / (lift_ms * 1e-3) / 1e9 if lift_ms > 0 else 0.0
-        value = world * N_OUT * args.steps / (ms_total * 1e-3)
+        frames = 1 if slab else world
+        value = frames * N_OUT * args.steps / (ms_total * 1e-3)
         cpu = None
         if world == 1 and not args.no_cpu:
             times, cores = cpu_forward_seconds(1, 0)
@@ -231,17 +241,19 @@ def run_b200(args):
         line = {
             "metric": "forward voxels/sec", "value": value, "unit": "voxels/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": world,
+            "higher_is_better": True, "scaling": "strong" if slab else "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": frames,
+                       "partition": "x-slab of one frame + NCCL halo exchange" if slab else "frame replicas",
                        "l2": "per-step working set (weights + activations, >2 GB) exceeds the 126 MB L2; no flush",
                        "cuda_graph": os.environ.get("OCCDEPTH_CUDA_GRAPH", "1") == "1"},
-            "e2e": {"value": world * N_OUT * args.steps / (ms_e2e * 1e-3), "unit": "voxels/s",
+            "e2e": {"value": frames * N_OUT * args.steps / (ms_e2e * 1e-3), "unit": "voxels/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": len(plan.ops) * args.steps,
             "clocks": sampler.summary(),
             "roofline": {"kernel": "conv_tc_kernel + conv_halo_kernel (tcgen05 implicit GEMM family, %d launches/step)" % sum(1 for n, t, f in prof if f > 0),
                          "bound": "tensor", "achieved": ach_t, "peak": tpeak, "unit": "TFLOP/s",
-                         "frac": ach_t / tpeak, "traffic": None, "peak_source": src + " bf16_tflops_sustained",
+                         "frac": ach_t / tpeak if prof else None, "traffic": None, "peak_source": src + " bf16_tflops_sustained",
                          "note": "achieved = sum of algorithmic FLOPs (2*MACs of the reference convs) / sum of the family's "
                                  "launch durations (CUDA events, back-to-back); per-shape ncu traffic: profiles/r01_ncu_summary.md",
                          "share_of_step": conv_ms / tot_ms if tot_ms else None,
@@ -273,6 +285,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--partition", default="frames", choices=["frames", "slab"],
+                    help="frames: one frame per GPU (default, weak scaling); slab: one frame, X-slab partition")
     ap.add_argument("--dump-profile", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

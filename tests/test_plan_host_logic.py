@@ -1,0 +1,70 @@
+"""Host-side planning logic without a GPU: the SIMT flavour of occd_conv_plan_create needs no CUDA driver, so whole
+launch plans can be BUILT (not run) on CPU tensors.  Checks the tap lists / shapes through the plan's MAC count
+against the reference's published layer arithmetic (3-D UNet + CRP at config 2 = 529.9 GMAC conv
++ 4.3 GMAC bmm) and the automatic halo-exchange insertion of the X-slab partition (24 exchanges, 1/8 of the work)."""
+import contextlib
+import io
+
+import pytest
+import torch
+import torch.nn as nn
+
+
+@pytest.fixture()
+def simt(monkeypatch):
+    monkeypatch.setenv("OCCDEPTH_CONV_IMPL", "simt")
+
+
+def _build(m, shape, slab=None):
+    from occdepth_b200.engine import Plan
+    plan = Plan(torch.device("cpu"), slab=slab)
+    x = plan.alloc(*shape)
+    with torch.no_grad():
+        y = m.emit(plan, x)
+    return plan, y
+
+
+def test_unet3d_config2_plan_macs_and_outputs(simt):
+    from occdepth_b200.models.unet3d_kitti import UNet3D
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = UNet3D(20, nn.BatchNorm3d, (256, 256, 32), 64, 2, context_prior=True, cascade_cls=True).eval()
+    plan, y = _build(m, (1, 128, 128, 16, 64))
+    gmac = plan.flops / 2e9
+    assert abs(gmac - (529.9 + 4.3)) / 534.2 < 0.01, gmac
+    assert tuple(y["ssc_logit"].shape) == (1, 20, 256, 256, 32) and tuple(y["occ_logit"].shape) == (1, 2, 256, 256, 32)
+    assert tuple(y["P_logits"].shape) == (1, 4, 512, 4096)
+    assert y["x3d_l1"].dims == (1, 128, 128, 16) and y["x3d_l3"].dims == (1, 32, 32, 4)
+
+
+def test_unet3d_config2_slab_plan(simt):
+    from occdepth_b200.models.unet3d_kitti import UNet3D
+    from occdepth_b200.parallel import SimSlabGroup
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = UNet3D(20, nn.BatchNorm3d, (256, 256, 32), 64, 2, context_prior=True, cascade_cls=True).eval()
+    full, _ = _build(m, (1, 128, 128, 16, 64))
+    grp = SimSlabGroup(8, halo=3)
+    plans = [_build(m, (1, 16, 128, 16, 64), slab=ctx) for ctx in (grp.ctxs[0], grp.ctxs[3])]
+    for (plan, y), ctx in zip(plans, (grp.ctxs[0], grp.ctxs[3])):
+        assert ctx.n_exchanges == 24 and ctx.n_gathers == 1
+        assert tuple(y["ssc_logit"].shape) == (1, 20, 32, 256, 32)
+        assert tuple(y["P_logits"].shape) == (1, 4, 512, 512)
+        # every conv is split 8 ways; only the tiny transposed mega-context GEMM operand is replicated
+        assert abs(plan.flops * 8 / full.flops - 1.0) < 0.01
+    assert len(plans[0][0].ops) == len(plans[1][0].ops)
+    # a slab thinner than the dilation-3 reach must be refused, not silently wrong
+    grp16 = SimSlabGroup(16, halo=3)
+    with pytest.raises(RuntimeError, match="slab"):
+        _build(m, (1, 8, 128, 16, 64), slab=grp16.ctxs[1])
+
+
+def test_unet2d_b7_plan_macs(simt):
+    """2D UNet per view at 376x1370: 531.7 GMAC (encoder ~54, DecoderBN ~478), SURVEY.md section 0"""
+    from occdepth_b200.models.unet2d import UNet2D
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = UNet2D.build(out_feature=64, use_decoder=True, backbone_2d_name="tf_efficientnet_b7_ns",
+                         return_up_feats=1).eval()
+    plan, y = _build(m, (1, 1, 376, 1370, 3))
+    dw = 2.7       # depthwise MACs are not tensor-core launches (not in plan.flops)
+    gmac = plan.flops / 2e9
+    assert abs(gmac + dw - 531.7) / 531.7 < 0.02, gmac
+    assert y["1_1"].dims == (1, 1, 376, 1370) and y["1_8"].dims == (1, 1, 47, 172) and y["1_16"].dims == (1, 1, 24, 86)
