@@ -936,11 +936,14 @@ extern "C" int occd_conv_plan_info(const occd_conv_plan* pl, int* info) {
 
 template <int KC>
 static int launch_tc(const occd_conv_plan* pl, cudaStream_t st) {
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static bool attr_set[64] = {false};  // per instantiation, per device (the attribute is per device)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
-    attr_set = true;
+    attr_set[dev] = true;
   }
   conv_tc_kernel<KC><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->tc, pl->tmA[0], pl->tmA[1], pl->tmA[2], pl->tmW);
   OCCD_CHECK_LAUNCH();
@@ -949,11 +952,14 @@ static int launch_tc(const occd_conv_plan* pl, cudaStream_t st) {
 
 template <int KC>
 static int launch_halo(const occd_conv_plan* pl, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};  // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
-    attr_set = true;
+    attr_set[dev] = true;
   }
   conv_halo_kernel<KC><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->halo, pl->tmA[0], pl->tmW);
   OCCD_CHECK_LAUNCH();

@@ -68,3 +68,19 @@ def test_unet2d_b7_plan_macs(simt):
     gmac = plan.flops / 2e9
     assert abs(gmac + dw - 531.7) / 531.7 < 0.02, gmac
     assert y["1_1"].dims == (1, 1, 376, 1370) and y["1_8"].dims == (1, 1, 47, 172) and y["1_16"].dims == (1, 1, 24, 86)
+
+
+def test_occdepth_config2_plan(simt, monkeypatch):
+    """the whole forward plan at the benchmark configuration: ~3.2 TFLOP of tensor-core launches (SURVEY.md section 0:
+    2 x 531.7 GMAC 2D + 529.9 + 4.3 GMAC 3D), one fused lift launch, logits in the reference's NCDHW layout"""
+    import bench
+    monkeypatch.setenv("OCCDEPTH_CUDA_GRAPH", "0")
+    m = bench.build_model()
+    N = 128 * 128 * 16
+    plan, img, pix, fov, out, depth0, n_lo = m._build(1, 2, bench.IMG_H, bench.IMG_W, N, 1, torch.device("cpu"), {})
+    gmac = plan.flops / 2e9
+    assert abs(gmac + 2 * 2.7 - (2 * 531.7 + 529.9 + 4.3)) / 1597.6 < 0.02, gmac
+    assert sum(1 for op in plan.ops if getattr(op, "name", "") == "sfa_lift") == 1
+    assert tuple(out["ssc_logit"].shape) == (1, 20, 256, 256, 32)
+    assert img.dims == (2, 1, bench.IMG_H, bench.IMG_W) and tuple(pix.shape) == (1, 2, N, 1, 2)
+    assert len(plan.ops) < 500      # both views batched, SE + projection batched over images
