@@ -180,6 +180,11 @@ int occd_copy_channels(const void* in, void* out, long long positions, int C, in
 int occd_dwconv2d_fwd(const void* in, const float* w, const float* bias, void* out, long long* pool, int B, int H,
                       int W, int OH, int OW, int C, int cs_in, int cs_out, int K, int stride, int pad_top,
                       int pad_left, int act, void* stream);
+/* same contract, shared-memory-tiled variant: one zero-filled input halo tile per CTA staged with    */
+/* cp.async, FMA loop out of shared memory (results equal up to fp32 summation order)                */
+int occd_dwconv2d_tiled_fwd(const void* in, const float* w, const float* bias, void* out, long long* pool, int B,
+                            int H, int W, int OH, int OW, int C, int cs_in, int cs_out, int K, int stride,
+                            int pad_top, int pad_left, int act, void* stream);
 /* gate[b][c] = sigmoid(W2 silu(W1 (pool[b] 2^-24 / HW) + b1) + b2); zeroes pool. w1 [R][C],       */
 /* w2t [R][C]; `gate` must hold B*C + B*R floats (the hidden layer is staged behind the gates)     */
 int occd_se_gate_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,

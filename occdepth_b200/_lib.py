@@ -102,6 +102,7 @@ SYMBOLS = {
     "occd_cl_transpose": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _vp]),
     "occd_copy_channels": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     "occd_dwconv2d_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp] + [_i] * 13 + [_vp]),
+    "occd_dwconv2d_tiled_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp] + [_i] * 13 + [_vp]),
     "occd_se_gate_fwd": (C.c_int, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "occd_se_gate_fold_fwd": (C.c_int, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "occd_scale_weights": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),

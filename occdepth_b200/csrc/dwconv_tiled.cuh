@@ -1,0 +1,306 @@
+// Shared-memory-tiled depthwise KxK conv + folded BN + activation + squeeze (channels-last bf16).
+// Same contract as dwconv_kernel (effnet_ops.cu); replaces geffnet conv_dw + bn + act (+ the SE squeeze) as
+// iterated by Encoder.forward (unet2d.py:188-196).
+//
+// Why a second variant: the direct kernel keeps a (PX-1)*S+K wide input window per filter row in registers and
+// ends up at 229-252 registers/thread for K = 5 (one 8-warp block per SM), so every layer runs latency-bound at
+// 0.6-0.9 TB/s.  Here a CTA stages ONE zero-filled input halo tile (TH x 16 outputs x 8*CVB channels) in shared
+// memory with cp.async -- every input byte crosses L2->SM once, coalesced in 16*CVB-byte runs -- and the FMA loop
+// reads 16-byte vectors from shared memory, so the register budget is the 4x8 accumulators + one filter row.
+//
+// The three phases are written as __host__ __device__ functions of (block index, thread index): the CUDA kernel
+// calls them with __syncthreads() in between, and tests/host_emul/ runs exactly the same index arithmetic
+// thread by thread on the CPU (no GPU needed to check tiling, padding, stride and ragged-edge handling).
+#pragma once
+#include <string.h>
+#include <math.h>
+#include "common.cuh"
+
+namespace dwt {
+
+constexpr int kThreads = 256;
+constexpr int kTW = 16;  // output tile width
+constexpr int kPX = 4;   // consecutive outputs (along W) per thread
+
+#define DWT_HD __host__ __device__ __forceinline__
+
+struct Args {
+  const __nv_bfloat16* in;
+  const float* w;     // [K*K][C] BN-folded filter taps
+  const float* bias;  // [C]
+  __nv_bfloat16* out;
+  long long* pool;    // [B][C] fixed-point (2^-24) squeeze sums, or null
+  int H, W, OH, OW, C, cs_in, cs_out, pad_top, pad_left, act, tiles_x;
+};
+
+template <int K, int S, int CVB, int TH>
+struct Cfg {
+  static constexpr int CT = CVB * 8;              // channels per CTA
+  static constexpr int GX = kTW / kPX;            // thread groups along W
+  static constexpr int GROUPS = kThreads / CVB;   // (row, x-group) slots per pass
+  static constexpr int RPP = GROUPS / GX;         // output rows per pass
+  static constexpr int PASSES = TH / RPP;
+  static_assert(TH % RPP == 0 && PASSES >= 1, "tile height must be a multiple of the rows per pass");
+  static constexpr int ITH = (TH - 1) * S + K, ITW = (kTW - 1) * S + K;  // input halo tile
+  static constexpr int NIN = (kPX - 1) * S + K;   // input vectors one thread reads per filter row
+  static constexpr int TILE_ELEMS = ITH * ITW * CT;  // bf16
+  static constexpr int W_ELEMS = K * K * CT;         // fp32, layout [tap][half][CVB][4]
+  static constexpr int RED_ELEMS = GROUPS * CT;      // fp32
+  static constexpr size_t kTileBytes = (size_t)TILE_ELEMS * 2;
+  static constexpr size_t kSmemBytes = kTileBytes + (size_t)W_ELEMS * 4 + (size_t)RED_ELEMS * 4;
+  static_assert(kTileBytes % 16 == 0, "weights must start 16-byte aligned");
+};
+
+DWT_HD void copy16_async(void* smem_dst, const void* gsrc) {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+#else
+  memcpy(smem_dst, gsrc, 16);
+#endif
+}
+
+DWT_HD void zero16(void* smem_dst) {
+#ifdef __CUDA_ARCH__
+  *reinterpret_cast<uint4*>(smem_dst) = make_uint4(0u, 0u, 0u, 0u);
+#else
+  memset(smem_dst, 0, 16);
+#endif
+}
+
+DWT_HD float bits2f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+
+// 8 bf16 (one 16-byte vector) -> 4 float2; element 2i sits in the low half of word i
+DWT_HD void unpack8f2(const uint4& u, float2* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) f[i] = make_float2(bits2f(w[i] << 16), bits2f(w[i] & 0xffff0000u));
+}
+
+DWT_HD float2 fma2(float2 a, float2 b, float2 c) {
+#ifdef __CUDA_ARCH__
+  return __ffma2_rn(a, b, c);  // one packed FFMA2 issue slot for two IEEE fp32 FMAs (sm_100)
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+
+// activation over one 8-channel vector (device: the same uniform-branch fast-math epilogue as the direct kernel)
+DWT_HD void act8(float* v, int act) {
+#ifdef __CUDA_ARCH__
+  apply_act8(v, act);
+#else
+  for (int i = 0; i < 8; ++i) {
+    switch (act) {
+      case ACT_RELU: v[i] = v[i] > 0.f ? v[i] : 0.f; break;
+      case ACT_LEAKY: v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i]; break;
+      case ACT_SILU: v[i] = v[i] / (1.f + expf(-v[i])); break;
+      case ACT_SIGMOID: v[i] = 1.f / (1.f + expf(-v[i])); break;
+      default: break;
+    }
+  }
+#endif
+}
+
+struct BlockIdx {
+  int x, y, z;
+};
+
+// ---- phase 1: stage the zero-filled input halo tile and this CTA's filter taps in shared memory ----------------
+template <int K, int S, int CVB, int TH>
+DWT_HD void phase_load(const Args& a, BlockIdx blk, int tid, __nv_bfloat16* tile, float* wsm) {
+  using C_ = Cfg<K, S, CVB, TH>;
+  const int b = blk.z, c0 = blk.y * C_::CT;
+  const int gy0 = (blk.x / a.tiles_x) * TH * S - a.pad_top;
+  const int gx0 = (blk.x % a.tiles_x) * kTW * S - a.pad_left;
+  const __nv_bfloat16* inb = a.in + (long long)b * a.H * a.W * a.cs_in;
+  for (int i = tid; i < C_::ITH * C_::ITW * CVB; i += kThreads) {
+    const int cv = i % CVB, pix = i / CVB;
+    const int iy = pix / C_::ITW, ix = pix - iy * C_::ITW;
+    const int gy = gy0 + iy, gx = gx0 + ix, c = c0 + cv * 8;
+    __nv_bfloat16* dst = tile + (long long)pix * C_::CT + cv * 8;
+    if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && c < a.C)
+      copy16_async(dst, inb + ((long long)gy * a.W + gx) * a.cs_in + c);
+    else
+      zero16(dst);
+  }
+  // filter taps: wsm[tap][half][cv][4] so that the 8 lanes of a quarter warp read 128 contiguous bytes
+  for (int i = tid; i < K * K * 2 * CVB; i += kThreads) {
+    const int cv = i % CVB, h = (i / CVB) % 2, tap = i / (2 * CVB);
+    const int c = c0 + cv * 8 + h * 4;
+    float* dst = wsm + ((tap * 2 + h) * CVB + cv) * 4;
+    if (c < a.C)
+      copy16_async(dst, a.w + (long long)tap * a.C + c);
+    else
+      zero16(dst);
+  }
+}
+
+// ---- phase 2: FMA loop out of shared memory, activation, bf16 store, per-thread squeeze partials -> red[] -----
+template <int K, int S, int CVB, int TH>
+DWT_HD void phase_compute(const Args& a, BlockIdx blk, int tid, const __nv_bfloat16* tile, const float* wsm,
+                          float* red) {
+  using C_ = Cfg<K, S, CVB, TH>;
+  const int cv = tid % CVB, g = tid / CVB;
+  const int gxi = g % C_::GX, r0 = g / C_::GX;
+  const int b = blk.z, c = blk.y * C_::CT + cv * 8;
+  const int ty0 = (blk.x / a.tiles_x) * TH, ox0 = (blk.x % a.tiles_x) * kTW + gxi * kPX;
+  const bool cvalid = c < a.C;
+  float2 psum[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) psum[i] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int pass = 0; pass < C_::PASSES; ++pass) {
+    const int orow = r0 + pass * C_::RPP, oy = ty0 + orow;
+    if (!cvalid || oy >= a.OH || ox0 >= a.OW) continue;
+    float2 acc[kPX][4];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(a.bias + c);
+      const float4 b1 = *reinterpret_cast<const float4*>(a.bias + c + 4);
+#pragma unroll
+      for (int p = 0; p < kPX; ++p) {
+        acc[p][0] = make_float2(b0.x, b0.y);
+        acc[p][1] = make_float2(b0.z, b0.w);
+        acc[p][2] = make_float2(b1.x, b1.y);
+        acc[p][3] = make_float2(b1.z, b1.w);
+      }
+    }
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      float2 wv[K][4];
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const float* wp = wsm + (((ky * K + kx) * 2) * CVB + cv) * 4;
+        const float4 w0 = *reinterpret_cast<const float4*>(wp);
+        const float4 w1 = *reinterpret_cast<const float4*>(wp + CVB * 4);
+        wv[kx][0] = make_float2(w0.x, w0.y);
+        wv[kx][1] = make_float2(w0.z, w0.w);
+        wv[kx][2] = make_float2(w1.x, w1.y);
+        wv[kx][3] = make_float2(w1.z, w1.w);
+      }
+      const __nv_bfloat16* rowp = tile + ((long long)(orow * S + ky) * C_::ITW + gxi * kPX * S) * C_::CT + cv * 8;
+#pragma unroll
+      for (int j = 0; j < C_::NIN; ++j) {
+        float2 x[4];
+        unpack8f2(*reinterpret_cast<const uint4*>(rowp + j * C_::CT), x);
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const int d = j - kx;  // input column j feeds output p = d / S through tap kx (compile-time resolved)
+          if (d >= 0 && d % S == 0 && d / S < kPX) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[d / S][i] = fma2(x[i], wv[kx][i], acc[d / S][i]);
+          }
+        }
+      }
+    }
+    __nv_bfloat16* orow_p = a.out + (((long long)b * a.OH + oy) * a.OW + ox0) * a.cs_out + c;
+#pragma unroll
+    for (int p = 0; p < kPX; ++p) {
+      if (ox0 + p >= a.OW) break;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[2 * i] = acc[p][i].x;
+        v[2 * i + 1] = acc[p][i].y;
+      }
+      act8(v, a.act);
+      uint4 packed;
+      uint32_t* pw = reinterpret_cast<uint32_t*>(&packed);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        uint32_t bits;
+        memcpy(&bits, &h2, 4);
+        pw[i] = bits;
+      }
+      *reinterpret_cast<uint4*>(orow_p + (long long)p * a.cs_out) = packed;
+      if (a.pool) {
+        // squeeze what the next layer will actually read (the bf16-rounded activation)
+        float2 r[4];
+        unpack8f2(packed, r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          psum[i].x += r[i].x;
+          psum[i].y += r[i].y;
+        }
+      }
+    }
+  }
+  if (a.pool) {
+    float* rp = red + g * C_::CT + cv * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      rp[2 * i] = psum[i].x;
+      rp[2 * i + 1] = psum[i].y;
+    }
+  }
+}
+
+// ---- phase 3: one thread per channel folds the CTA's partials and adds them to pool[b][c] (integer atomics:
+//      order-independent, so the SE gates are bit-reproducible run to run) ---------------------------------------
+template <int K, int S, int CVB, int TH>
+DWT_HD void phase_pool(const Args& a, BlockIdx blk, int tid, const float* red) {
+  using C_ = Cfg<K, S, CVB, TH>;
+  const int c = blk.y * C_::CT + tid;
+  if (tid >= C_::CT || c >= a.C) return;
+  float s = 0.f;
+  for (int g = 0; g < C_::GROUPS; ++g) s += red[g * C_::CT + tid];
+  long long* dst = a.pool + (long long)blk.z * a.C + c;
+#ifdef __CUDA_ARCH__
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)__float2ll_rn(s * 16777216.f));
+#else
+  *dst += llrintf(s * 16777216.f);
+#endif
+}
+
+#ifdef __CUDACC__
+template <int K, int S, int CVB, int TH>
+__global__ void __launch_bounds__(kThreads, 2) dwconv_tiled_kernel(const Args a) {
+  using C_ = Cfg<K, S, CVB, TH>;
+  extern __shared__ __align__(16) unsigned char dwt_smem[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(dwt_smem);
+  float* wsm = reinterpret_cast<float*>(dwt_smem + C_::kTileBytes);
+  float* red = wsm + C_::W_ELEMS;
+  const BlockIdx blk{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z};
+  const int tid = threadIdx.x;
+  phase_load<K, S, CVB, TH>(a, blk, tid, tile, wsm);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  phase_compute<K, S, CVB, TH>(a, blk, tid, tile, wsm, red);
+  if (a.pool) {
+    __syncthreads();
+    phase_pool<K, S, CVB, TH>(a, blk, tid, red);
+  }
+}
+#endif
+
+// tile-shape choice shared by the launcher and the host emulation: CVB = 4 for layers narrower than 64 channels,
+// tall tiles (TH = 16) when the layer still fills the GPU twice over, TH = 8 otherwise and for stride 2
+struct Choice {
+  int cvb, th;
+};
+static inline Choice choose(int B, int OH, int OW, int C, int S, int n_sms) {
+  Choice ch;
+  ch.cvb = C < 64 ? 4 : 8;
+  if (ch.cvb == 4) {
+    ch.th = 16;
+  } else if (S == 2) {
+    ch.th = 8;
+  } else {
+    const long long tiles16 = (long long)B * ((OH + 15) / 16) * ((OW + kTW - 1) / kTW) * ((C + 63) / 64);
+    ch.th = tiles16 >= 4LL * n_sms ? 16 : 8;
+  }
+  return ch;
+}
+
+}  // namespace dwt

@@ -6,6 +6,7 @@
 // replaces geffnet DepthwiseSeparableConv / InvertedResidual internals (conv_dw, bn, act, se) as iterated by
 // Encoder.forward (unet2d.py:188-196) and F.interpolate in UpSampleBN.forward.
 #include "common.cuh"
+#include "dwconv_tiled.cuh"
 #include "../../include/occdepth_b200.h"
 
 namespace {
@@ -263,6 +264,66 @@ extern "C" int occd_dwconv2d_fwd(const void* in, const float* w, const float* bi
 #undef OCCD_DW
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
+}
+
+
+namespace {
+
+template <int K, int S, int CVB, int TH>
+int launch_dw_tiled(const dwt::Args& a, int B, cudaStream_t st) {
+  using C_ = dwt::Cfg<K, S, CVB, TH>;
+  static bool attr_set[64] = {false};  // per instantiation, per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv_tiled_kernel<K, S, CVB, TH>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::kSmemBytes);
+    if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
+    attr_set[dev] = true;
+  }
+  const int tiles_y = (a.OH + TH - 1) / TH;
+  dim3 grid(a.tiles_x * tiles_y, (a.C + C_::CT - 1) / C_::CT, B);
+  dwt::dwconv_tiled_kernel<K, S, CVB, TH><<<grid, dwt::kThreads, C_::kSmemBytes, st>>>(a);
+  OCCD_CHECK_LAUNCH();
+  return OCCD_OK;
+}
+
+template <int K, int S>
+int launch_dw_tiled_ks(const dwt::Args& a, int B, dwt::Choice ch, cudaStream_t st) {
+  if (ch.cvb == 4) return launch_dw_tiled<K, S, 4, 16>(a, B, st);
+  if (ch.th == 16) return launch_dw_tiled<K, S, 8, 16>(a, B, st);
+  return launch_dw_tiled<K, S, 8, 8>(a, B, st);
+}
+
+}  // namespace
+
+// Shared-memory-tiled variant of occd_dwconv2d_fwd (same arguments, same results up to fp32 summation order).
+extern "C" int occd_dwconv2d_tiled_fwd(const void* in, const float* w, const float* bias, void* out, long long* pool,
+                                       int B, int H, int W, int OH, int OW, int C, int cs_in, int cs_out, int K,
+                                       int stride, int pad_top, int pad_left, int act, void* stream) {
+  OCCD_CHECK_ARG(in && w && bias && out && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "occd_dwconv2d_tiled_fwd: args");
+  OCCD_CHECK_ARG(C > 0 && C % 8 == 0 && cs_in % 8 == 0 && cs_out % 8 == 0 && cs_in >= C && cs_out >= C,
+                 "occd_dwconv2d_tiled_fwd: channels must be a multiple of 8");
+  OCCD_CHECK_ARG(K == 3 || K == 5, "occd_dwconv2d_tiled_fwd: kernel size must be 3 or 5");
+  OCCD_CHECK_ARG(stride == 1 || stride == 2, "occd_dwconv2d_tiled_fwd: stride must be 1 or 2");
+  OCCD_CHECK_ARG(B <= 65535 && (C + 31) / 32 <= 65535, "occd_dwconv2d_tiled_fwd: B/C too large");
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sms <= 0) n_sms = 148;
+  }
+  dwt::Args a;
+  a.in = (const __nv_bfloat16*)in; a.w = w; a.bias = bias; a.out = (__nv_bfloat16*)out; a.pool = pool;
+  a.H = H; a.W = W; a.OH = OH; a.OW = OW; a.C = C; a.cs_in = cs_in; a.cs_out = cs_out;
+  a.pad_top = pad_top; a.pad_left = pad_left; a.act = act; a.tiles_x = (OW + dwt::kTW - 1) / dwt::kTW;
+  const dwt::Choice ch = dwt::choose(B, OH, OW, C, stride, n_sms);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K == 3 && stride == 1) return launch_dw_tiled_ks<3, 1>(a, B, ch, st);
+  if (K == 3) return launch_dw_tiled_ks<3, 2>(a, B, ch, st);
+  if (stride == 1) return launch_dw_tiled_ks<5, 1>(a, B, ch, st);
+  return launch_dw_tiled_ks<5, 2>(a, B, ch, st);
 }
 
 extern "C" int occd_se_gate_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,

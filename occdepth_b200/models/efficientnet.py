@@ -7,6 +7,7 @@ se.conv_expand,conv_pwl,bn3}, conv_head, bn2, classifier`), so reference checkpo
 definition: see `block_specs`.  TF "SAME" padding, Swish, BN eps 1e-3.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -57,6 +58,15 @@ class SqueezeExcite(nn.Module):
         self.conv_expand = nn.Conv2d(reduce_chs, chs, 1, bias=True)
 
 
+def _dw_entry(L):
+    """depthwise entry point: the shared-memory-tiled kernel by default (2-4x the direct one on every B7 layer
+    shape, profiles/r01_dw_check.txt); OCCDEPTH_DW_IMPL=direct selects the register-window variant."""
+    impl = os.environ.get("OCCDEPTH_DW_IMPL", "tiled")
+    if impl not in ("tiled", "direct"):
+        raise ValueError(f"OCCDEPTH_DW_IMPL must be 'tiled' or 'direct', got {impl!r}")
+    return L.occd_dwconv2d_tiled_fwd if impl == "tiled" else L.occd_dwconv2d_fwd
+
+
 def _emit_dw_se_project(plan, x, conv_dw, bn_dw, se, conv_proj, bn_proj, k, stride, residual, out=None, name=""):
     """dw conv + BN + SiLU (+ squeeze) -> SE gate -> gate folded into the 1x1 projection's weights ->
     projection + BN (+ residual).  x: CL [B,1,H,W,C]."""
@@ -71,9 +81,10 @@ def _emit_dw_se_project(plan, x, conv_dw, bn_dw, se, conv_proj, bn_proj, k, stri
     wdw = w.reshape(Cm, k * k).t().contiguous()                # [K*K][C] fp32
     y = plan.alloc(B, 1, OH, OW, Cm)
     pool = torch.zeros(B, Cm, dtype=torch.int64, device=dev)      # squeeze sums, fixed point 2^-24 (deterministic)
-    plan.add(FnOp(lambda st: L.occd_dwconv2d_fwd(x.ptr, wdw.data_ptr(), b.data_ptr(), y.ptr, pool.data_ptr(), B, H,
-                                                 W, OH, OW, Cm, x.cstride, y.cstride, k, stride, pt, pl,
-                                                 _lib.ACT_SILU, st), name + ".dw", keep=(x, wdw, b, y, pool)))
+    dw_fwd = _dw_entry(L)
+    plan.add(FnOp(lambda st: dw_fwd(x.ptr, wdw.data_ptr(), b.data_ptr(), y.ptr, pool.data_ptr(), B, H,
+                                    W, OH, OW, Cm, x.cstride, y.cstride, k, stride, pt, pl,
+                                    _lib.ACT_SILU, st), name + ".dw", keep=(x, wdw, b, y, pool)))
     R = se.conv_reduce.out_channels
     w1 = se.conv_reduce.weight.detach().float().reshape(R, Cm).contiguous()
     b1 = se.conv_reduce.bias.detach().float().contiguous()

@@ -14,9 +14,11 @@ def _bf(t):
     return t.to(torch.bfloat16).float()
 
 
+@pytest.mark.parametrize("variant", ["tiled", "direct"])
 @pytest.mark.parametrize("C,H,W,K,S", [(64, 21, 45, 3, 1), (24 * 8, 20, 33, 3, 2), (40, 17, 29, 5, 1), (288, 9, 14, 5, 2),
-                                        (480, 12, 43, 5, 1)])
-def test_dwconv_silu_and_squeeze(C, H, W, K, S):
+                                        (480, 12, 43, 5, 1), (24, 19, 30, 3, 2), (16, 33, 37, 5, 2),
+                                        (384, 70, 150, 5, 1)])
+def test_dwconv_silu_and_squeeze(C, H, W, K, S, variant):
     """depthwise conv + bias + SiLU (TF-SAME padding) and the squeeze partial sums"""
     from occdepth_b200 import _lib
     L = _lib.lib()
@@ -33,8 +35,9 @@ def test_dwconv_silu_and_squeeze(C, H, W, K, S):
     y = torch.empty(B, OH, OW, C, dtype=torch.bfloat16, device="cuda")
     wk = w.reshape(C, K * K).t().contiguous().cuda()
     pool = torch.zeros(B, C, dtype=torch.int64, device="cuda")
-    rc = L.occd_dwconv2d_fwd(xc.data_ptr(), wk.data_ptr(), b.cuda().data_ptr(), y.data_ptr(), pool.data_ptr(), B, H, W,
-                             OH, OW, C, C, C, K, S, ph // 2, pw // 2, _lib.ACT_SILU, _lib.stream_ptr())
+    fn = L.occd_dwconv2d_tiled_fwd if variant == "tiled" else L.occd_dwconv2d_fwd
+    rc = fn(xc.data_ptr(), wk.data_ptr(), b.cuda().data_ptr(), y.data_ptr(), pool.data_ptr(), B, H, W,
+            OH, OW, C, C, C, K, S, ph // 2, pw // 2, _lib.ACT_SILU, _lib.stream_ptr())
     assert rc == 0
     got = y.float().cpu().permute(0, 3, 1, 2)
     assert float((got - ref).abs().max()) <= 2 ** -7 * float(ref.abs().max())
