@@ -194,6 +194,10 @@ int occd_se_gate_fwd(long long* pool, float inv_hw, const float* w1, const float
 int occd_se_gate_fold_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
                           const float* b2, float* hidden, const float* master, void* wout, int B, int C, int R,
                           int rows, int Kpad, void* stream);
+/* same contract; the fold is decomposed into one CTA per 32-channel strip so each gate is evaluated once */
+int occd_se_gate_fold_strip_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
+                                const float* b2, float* hidden, const float* master, void* wout, int B, int C,
+                                int R, int rows, int Kpad, void* stream);
 /* out[row][k] = bf16(master[row][k] * gate[k]): folds x * gate into the next 1x1 conv's weights   */
 int occd_scale_weights(const float* master, const float* gate, void* out, int rows, int Kpad, int C,
                        void* stream);

@@ -105,6 +105,7 @@ SYMBOLS = {
     "occd_dwconv2d_tiled_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp] + [_i] * 13 + [_vp]),
     "occd_se_gate_fwd": (C.c_int, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "occd_se_gate_fold_fwd": (C.c_int, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "occd_se_gate_fold_strip_fwd": (C.c_int, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "occd_scale_weights": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "occd_frustum_sample_fwd": (C.c_int, [_vp, _vp] + [_i] * 7 + [_f] * 4 + [_i, _vp, _i, _vp]),
     "occd_softmax_planar": (C.c_int, [_vp, _vp, _ll, _i, _ll, _vp]),

@@ -5,8 +5,11 @@
 //   bilinear resize with align_corners=True (UpSampleBN, unet2d.py:39-44)
 // replaces geffnet DepthwiseSeparableConv / InvertedResidual internals (conv_dw, bn, act, se) as iterated by
 // Encoder.forward (unet2d.py:188-196) and F.interpolate in UpSampleBN.forward.
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "dwconv_tiled.cuh"
+#include "se_fold_strip.cuh"
 #include "../../include/occdepth_b200.h"
 
 namespace {
@@ -367,15 +370,21 @@ extern "C" int occd_upsample_bilinear_ac(const void* in, void* out, int B, int h
   return OCCD_OK;
 }
 
-extern "C" int occd_se_gate_fold_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
-                                     const float* b2, float* hidden, const float* master, void* wout, int B, int C,
-                                     int R, int rows, int Kpad, void* stream) {
+static int se_gate_fold_impl(bool strip, long long* pool, float inv_hw, const float* w1, const float* b1,
+                             const float* w2t, const float* b2, float* hidden, const float* master, void* wout, int B,
+                             int C, int R, int rows, int Kpad, void* stream) {
   OCCD_CHECK_ARG(pool && w1 && b1 && w2t && b2 && hidden && master && wout && C > 0 && R > 0 && rows > 0 &&
                  Kpad >= C && R <= 8192, "occd_se_gate_fold_fwd: args");
   cudaStream_t st = (cudaStream_t)stream;
   OCCD_CHECK_ARG(B >= 1 && B <= 65535, "occd_se_gate_fold_fwd: B");
   se_fc1_kernel<<<dim3(R, B), 128, 0, st>>>(pool, inv_hw, w1, b1, hidden, C, R);
   OCCD_CHECK_LAUNCH();
+  if (strip) {
+    sef::Args a{pool, hidden, w2t, b2, master, (__nv_bfloat16*)wout, C, R, rows, Kpad};
+    sef::se_fc2_fold_strip_kernel<<<dim3((Kpad + sef::kStrip - 1) / sef::kStrip, B), sef::kThreads, 0, st>>>(a);
+    OCCD_CHECK_LAUNCH();
+    return OCCD_OK;
+  }
   const int kblocks = (Kpad + 255) / 256;
   int rows_per_block = rows;
   while (rows_per_block > 16 && B * kblocks * ((rows + rows_per_block - 1) / rows_per_block) < 296) rows_per_block /= 2;
@@ -384,4 +393,17 @@ extern "C" int occd_se_gate_fold_fwd(long long* pool, float inv_hw, const float*
                                                            (__nv_bfloat16*)wout, C, R, rows, Kpad, rows_per_block);
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
+}
+
+extern "C" int occd_se_gate_fold_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
+                                     const float* b2, float* hidden, const float* master, void* wout, int B, int C,
+                                     int R, int rows, int Kpad, void* stream) {
+  return se_gate_fold_impl(false, pool, inv_hw, w1, b1, w2t, b2, hidden, master, wout, B, C, R, rows, Kpad, stream);
+}
+
+// same contract; the fold runs as one CTA per 32-channel strip so that every gate value is evaluated once
+extern "C" int occd_se_gate_fold_strip_fwd(long long* pool, float inv_hw, const float* w1, const float* b1,
+                                           const float* w2t, const float* b2, float* hidden, const float* master,
+                                           void* wout, int B, int C, int R, int rows, int Kpad, void* stream) {
+  return se_gate_fold_impl(true, pool, inv_hw, w1, b1, w2t, b2, hidden, master, wout, B, C, R, rows, Kpad, stream);
 }

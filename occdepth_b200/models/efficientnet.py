@@ -67,6 +67,15 @@ def _dw_entry(L):
     return L.occd_dwconv2d_tiled_fwd if impl == "tiled" else L.occd_dwconv2d_fwd
 
 
+def _se_entry(L):
+    """SE MLP + gate fold entry point.  OCCDEPTH_SE_IMPL=strip selects the one-CTA-per-32-channel-strip fold
+    (each gate evaluated once; CPU-emulation tested, not yet timed on a B200), default is the 256-wide fold."""
+    impl = os.environ.get("OCCDEPTH_SE_IMPL", "wide")
+    if impl not in ("wide", "strip"):
+        raise ValueError(f"OCCDEPTH_SE_IMPL must be 'wide' or 'strip', got {impl!r}")
+    return L.occd_se_gate_fold_strip_fwd if impl == "strip" else L.occd_se_gate_fold_fwd
+
+
 def _emit_dw_se_project(plan, x, conv_dw, bn_dw, se, conv_proj, bn_proj, k, stride, residual, out=None, name=""):
     """dw conv + BN + SiLU (+ squeeze) -> SE gate -> gate folded into the 1x1 projection's weights ->
     projection + BN (+ residual).  x: CL [B,1,H,W,C]."""
@@ -100,7 +109,8 @@ def _emit_dw_se_project(plan, x, conv_dw, bn_dw, se, conv_proj, bn_proj, k, stri
     hidden = torch.empty(B, R, dtype=torch.float32, device=dev)
     # the gate is per image -> one projection-weight set per image, all images in ONE SE launch pair + ONE GEMM
     wbuf = torch.zeros(B, Cout_pad, Kp, dtype=torch.bfloat16, device=dev)
-    plan.add(FnOp(lambda st: L.occd_se_gate_fold_fwd(
+    se_fwd = _se_entry(L)
+    plan.add(FnOp(lambda st: se_fwd(
         pool.data_ptr(), 1.0 / (OH * OW), w1.data_ptr(), b1.data_ptr(), w2t.data_ptr(), b2.data_ptr(),
         hidden.data_ptr(), master.data_ptr(), wbuf.data_ptr(), B, Cm, R, Cout_pad, Kp, st),
         name + ".se", keep=(pool, w1, b1, w2t, b2, hidden, master, wbuf)))

@@ -1,5 +1,6 @@
 """Kernel-level parity of the bandwidth kernels (through the C ABI) vs plain PyTorch fp32 on the same inputs."""
 import math
+import os
 
 import pytest
 import torch
@@ -45,9 +46,12 @@ def test_dwconv_silu_and_squeeze(C, H, W, K, S, variant):
     assert float((sums - got.sum((2, 3))).abs().max()) <= 1e-3 * float(got.sum((2, 3)).abs().max())
 
 
-def test_se_gate_fold():
+@pytest.mark.parametrize("variant", ["wide", "strip"])
+def test_se_gate_fold(variant):
     from occdepth_b200 import _lib
     L = _lib.lib()
+    if variant == "strip" and os.environ.get("OCCD_EXPERIMENTAL") != "1":
+        pytest.skip("strip fold: CPU-emulation tested (tests/test_se_fold_host.py); first GPU run is opt-in")
     g = torch.Generator().manual_seed(0)
     C, R, rows = 192, 12, 48
     Kp = 192
@@ -62,9 +66,10 @@ def test_se_gate_fold():
     hid = torch.zeros(R, device="cuda")
     d = lambda t: t.contiguous().cuda()
     bufs = [d(pool), d(w1), d(b1), d(w2.t()), d(b2), d(master)]
-    rc = L.occd_se_gate_fold_fwd(bufs[0].data_ptr(), 1.0 / hw, bufs[1].data_ptr(), bufs[2].data_ptr(),
-                                 bufs[3].data_ptr(), bufs[4].data_ptr(), hid.data_ptr(), bufs[5].data_ptr(),
-                                 out.data_ptr(), 1, C, R, rows, Kp, _lib.stream_ptr())
+    fn = L.occd_se_gate_fold_strip_fwd if variant == "strip" else L.occd_se_gate_fold_fwd
+    rc = fn(bufs[0].data_ptr(), 1.0 / hw, bufs[1].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(),
+            bufs[4].data_ptr(), hid.data_ptr(), bufs[5].data_ptr(), out.data_ptr(), 1, C, R, rows, Kp,
+            _lib.stream_ptr())
     assert rc == 0
     assert float((out.float().cpu() - want).abs().max()) <= 2 ** -7 * float(want.abs().max())
 
