@@ -96,6 +96,9 @@ int occd_cl_to_planar(const void* in, int in_dtype, float* out, long long B, int
 #define OCCD_CONV_IMPL_HALO 2 /* tcgen05, halo tile loaded once + row-shifted smem views per tap:    */
                               /* stride-1 {-d,0,d}-tap convs, Cin <= 64, resident weights; returns  */
                               /* OCCD_ERR_UNSUPPORTED from plan_create when the shape does not fit   */
+#define OCCD_CONV_IMPL_HALOX 3 /* halo tile, the three W taps of each (dz,dy) pair packed into ONE MMA */
+                              /* (N = 3*Cout_pad <= 256, box 32 positions wide, epilogue sums the      */
+                              /* lane-shifted partials); taps in lexicographic (dz,dy,dx) order         */
 #define OCCD_OUT1_NONE 0
 #define OCCD_OUT1_BF16_CL 1    /* pre-activation copy, channels-last bf16                          */
 #define OCCD_OUT1_F32_PLANAR 2 /* pre-activation copy, fp32 [B][C][positions] (reference layout)   */

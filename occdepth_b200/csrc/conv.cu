@@ -268,10 +268,21 @@ struct HaloParams {
   int bo_mode;                // UMMA descriptor base-offset convention for row-shifted swizzled views
   int b_stride, w_bytes;
   int tap_off16[27];          // (R0 + (a*PH + b)*PW + c) * row_bytes / 16: A-descriptor advance per tap
+  int CP;                     // x-packed variant: output channels (padded) per W tap, N_tile == 3 * CP
   long long* trace;
 };
 
-template <int KC>
+//
+// XP ("x-packed") variant: tcgen05.mma at N <= 128 is bound by a ~79-cycle floor per M128xK16 instruction, not by
+// the tensor pipe, so a 32-channel conv leaves 3/4 of the MMA time unused.  With the halo box exactly 32 positions
+// wide (30 outputs + 2 halo columns) one smem row == one TMEM lane == one lane of an epilogue warp, and the three
+// taps along W of one (dz, dy) pair can share ONE instruction: its B operand is the three taps' weights stacked
+// along N (N = 3 * CP; with taps in lexicographic order that is 3 consecutive tap slices of the ordinary weight
+// tensor, no re-layout), its A operand the un-shifted rows.  The accumulator then holds
+//   Q_c[r] = sum_{a,b} W[a][b][c] . in[r + (a*PH + b)*PW]     (c = 0,1,2)
+// and the epilogue forms out[r] = Q_0[r-1] + Q_1[r] + Q_2[r+1] with two warp shuffles per channel: 9 MMA groups
+// instead of 27, every A start address a multiple of 32 rows (whole swizzle atoms).
+template <int KC, bool XP>
 __global__ void __launch_bounds__(kTcThreads)
 conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ CUtensorMap tmA,
                  const __grid_constant__ CUtensorMap tmW) {
@@ -420,10 +431,24 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
                            pw < p.hw + p.BW && od < p.D && oh < p.H && ow < p.W;
         const uint32_t taddr = tmem_base + set * (uint32_t)p.set_stride + (uint32_t)(m * p.N_tile) +
                                ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
-          float v[16];
-          tc::tmem_ld16(taddr + (uint32_t)c0, v);
-          if (valid) conv_epilogue_row<16>(p.epi, b, od, oh, ow, c0, v);
+        if constexpr (XP) {
+          // lane == pw (PW == 32, R0 a multiple of 32): neighbours along W are the neighbouring lanes
+          for (int c0 = 0; c0 < p.CP; c0 += 16) {
+            float lo[16], v[16], hi[16];
+            tc::tmem_ld16(taddr + (uint32_t)c0, lo);
+            tc::tmem_ld16(taddr + (uint32_t)(p.CP + c0), v);
+            tc::tmem_ld16(taddr + (uint32_t)(2 * p.CP + c0), hi);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              v[i] += __shfl_up_sync(0xffffffffu, lo[i], 1) + __shfl_down_sync(0xffffffffu, hi[i], 1);
+            if (valid) conv_epilogue_row<16>(p.epi, b, od, oh, ow, c0, v);
+          }
+        } else {
+          for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
+            float v[16];
+            tc::tmem_ld16(taddr + (uint32_t)c0, v);
+            if (valid) conv_epilogue_row<16>(p.epi, b, od, oh, ow, c0, v);
+          }
         }
       }
       tc::fence_before_sync();
@@ -566,7 +591,8 @@ static int n_sms_cached() {
 }
 
 // Halo-tile plan: stride-1 "same" convolution whose taps are {-d,0,d} offsets, one source, one k-chunk, one N tile.
-static int build_halo_plan(const occd_conv_desc* d, occd_conv_plan* pl) {
+// halo_geometry is pure host arithmetic (tests/host_emul/ runs it without a GPU); halo_encode builds the tensor maps.
+static int halo_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
 #define HALO_REQUIRE(cond, msg) do { if (!(cond)) { occd_set_last_error("occd_conv_plan_create(halo): " msg); return OCCD_ERR_UNSUPPORTED; } } while (0)
   HALO_REQUIRE(d->n_src == 1, "one source only");
   HALO_REQUIRE(d->stride[0] == 1 && d->stride[1] == 1 && d->stride[2] == 1, "stride must be 1");
@@ -589,6 +615,16 @@ static int build_halo_plan(const occd_conv_desc* d, occd_conv_plan* pl) {
     if (d->taps[i].dy) hal[1] = 1;
     if (d->taps[i].dx) hal[2] = 1;
   }
+  if (xp) {
+    // x-packed: the taps must come as lexicographic (dz, dy) groups of three W taps -d, 0, +d
+    HALO_REQUIRE(hal[2] == 1 && d->n_taps % 3 == 0, "x-packed: taps along W required");
+    for (int i = 0; i < d->n_taps; i += 3)
+      HALO_REQUIRE(d->taps[i].dx == -dil && d->taps[i + 1].dx == 0 && d->taps[i + 2].dx == dil &&
+                   d->taps[i].dz == d->taps[i + 1].dz && d->taps[i].dz == d->taps[i + 2].dz &&
+                   d->taps[i].dy == d->taps[i + 1].dy && d->taps[i].dy == d->taps[i + 2].dy,
+                   "x-packed: taps must be ordered (dz, dy) groups of dx = -d, 0, +d");
+    HALO_REQUIRE(3 * d->Cout_pad <= 256, "x-packed: 3 * Cout_pad must fit one MMA (N <= 256)");
+  }
   HaloParams& h = pl->halo;
   fill_epi(d, &h.epi);
   const int C = d->src_C[0];
@@ -599,23 +635,26 @@ static int build_halo_plan(const occd_conv_desc* d, occd_conv_plan* pl) {
   h.d = dil; h.D = d->OD; h.H = d->IH; h.W = d->IW;
   h.src_d0 = d->src_d0;
   h.hd = hal[0]; h.hh = hal[1]; h.hw = hal[2];
-  h.n_taps = d->n_taps;
-  h.N_tile = d->Cout_pad;
+  h.n_taps = xp ? d->n_taps / 3 : d->n_taps;   // MMA groups per M tile
+  h.CP = d->Cout_pad;
+  h.N_tile = xp ? 3 * d->Cout_pad : d->Cout_pad;
   h.b_stride = round_up(h.N_tile * row_bytes, 1024);
   h.w_bytes = h.n_taps * h.b_stride;
   HALO_REQUIRE(h.w_bytes <= 112 * 1024, "weights do not fit in shared memory");
   const int sD = (d->OD + dil - 1) / dil, sH = (d->IH + dil - 1) / dil, sW = (d->IW + dil - 1) / dil;
   const int smem_total = 224 * 1024 - h.w_bytes - 2048;
   // W extent of the box: the whole sub-sampled line when it fits, else equal splits of at most 62
-  const int nW = (sW + 61) / 62;
-  const int BW = (sW + nW - 1) / nW;
+  // x-packed: the box is exactly one warp wide (30 outputs + 2 halo columns)
+  const int nW = xp ? (sW + 29) / 30 : (sW + 61) / 62;
+  const int BW = xp ? 30 : (sW + nW - 1) / nW;
   long long best_cost = -1;
   for (int BD = 1; BD <= (hal[0] ? 4 : 1); ++BD)
     for (int BH = 1; BH <= sH && BH <= 96; ++BH) {
       const int PD = BD + 2 * hal[0], PH = BH + 2 * hal[1], PW = BW + 2 * hal[2];
       if ((PW - 1) * dil + 1 > 256 || (PH - 1) * dil + 1 > 256 || (PD - 1) * dil + 1 > 256) continue;
-      const int R0 = (hal[0] * PH + hal[1]) * PW + hal[2];
-      const int Rend = ((BD - 1 + hal[0]) * PH + (BH - 1 + hal[1])) * PW + (BW - 1 + hal[2]);
+      // x-packed: M tiles cover whole box rows (columns 0..31), so lanes and box columns coincide
+      const int R0 = (hal[0] * PH + hal[1]) * PW + (xp ? 0 : hal[2]);
+      const int Rend = ((BD - 1 + hal[0]) * PH + (BH - 1 + hal[1])) * PW + (xp ? PW - 1 : BW - 1 + hal[2]);
       const int nM = (Rend - R0 + 1 + 127) / 128;
       if (nM * h.N_tile > 256) continue;
       int rows_alloc = PD * PH * PW;
@@ -639,9 +678,14 @@ static int build_halo_plan(const occd_conv_desc* d, occd_conv_plan* pl) {
   h.set_stride = 32;
   while (h.set_stride < h.nM * h.N_tile) h.set_stride *= 2;
   h.tmem_cols = 2 * h.set_stride;
-  for (int i = 0; i < d->n_taps; ++i)
-    h.tap_off16[i] = (h.R0 + ((d->taps[i].dz / dil) * h.PH + d->taps[i].dy / dil) * h.PW + d->taps[i].dx / dil) *
-                     row_bytes / 16;
+  if (xp) {
+    for (int g = 0; g < h.n_taps; ++g)   // the group's A rows are NOT shifted along W: the epilogue shifts instead
+      h.tap_off16[g] = (h.R0 + ((d->taps[3 * g].dz / dil) * h.PH + d->taps[3 * g].dy / dil) * h.PW) * row_bytes / 16;
+  } else {
+    for (int i = 0; i < d->n_taps; ++i)
+      h.tap_off16[i] = (h.R0 + ((d->taps[i].dz / dil) * h.PH + d->taps[i].dy / dil) * h.PW + d->taps[i].dx / dil) *
+                       row_bytes / 16;
+  }
   { const char* e = getenv("OCCD_HALO_BO"); h.bo_mode = e ? atoi(e) : 0; }  // measured on B200: absolute address bits
   { const char* e = getenv("OCCD_CONV_TRACE_PTR"); h.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
   pl->smem = (size_t)h.w_bytes + (size_t)h.stages * h.a_stage_bytes + 128 + 1024;
@@ -649,7 +693,13 @@ static int build_halo_plan(const occd_conv_desc* d, occd_conv_plan* pl) {
   HALO_REQUIRE(num_tiles < 2147483647LL, "too many tiles");
   const int n_sms = n_sms_cached();
   pl->grid = dim3((unsigned)(num_tiles < n_sms ? num_tiles : n_sms));
+#undef HALO_REQUIRE
+  return OCCD_OK;
+}
 
+static int halo_encode(const occd_conv_desc* d, occd_conv_plan* pl) {
+  const HaloParams& h = pl->halo;
+  const int KC = pl->kc, C = d->src_C[0], dil = h.d;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     occd_set_last_error("occd_conv_plan_create: cuTensorMapEncodeTiled unavailable (no CUDA driver / GPU?)");
@@ -680,8 +730,12 @@ static int build_halo_plan(const occd_conv_desc* d, occd_conv_plan* pl) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { occd_set_last_error("occd_conv_plan_create(halo): cuTensorMapEncodeTiled(weights) failed"); return OCCD_ERR_CUDA; }
   }
-#undef HALO_REQUIRE
   return OCCD_OK;
+}
+
+static int build_halo_plan(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
+  const int rc = halo_geometry(d, pl, xp);
+  return rc != OCCD_OK ? rc : halo_encode(d, pl);
 }
 
 extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** out) {
@@ -725,9 +779,10 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
     OCCD_CHECK_ARG(abs(d->taps[i].dz) < 30000 && abs(d->taps[i].dy) < 30000 && abs(d->taps[i].dx) < 30000,
                    "occd_conv_plan_create: tap offset");
   }
-  OCCD_CHECK_ARG(d->impl == OCCD_CONV_IMPL_TC || d->impl == OCCD_CONV_IMPL_SIMT || d->impl == OCCD_CONV_IMPL_HALO,
-                 "occd_conv_plan_create: impl");
-  OCCD_CHECK_ARG(!d->weight_per_image || d->impl != OCCD_CONV_IMPL_HALO, "occd_conv_plan_create: per-image weights: TC or SIMT impl");
+  OCCD_CHECK_ARG(d->impl == OCCD_CONV_IMPL_TC || d->impl == OCCD_CONV_IMPL_SIMT || d->impl == OCCD_CONV_IMPL_HALO ||
+                 d->impl == OCCD_CONV_IMPL_HALOX, "occd_conv_plan_create: impl");
+  OCCD_CHECK_ARG(!d->weight_per_image || (d->impl != OCCD_CONV_IMPL_HALO && d->impl != OCCD_CONV_IMPL_HALOX),
+                 "occd_conv_plan_create: per-image weights: TC or SIMT impl");
 
   occd_conv_plan* pl = new (std::nothrow) occd_conv_plan;
   OCCD_CHECK_ARG(pl != nullptr, "occd_conv_plan_create: out of memory");
@@ -757,8 +812,8 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
     return OCCD_OK;
   }
 
-  if (d->impl == OCCD_CONV_IMPL_HALO) {
-    const int rc = build_halo_plan(d, pl);
+  if (d->impl == OCCD_CONV_IMPL_HALO || d->impl == OCCD_CONV_IMPL_HALOX) {
+    const int rc = build_halo_plan(d, pl, d->impl == OCCD_CONV_IMPL_HALOX);
     if (rc != OCCD_OK) { delete pl; return rc; }
     *out = pl;
     return OCCD_OK;
@@ -922,7 +977,7 @@ extern "C" int occd_conv_plan_info(const occd_conv_plan* pl, int* info) {
     info[6] = (int)pl->grid.x;
     return OCCD_OK;
   }
-  if (pl->impl == OCCD_CONV_IMPL_HALO) {
+  if (pl->impl == OCCD_CONV_IMPL_HALO || pl->impl == OCCD_CONV_IMPL_HALOX) {
     const HaloParams& h = pl->halo;
     info[0] = h.BD; info[1] = h.BH; info[2] = h.BW; info[3] = h.N_tile; info[4] = pl->kc;
     info[5] = h.stages * 100 + h.nM; info[6] = (int)pl->grid.x;
@@ -950,18 +1005,18 @@ static int launch_tc(const occd_conv_plan* pl, cudaStream_t st) {
   return OCCD_OK;
 }
 
-template <int KC>
+template <int KC, bool XP>
 static int launch_halo(const occd_conv_plan* pl, cudaStream_t st) {
   static bool attr_set[64] = {false};  // per device
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KC, XP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
     attr_set[dev] = true;
   }
-  conv_halo_kernel<KC><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->halo, pl->tmA[0], pl->tmW);
+  conv_halo_kernel<KC, XP><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->halo, pl->tmA[0], pl->tmW);
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
@@ -976,9 +1031,16 @@ extern "C" int occd_conv_run(const occd_conv_plan* pl, void* stream) {
   }
   if (pl->impl == OCCD_CONV_IMPL_HALO) {
     switch (pl->kc) {
-      case 64: return launch_halo<64>(pl, st);
-      case 32: return launch_halo<32>(pl, st);
-      case 16: return launch_halo<16>(pl, st);
+      case 64: return launch_halo<64, false>(pl, st);
+      case 32: return launch_halo<32, false>(pl, st);
+      case 16: return launch_halo<16, false>(pl, st);
+    }
+  }
+  if (pl->impl == OCCD_CONV_IMPL_HALOX) {
+    switch (pl->kc) {
+      case 64: return launch_halo<64, true>(pl, st);
+      case 32: return launch_halo<32, true>(pl, st);
+      case 16: return launch_halo<16, true>(pl, st);
     }
   }
   switch (pl->kc) {

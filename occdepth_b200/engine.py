@@ -24,9 +24,28 @@ def default_impl():
     """'auto' (default): halo-tile tcgen05 kernel where the shape qualifies, else the per-tap tcgen05 kernel;
     'tc' / 'halo' / 'simt' force one implementation (simt = CUDA-core cross-check)."""
     v = os.environ.get("OCCDEPTH_CONV_IMPL", "auto").lower()
-    if v not in ("auto", "tc", "simt", "halo"):
-        raise ValueError("OCCDEPTH_CONV_IMPL must be 'auto', 'tc', 'halo' or 'simt'")
-    return {"auto": None, "tc": _lib.CONV_IMPL_TC, "simt": _lib.CONV_IMPL_SIMT, "halo": _lib.CONV_IMPL_HALO}[v]
+    if v not in ("auto", "tc", "simt", "halo", "halox"):
+        raise ValueError("OCCDEPTH_CONV_IMPL must be 'auto', 'tc', 'halo', 'halox' or 'simt'")
+    return {"auto": None, "tc": _lib.CONV_IMPL_TC, "simt": _lib.CONV_IMPL_SIMT, "halo": _lib.CONV_IMPL_HALO,
+            "halox": _lib.CONV_IMPL_HALOX}[v]
+
+
+def prefer_halox():
+    """OCCDEPTH_HALOX=1: in 'auto' mode try the x-packed halo kernel (three W taps per MMA) first where the tap
+    list qualifies.  Off by default: its plan geometry and lane-shift epilogue are checked on the CPU model
+    (tests/test_halo_model_host.py); the kernel itself has not run on a B200 yet."""
+    return os.environ.get("OCCDEPTH_HALOX", "0") == "1"
+
+
+def halox_eligible(taps, Cout_pad):
+    """(dz, dy) groups of three W taps -d, 0, +d in lexicographic order (what conv_taps emits), N = 3*Cout_pad <= 256"""
+    if len(taps) % 3 or 3 * Cout_pad > 256:
+        return False
+    for i in range(0, len(taps), 3):
+        a, b, c = taps[i], taps[i + 1], taps[i + 2]
+        if not (a[:3] == b[:3] == c[:3] and b[3] == 0 and c[3] > 0 and a[3] == -c[3]):
+            return False
+    return True
 
 
 def halo_eligible(srcs, taps, stride, omul, out_dims, Cout_pad, weight_buf):
@@ -186,6 +205,8 @@ class ConvOp:
         if auto:
             impl = (_lib.CONV_IMPL_HALO if halo_eligible(srcs, taps, stride, omul, out_dims, Cout_pad, weight_buf)
                     else _lib.CONV_IMPL_TC)
+            if impl == _lib.CONV_IMPL_HALO and prefer_halox() and halox_eligible(taps, Cout_pad):
+                impl = _lib.CONV_IMPL_HALOX
         d.impl = impl
         d.n_src = len(srcs)
         for i, s in enumerate(srcs):
@@ -228,6 +249,9 @@ class ConvOp:
         self.flops = 2 * B * OD * OH * OW * Cout * sum(srcs[t[0]].C for t in taps)
         h = C.c_void_p()
         rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
+        if rc != 0 and auto and d.impl == _lib.CONV_IMPL_HALOX:
+            d.impl = _lib.CONV_IMPL_HALO    # x-packed geometry did not fit: 27-tap halo kernel
+            rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
         if rc != 0 and auto and d.impl == _lib.CONV_IMPL_HALO:
             d.impl = _lib.CONV_IMPL_TC      # shape did not fit the halo scheme: per-tap tcgen05 kernel
             rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
