@@ -7,6 +7,7 @@
 #include "conv_common.cuh"
 #include "conv_tc.cuh"
 #include <new>
+#include <utility>
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
@@ -29,6 +30,7 @@ struct TcParams {
   int stages, group;
   int a_bytes, b_stride, b_bytes;
   int tmem_cols;
+  int pdl;           // launched with programmatic stream serialization: wait for the producer grid after the prologue
   long long* trace;  // optional [tile][8] clock64 stamps of CTA 0 (tools/conv_trace.py)
   signed char tap_src[OCCD_CONV_MAX_TAPS];
   short tap_dz[OCCD_CONV_MAX_TAPS], tap_dy[OCCD_CONV_MAX_TAPS], tap_dx[OCCD_CONV_MAX_TAPS];
@@ -88,6 +90,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   tc::fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (p.pdl) {
+    // programmatic dependent launch: everything above (barrier init, TMEM alloc, tensor-map prefetch) overlapped
+    // the tail of the producer grid; its results are only touched below this point
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
   const uint32_t acc_stride = (uint32_t)p.tmem_cols >> 1;  // column offset of the second accumulator
 
   if (warp == 0) {
@@ -269,6 +277,7 @@ struct HaloParams {
   int b_stride, w_bytes;
   int tap_off16[27];          // (R0 + (a*PH + b)*PW + c) * row_bytes / 16: A-descriptor advance per tap
   int CP;                     // x-packed variant: output channels (padded) per W tap, N_tile == 3 * CP
+  int pdl;                    // see TcParams::pdl
   long long* trace;
 };
 
@@ -328,6 +337,12 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
   tc::fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (p.pdl) {
+    // programmatic dependent launch: everything above (barrier init, TMEM alloc, tensor-map prefetch) overlapped
+    // the tail of the producer grid; its results are only touched below this point
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
 
   // tile -> (batch, residue class, sub-grid tile origin)
   auto decode = [&](int tile, int& b, int& ra, int& rb, int& rc, int& td, int& th, int& tw) {
@@ -577,6 +592,33 @@ static int fill_epi(const occd_conv_desc* d, ConvEpi* e) {
 }
 
 
+// OCCD_PDL=1: conv launches carry cudaLaunchAttributeProgrammaticStreamSerialization and the kernels wait on
+// griddepcontrol after their prologue (off by default: not yet timed on a B200)
+static int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OCCD_PDL");
+    v = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  return v;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 static int n_sms_cached() {
   static int n_sms = 0;
   if (n_sms == 0) {
@@ -688,6 +730,7 @@ static int halo_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
   }
   { const char* e = getenv("OCCD_HALO_BO"); h.bo_mode = e ? atoi(e) : 0; }  // measured on B200: absolute address bits
   { const char* e = getenv("OCCD_CONV_TRACE_PTR"); h.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
+  h.pdl = pdl_enabled();
   pl->smem = (size_t)h.w_bytes + (size_t)h.stages * h.a_stage_bytes + 128 + 1024;
   const long long num_tiles = (long long)d->B * dil * dil * dil * h.tilesD * h.tilesH * h.tilesW;
   HALO_REQUIRE(num_tiles < 2147483647LL, "too many tiles");
@@ -880,6 +923,7 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
   while (t.tmem_cols < t.N_tile) t.tmem_cols *= 2;
   { const char* e = getenv("OCCD_CONV_TRACE_PTR"); t.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
   t.tmem_cols *= 2;  // two accumulators: the epilogue of tile j overlaps the MMAs of tile j+1
+  t.pdl = pdl_enabled();
   t.a_bytes = 128 * KC * 2;
   t.b_bytes = t.N_tile * KC * 2;
   t.b_stride = round_up(t.b_bytes, 1024);
@@ -1000,6 +1044,12 @@ static int launch_tc(const occd_conv_plan* pl, cudaStream_t st) {
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
     attr_set[dev] = true;
   }
+  if (pl->tc.pdl) {
+    cudaError_t e = launch_pdl(conv_tc_kernel<KC>, pl->grid, kTcThreads, pl->smem, st, pl->tc, pl->tmA[0], pl->tmA[1],
+                               pl->tmA[2], pl->tmW);
+    if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
+    return OCCD_OK;
+  }
   conv_tc_kernel<KC><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->tc, pl->tmA[0], pl->tmA[1], pl->tmA[2], pl->tmW);
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
@@ -1015,6 +1065,12 @@ static int launch_halo(const occd_conv_plan* pl, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KC, XP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
     attr_set[dev] = true;
+  }
+  if (pl->halo.pdl) {
+    cudaError_t e = launch_pdl(conv_halo_kernel<KC, XP>, pl->grid, kTcThreads, pl->smem, st, pl->halo, pl->tmA[0],
+                               pl->tmW);
+    if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
+    return OCCD_OK;
   }
   conv_halo_kernel<KC, XP><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->halo, pl->tmA[0], pl->tmW);
   OCCD_CHECK_LAUNCH();
