@@ -25,6 +25,7 @@ struct TcParams {
   int src_d0;
   int w_batch_rows;  // weight rows per image (0: shared weights)
   int TD, TH, TW;
+  int TWv;           // output columns per tile row: TW, or 30 for the x-packed variant (one halo column each side)
   int stride[3];
   int Cout_pad, N_tile;
   int stages, group;
@@ -36,7 +37,10 @@ struct TcParams {
   short tap_dz[OCCD_CONV_MAX_TAPS], tap_dy[OCCD_CONV_MAX_TAPS], tap_dx[OCCD_CONV_MAX_TAPS];
 };
 
-template <int KC>
+// XP: x-packed variant (scheme described at conv_halo_kernel): the pipeline items are (source, dz, dy) groups
+// whose B operand stacks the three W taps (N_tile = 3 * Cout_pad), tiles are 32 wide with one halo column on each
+// side, and the epilogue adds the lane-shifted partial sums.
+template <int KC, bool XP>
 __global__ void __launch_bounds__(kTcThreads)
 conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -62,7 +66,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tiles_n = p.Cout_pad / p.N_tile;
+  const int n_tiles_n = XP ? 1 : p.Cout_pad / p.N_tile;
   const int num_tiles = p.num_m_tiles * n_tiles_n;
 
   int iters_per_tile = 0;
@@ -111,7 +115,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         const int th = t % p.tiles_h; t /= p.tiles_h;
         const int td = t % p.tiles_d; t /= p.tiles_d;
         const int b = t;
-        const int iw0 = tw * p.TW * p.stride[2], ih0 = th * p.TH * p.stride[1],
+        const int iw0 = XP ? tw * 30 - 1 : tw * p.TW * p.stride[2], ih0 = th * p.TH * p.stride[1],
                   id0 = td * p.TD * p.stride[0] + p.src_d0;
         const int n0 = nt * p.N_tile;
         // items (tap, k-chunk) are loaded in groups of p.group per pipeline stage: one barrier hand-off per group
@@ -122,7 +126,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         for (int tp = 0; tp < p.n_taps; ++tp) {
           const int src = p.tap_src[tp];
           const int cw = iw0 + p.tap_dx[tp], ch = ih0 + p.tap_dy[tp], cd = id0 + p.tap_dz[tp];
-          const int wrow = b * p.w_batch_rows + tp * p.Cout_pad + n0;
+          const int wrow = b * p.w_batch_rows + (XP ? tp * p.N_tile : tp * p.Cout_pad + n0);
           const int nk = p.n_kchunks[src];
           for (int kc = 0; kc < nk; ++kc) {
             if (g == 0) {
@@ -200,8 +204,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       const int th = t % p.tiles_h; t /= p.tiles_h;
       const int td = t % p.tiles_d; t /= p.tiles_d;
       const int b = t;
-      const int od = td * p.TD + rd, oh = th * p.TH + rh, ow = tw * p.TW + rw;
-      const bool valid = od < p.epi.OD && oh < p.epi.OH && ow < p.epi.OW;
+      const int od = td * p.TD + rd, oh = th * p.TH + rh, ow = XP ? tw * 30 + rw - 1 : tw * p.TW + rw;
+      const bool valid = od < p.epi.OD && oh < p.epi.OH && ow < p.epi.OW && (!XP || (rw >= 1 && rw <= 30));
       const int n0 = nt * p.N_tile;
       const uint32_t acc = (uint32_t)grp;
       if (tracer && j < 64) p.trace[j * 8 + 4] = clock64();
@@ -209,6 +213,24 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       tc::fence_after_sync();
       if (tracer && j < 64) p.trace[j * 8 + 5] = clock64();
       const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
+      if constexpr (XP) {
+        // TW == 32: lane == tile column, so the W neighbours are the neighbouring lanes; the two column halves of
+        // the epilogue groups split the Cout_pad output channels, each needing its three tap slices
+        const int CP = p.Cout_pad;
+        const int xch = CP >> 4;
+        const int xb = half == 0 ? 0 : ((xch + 1) >> 1) * 16;
+        const int xe = half == 0 ? ((xch + 1) >> 1) * 16 : CP;
+        for (int c0 = xb; c0 < xe; c0 += 16) {
+          float lo[16], v[16], hi[16];
+          tc::tmem_ld16(taddr + (uint32_t)c0, lo);
+          tc::tmem_ld16(taddr + (uint32_t)(CP + c0), v);
+          tc::tmem_ld16(taddr + (uint32_t)(2 * CP + c0), hi);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            v[i] += __shfl_up_sync(0xffffffffu, lo[i], 1) + __shfl_down_sync(0xffffffffu, hi[i], 1);
+          if (valid) conv_epilogue_row<16>(p.epi, b, od, oh, ow, c0, v);
+        }
+      } else {
       // software-pipelined: the tcgen05.ld of the next 16 columns is in flight while these 16 are stored
       if (c_begin < c_end) {
         uint32_t ra[16], rb[16];
@@ -235,6 +257,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
             if (c0 + 32 < c_end) tc::tmem_ld_wait16(ra);
           }
         }
+      }
       }
       tc::fence_before_sync();
       tc::mbar_arrive(tmem_empty_bar + 8u * acc);  // this thread's TMEM reads of the buffer are done
@@ -781,6 +804,185 @@ static int build_halo_plan(const occd_conv_desc* d, occd_conv_plan* pl, bool xp)
   return rc != OCCD_OK ? rc : halo_encode(d, pl);
 }
 
+// Per-tap (TC) plan: host arithmetic only (tests/host_emul/ runs it without a GPU); tc_encode builds the tensor maps.
+static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
+  int maxC = 0;
+  for (int s = 0; s < d->n_src; ++s) maxC = d->src_C[s] > maxC ? d->src_C[s] : maxC;
+  TcParams& t = pl->tc;
+  fill_epi(d, &t.epi);
+  const int KC = maxC > 32 ? 64 : (maxC > 16 ? 32 : 16);
+  pl->kc = KC;
+  if (d->Kpad % KC != 0) {
+    occd_set_last_error("occd_conv_plan_create: Kpad must be a multiple of the K chunk (64/32/16)");
+    return OCCD_ERR_ARG;
+  }
+  t.n_taps = xp ? d->n_taps / 3 : d->n_taps;  // x-packed: one pipeline item per (source, dz, dy) group
+  t.src_d0 = d->src_d0;
+  t.w_batch_rows = d->weight_per_image ? d->n_taps * d->Cout_pad : 0;
+  for (int s = 0; s < OCCD_CONV_MAX_SRC; ++s) t.n_kchunks[s] = s < d->n_src ? (d->src_C[s] + KC - 1) / KC : 0;
+  for (int i = 0; i < 3; ++i) t.stride[i] = d->stride[i];
+  if (xp) {
+    // x-packed (see conv_halo_kernel): groups of three W taps -1, 0, +1 share one MMA with N = 3 * Cout_pad; the
+    // tile is 32 positions wide (30 outputs + one halo column each side) so that lane == column in the epilogue
+    if (d->n_taps % 3 || d->stride[2] != 1 || 3 * d->Cout_pad > 256) {
+      occd_set_last_error("occd_conv_plan_create(tcx): needs W-tap triples, W stride 1 and 3 * Cout_pad <= 256");
+      return OCCD_ERR_UNSUPPORTED;
+    }
+    for (int i = 0; i < d->n_taps; i += 3) {
+      const occd_conv_tap &a = d->taps[i], &b = d->taps[i + 1], &c = d->taps[i + 2];
+      if (!(a.dx == -1 && b.dx == 0 && c.dx == 1 && a.src == b.src && a.src == c.src && a.dz == b.dz &&
+            a.dz == c.dz && a.dy == b.dy && a.dy == c.dy)) {
+        occd_set_last_error("occd_conv_plan_create(tcx): taps must be ordered (src, dz, dy) groups of dx = -1, 0, +1");
+        return OCCD_ERR_UNSUPPORTED;
+      }
+      t.tap_src[i / 3] = (signed char)b.src;
+      t.tap_dz[i / 3] = (short)b.dz; t.tap_dy[i / 3] = (short)b.dy; t.tap_dx[i / 3] = 0;
+    }
+    t.TW = 32;
+    long long best = -1;
+    for (int th = 4; th >= 1; th >>= 1) {
+      const int tdd = 4 / th;
+      const long long vol = (long long)round_up(d->OH, th) * round_up(d->OD, tdd);
+      if (best < 0 || vol < best) { best = vol; t.TH = th; t.TD = tdd; }
+    }
+  } else {
+  for (int i = 0; i < d->n_taps; ++i) {
+    t.tap_src[i] = (signed char)d->taps[i].src;
+    t.tap_dz[i] = (short)d->taps[i].dz; t.tap_dy[i] = (short)d->taps[i].dy; t.tap_dx[i] = (short)d->taps[i].dx;
+  }
+  // tile box (TD,TH,TW), product 128, minimal padded volume; ties -> widest TW
+  {
+    // minimal padded volume, but a wide innermost extent (long contiguous TMA runs, coalesced stores) wins
+    // whenever it costs < 4% extra positions
+    long long best = -1;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int tw = 128; tw >= 1; tw >>= 1)
+        for (int th = 128 / tw; th >= 1; th >>= 1) {
+          const int tdd = 128 / (tw * th);
+          if (tw * d->stride[2] > 256 || th * d->stride[1] > 256 || tdd * d->stride[0] > 256) continue;
+          const long long vol = (long long)round_up(d->OW, tw) * round_up(d->OH, th) * round_up(d->OD, tdd);
+          if (pass == 0) {
+            if (best < 0 || vol < best) best = vol;
+          } else if (vol * 100 <= best * 104) {
+            t.TW = tw; t.TH = th; t.TD = tdd;
+            pass = 2; tw = 0; break;  // first hit in (widest TW, tallest TH) order
+          }
+        }
+  }
+  }
+  t.TWv = xp ? 30 : t.TW;
+  t.tiles_w = (d->OW + t.TWv - 1) / t.TWv; t.tiles_h = (d->OH + t.TH - 1) / t.TH; t.tiles_d = (d->OD + t.TD - 1) / t.TD;
+  // N tile: largest divisor of Cout_pad that is a multiple of 16 and <= 256
+  t.Cout_pad = d->Cout_pad;
+  t.N_tile = 16;
+  for (int n = 16; n <= 256 && n <= d->Cout_pad; n += 16)
+    if (d->Cout_pad % n == 0) t.N_tile = n;
+  {
+    // small-M layers (late encoder stages): a narrower N tile that still keeps >= 64 columns trades some A
+    // re-reads for enough tiles to occupy every SM
+    const long long m_tiles0 = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w;
+    const int n_sms = n_sms_cached();
+    int best = t.N_tile;
+    for (int n = t.N_tile; n >= 64; n -= 16) {
+      if (d->Cout_pad % n) continue;
+      best = n;
+      if (m_tiles0 * (d->Cout_pad / n) >= n_sms) break;
+    }
+    if (m_tiles0 * (d->Cout_pad / t.N_tile) < n_sms) t.N_tile = best;
+  }
+  if (xp) t.N_tile = 3 * d->Cout_pad;  // one N tile: the three taps' weights stacked
+  t.tmem_cols = 32;
+  while (t.tmem_cols < t.N_tile) t.tmem_cols *= 2;
+  { const char* e = getenv("OCCD_CONV_TRACE_PTR"); t.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
+  t.tmem_cols *= 2;  // two accumulators: the epilogue of tile j overlaps the MMAs of tile j+1
+  t.pdl = pdl_enabled();
+  t.a_bytes = 128 * KC * 2;
+  t.b_bytes = t.N_tile * KC * 2;
+  t.b_stride = round_up(t.b_bytes, 1024);
+  const int stage_bytes = t.a_bytes + t.b_stride;
+  int total_iters = 0;
+  for (int i = 0; i < t.n_taps; ++i) total_iters += t.n_kchunks[t.tap_src[i]];
+  const int budget = 200 * 1024;  // persistent kernel: one CTA per SM owns the shared memory
+  // (tap, k-chunk) items per pipeline stage: the single-thread producer/MMA hand-off costs ~0.25 us, so a stage
+  // must carry >= ~512 tensor-pipe cycles of work (or up to 9 items) while leaving >= 3 stages in flight
+  const int mma_cycles_per_item = (KC / 16) * (128 * t.N_tile / 256);
+  int group = (512 + mma_cycles_per_item - 1) / mma_cycles_per_item;
+  if (group > 9) group = 9;
+  if (group > total_iters) group = total_iters;
+  while (group > 1 && 3 * group * stage_bytes > budget) --group;
+  t.group = group;
+  int stages = budget / (group * stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  const int groups_per_tile = (total_iters + group - 1) / group;
+  if (stages > 2 * groups_per_tile) stages = 2 * groups_per_tile;
+  if (stages < 1) stages = 1;
+  t.stages = stages;
+  pl->smem = (size_t)stages * group * stage_bytes + 16 * kMaxStages + 64 + 1024;  // + barriers + alignment slack
+  const long long m_tiles = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w;
+  const long long all_tiles = m_tiles * (xp ? 1 : d->Cout_pad / t.N_tile);
+  if (all_tiles > 2147483647LL) {
+    occd_set_last_error("occd_conv_plan_create: too many tiles");
+    return OCCD_ERR_UNSUPPORTED;
+  }
+  t.num_m_tiles = (int)m_tiles;
+  {
+    const int n_sms = n_sms_cached();
+    pl->grid = dim3((unsigned)(all_tiles < n_sms ? all_tiles : n_sms));
+  }
+
+  return OCCD_OK;
+}
+
+static int tc_encode(const occd_conv_desc* d, occd_conv_plan* pl) {
+  const TcParams& t = pl->tc;
+  const int KC = pl->kc;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    occd_set_last_error("occd_conv_plan_create: cuTensorMapEncodeTiled unavailable (no CUDA driver / GPU?)");
+    return OCCD_ERR_CUDA;
+  }
+  const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                         : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  for (int s = 0; s < d->n_src; ++s) {
+    const cuuint64_t cs = (cuuint64_t)d->src_cstride[s] * 2;
+    cuuint64_t gdim[5] = {(cuuint64_t)d->src_C[s], (cuuint64_t)d->IW, (cuuint64_t)d->IH, (cuuint64_t)d->ID,
+                          (cuuint64_t)d->B};
+    cuuint64_t gstr[4] = {cs, cs * d->IW, cs * d->IW * d->IH, cs * d->IW * d->IH * d->ID};
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)(t.TW * d->stride[2]), (cuuint32_t)(t.TH * d->stride[1]),
+                         (cuuint32_t)(t.TD * d->stride[0]), 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)d->stride[2], (cuuint32_t)d->stride[1], (cuuint32_t)d->stride[0], 1};
+    void* base = (void*)((const char*)d->src[s] + (size_t)d->src_coff[s] * 2);
+    CUresult r = enc(&pl->tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      char msg[160];
+      snprintf(msg, sizeof(msg), "occd_conv_plan_create: cuTensorMapEncodeTiled(source %d) failed with %d", s, (int)r);
+        occd_set_last_error(msg);
+      return OCCD_ERR_CUDA;
+    }
+  }
+  for (int s = d->n_src; s < OCCD_CONV_MAX_SRC; ++s) pl->tmA[s] = pl->tmA[0];
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)d->Kpad,
+                          (cuuint64_t)d->n_taps * d->Cout_pad * (d->weight_per_image ? d->B : 1)};
+    cuuint64_t gstr[1] = {(cuuint64_t)d->Kpad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)t.N_tile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&pl->tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d->weight, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      char msg[160];
+      snprintf(msg, sizeof(msg), "occd_conv_plan_create: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+        occd_set_last_error(msg);
+      return OCCD_ERR_CUDA;
+    }
+  }
+  return OCCD_OK;
+}
+
+
 extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** out) {
   OCCD_CHECK_ARG(d && out, "occd_conv_plan_create: null argument");
   OCCD_CHECK_ARG(d->n_src >= 1 && d->n_src <= OCCD_CONV_MAX_SRC, "occd_conv_plan_create: n_src");
@@ -823,7 +1025,7 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
                    "occd_conv_plan_create: tap offset");
   }
   OCCD_CHECK_ARG(d->impl == OCCD_CONV_IMPL_TC || d->impl == OCCD_CONV_IMPL_SIMT || d->impl == OCCD_CONV_IMPL_HALO ||
-                 d->impl == OCCD_CONV_IMPL_HALOX, "occd_conv_plan_create: impl");
+                 d->impl == OCCD_CONV_IMPL_HALOX || d->impl == OCCD_CONV_IMPL_TCX, "occd_conv_plan_create: impl");
   OCCD_CHECK_ARG(!d->weight_per_image || (d->impl != OCCD_CONV_IMPL_HALO && d->impl != OCCD_CONV_IMPL_HALOX),
                  "occd_conv_plan_create: per-image weights: TC or SIMT impl");
 
@@ -862,148 +1064,11 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
     return OCCD_OK;
   }
 
-  // ---------------- TC plan ----------------
-  TcParams& t = pl->tc;
-  fill_epi(d, &t.epi);
-  const int KC = maxC > 32 ? 64 : (maxC > 16 ? 32 : 16);
-  pl->kc = KC;
-  if (d->Kpad % KC != 0) {
-    delete pl;
-    occd_set_last_error("occd_conv_plan_create: Kpad must be a multiple of the K chunk (64/32/16)");
-    return OCCD_ERR_ARG;
-  }
-  t.n_taps = d->n_taps;
-  t.src_d0 = d->src_d0;
-  t.w_batch_rows = d->weight_per_image ? d->n_taps * d->Cout_pad : 0;
-  for (int s = 0; s < OCCD_CONV_MAX_SRC; ++s) t.n_kchunks[s] = s < d->n_src ? (d->src_C[s] + KC - 1) / KC : 0;
-  for (int i = 0; i < 3; ++i) t.stride[i] = d->stride[i];
-  for (int i = 0; i < d->n_taps; ++i) {
-    t.tap_src[i] = (signed char)d->taps[i].src;
-    t.tap_dz[i] = (short)d->taps[i].dz; t.tap_dy[i] = (short)d->taps[i].dy; t.tap_dx[i] = (short)d->taps[i].dx;
-  }
-  // tile box (TD,TH,TW), product 128, minimal padded volume; ties -> widest TW
+  // ---------------- TC plan (per-tap kernel; TCX: three W taps per MMA) ----------------
   {
-    // minimal padded volume, but a wide innermost extent (long contiguous TMA runs, coalesced stores) wins
-    // whenever it costs < 4% extra positions
-    long long best = -1;
-    for (int pass = 0; pass < 2; ++pass)
-      for (int tw = 128; tw >= 1; tw >>= 1)
-        for (int th = 128 / tw; th >= 1; th >>= 1) {
-          const int tdd = 128 / (tw * th);
-          if (tw * d->stride[2] > 256 || th * d->stride[1] > 256 || tdd * d->stride[0] > 256) continue;
-          const long long vol = (long long)round_up(d->OW, tw) * round_up(d->OH, th) * round_up(d->OD, tdd);
-          if (pass == 0) {
-            if (best < 0 || vol < best) best = vol;
-          } else if (vol * 100 <= best * 104) {
-            t.TW = tw; t.TH = th; t.TD = tdd;
-            pass = 2; tw = 0; break;  // first hit in (widest TW, tallest TH) order
-          }
-        }
-  }
-  t.tiles_w = (d->OW + t.TW - 1) / t.TW; t.tiles_h = (d->OH + t.TH - 1) / t.TH; t.tiles_d = (d->OD + t.TD - 1) / t.TD;
-  // N tile: largest divisor of Cout_pad that is a multiple of 16 and <= 256
-  t.Cout_pad = d->Cout_pad;
-  t.N_tile = 16;
-  for (int n = 16; n <= 256 && n <= d->Cout_pad; n += 16)
-    if (d->Cout_pad % n == 0) t.N_tile = n;
-  {
-    // small-M layers (late encoder stages): a narrower N tile that still keeps >= 64 columns trades some A
-    // re-reads for enough tiles to occupy every SM
-    const long long m_tiles0 = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w;
-    const int n_sms = n_sms_cached();
-    int best = t.N_tile;
-    for (int n = t.N_tile; n >= 64; n -= 16) {
-      if (d->Cout_pad % n) continue;
-      best = n;
-      if (m_tiles0 * (d->Cout_pad / n) >= n_sms) break;
-    }
-    if (m_tiles0 * (d->Cout_pad / t.N_tile) < n_sms) t.N_tile = best;
-  }
-  t.tmem_cols = 32;
-  while (t.tmem_cols < t.N_tile) t.tmem_cols *= 2;
-  { const char* e = getenv("OCCD_CONV_TRACE_PTR"); t.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
-  t.tmem_cols *= 2;  // two accumulators: the epilogue of tile j overlaps the MMAs of tile j+1
-  t.pdl = pdl_enabled();
-  t.a_bytes = 128 * KC * 2;
-  t.b_bytes = t.N_tile * KC * 2;
-  t.b_stride = round_up(t.b_bytes, 1024);
-  const int stage_bytes = t.a_bytes + t.b_stride;
-  int total_iters = 0;
-  for (int i = 0; i < d->n_taps; ++i) total_iters += t.n_kchunks[d->taps[i].src];
-  const int budget = 200 * 1024;  // persistent kernel: one CTA per SM owns the shared memory
-  // (tap, k-chunk) items per pipeline stage: the single-thread producer/MMA hand-off costs ~0.25 us, so a stage
-  // must carry >= ~512 tensor-pipe cycles of work (or up to 9 items) while leaving >= 3 stages in flight
-  const int mma_cycles_per_item = (KC / 16) * (128 * t.N_tile / 256);
-  int group = (512 + mma_cycles_per_item - 1) / mma_cycles_per_item;
-  if (group > 9) group = 9;
-  if (group > total_iters) group = total_iters;
-  while (group > 1 && 3 * group * stage_bytes > budget) --group;
-  t.group = group;
-  int stages = budget / (group * stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  const int groups_per_tile = (total_iters + group - 1) / group;
-  if (stages > 2 * groups_per_tile) stages = 2 * groups_per_tile;
-  if (stages < 1) stages = 1;
-  t.stages = stages;
-  pl->smem = (size_t)stages * group * stage_bytes + 16 * kMaxStages + 64 + 1024;  // + barriers + alignment slack
-  const long long m_tiles = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w;
-  const long long all_tiles = m_tiles * (d->Cout_pad / t.N_tile);
-  if (all_tiles > 2147483647LL) {
-    delete pl;
-    occd_set_last_error("occd_conv_plan_create: too many tiles");
-    return OCCD_ERR_UNSUPPORTED;
-  }
-  t.num_m_tiles = (int)m_tiles;
-  {
-    const int n_sms = n_sms_cached();
-    pl->grid = dim3((unsigned)(all_tiles < n_sms ? all_tiles : n_sms));
-  }
-
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) {
-    delete pl;
-    occd_set_last_error("occd_conv_plan_create: cuTensorMapEncodeTiled unavailable (no CUDA driver / GPU?)");
-    return OCCD_ERR_CUDA;
-  }
-  const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                         : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  for (int s = 0; s < d->n_src; ++s) {
-    const cuuint64_t cs = (cuuint64_t)d->src_cstride[s] * 2;
-    cuuint64_t gdim[5] = {(cuuint64_t)d->src_C[s], (cuuint64_t)d->IW, (cuuint64_t)d->IH, (cuuint64_t)d->ID,
-                          (cuuint64_t)d->B};
-    cuuint64_t gstr[4] = {cs, cs * d->IW, cs * d->IW * d->IH, cs * d->IW * d->IH * d->ID};
-    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)(t.TW * d->stride[2]), (cuuint32_t)(t.TH * d->stride[1]),
-                         (cuuint32_t)(t.TD * d->stride[0]), 1};
-    cuuint32_t estr[5] = {1, (cuuint32_t)d->stride[2], (cuuint32_t)d->stride[1], (cuuint32_t)d->stride[0], 1};
-    void* base = (void*)((const char*)d->src[s] + (size_t)d->src_coff[s] * 2);
-    CUresult r = enc(&pl->tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      char msg[160];
-      snprintf(msg, sizeof(msg), "occd_conv_plan_create: cuTensorMapEncodeTiled(source %d) failed with %d", s, (int)r);
-      delete pl;
-      occd_set_last_error(msg);
-      return OCCD_ERR_CUDA;
-    }
-  }
-  for (int s = d->n_src; s < OCCD_CONV_MAX_SRC; ++s) pl->tmA[s] = pl->tmA[0];
-  {
-    cuuint64_t gdim[2] = {(cuuint64_t)d->Kpad,
-                          (cuuint64_t)d->n_taps * d->Cout_pad * (d->weight_per_image ? d->B : 1)};
-    cuuint64_t gstr[1] = {(cuuint64_t)d->Kpad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)t.N_tile};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&pl->tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d->weight, gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      char msg[160];
-      snprintf(msg, sizeof(msg), "occd_conv_plan_create: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
-      delete pl;
-      occd_set_last_error(msg);
-      return OCCD_ERR_CUDA;
-    }
+    int rc = tc_geometry(d, pl, d->impl == OCCD_CONV_IMPL_TCX);
+    if (rc == OCCD_OK) rc = tc_encode(d, pl);
+    if (rc != OCCD_OK) { delete pl; return rc; }
   }
   *out = pl;
   return OCCD_OK;
@@ -1033,24 +1098,24 @@ extern "C" int occd_conv_plan_info(const occd_conv_plan* pl, int* info) {
   return OCCD_OK;
 }
 
-template <int KC>
+template <int KC, bool XP>
 static int launch_tc(const occd_conv_plan* pl, cudaStream_t st) {
   static bool attr_set[64] = {false};  // per instantiation, per device (the attribute is per device)
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, XP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
     attr_set[dev] = true;
   }
   if (pl->tc.pdl) {
-    cudaError_t e = launch_pdl(conv_tc_kernel<KC>, pl->grid, kTcThreads, pl->smem, st, pl->tc, pl->tmA[0], pl->tmA[1],
+    cudaError_t e = launch_pdl(conv_tc_kernel<KC, XP>, pl->grid, kTcThreads, pl->smem, st, pl->tc, pl->tmA[0], pl->tmA[1],
                                pl->tmA[2], pl->tmW);
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
     return OCCD_OK;
   }
-  conv_tc_kernel<KC><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->tc, pl->tmA[0], pl->tmA[1], pl->tmA[2], pl->tmW);
+  conv_tc_kernel<KC, XP><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->tc, pl->tmA[0], pl->tmA[1], pl->tmA[2], pl->tmW);
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
@@ -1099,10 +1164,17 @@ extern "C" int occd_conv_run(const occd_conv_plan* pl, void* stream) {
       case 16: return launch_halo<16, true>(pl, st);
     }
   }
+  if (pl->impl == OCCD_CONV_IMPL_TCX) {
+    switch (pl->kc) {
+      case 64: return launch_tc<64, true>(pl, st);
+      case 32: return launch_tc<32, true>(pl, st);
+      case 16: return launch_tc<16, true>(pl, st);
+    }
+  }
   switch (pl->kc) {
-    case 64: return launch_tc<64>(pl, st);
-    case 32: return launch_tc<32>(pl, st);
-    case 16: return launch_tc<16>(pl, st);
+    case 64: return launch_tc<64, false>(pl, st);
+    case 32: return launch_tc<32, false>(pl, st);
+    case 16: return launch_tc<16, false>(pl, st);
   }
   occd_set_last_error("occd_conv_run: bad plan");
   return OCCD_ERR_ARG;

@@ -24,10 +24,10 @@ def default_impl():
     """'auto' (default): halo-tile tcgen05 kernel where the shape qualifies, else the per-tap tcgen05 kernel;
     'tc' / 'halo' / 'simt' force one implementation (simt = CUDA-core cross-check)."""
     v = os.environ.get("OCCDEPTH_CONV_IMPL", "auto").lower()
-    if v not in ("auto", "tc", "simt", "halo", "halox"):
-        raise ValueError("OCCDEPTH_CONV_IMPL must be 'auto', 'tc', 'halo', 'halox' or 'simt'")
+    if v not in ("auto", "tc", "simt", "halo", "halox", "tcx"):
+        raise ValueError("OCCDEPTH_CONV_IMPL must be 'auto', 'tc', 'tcx', 'halo', 'halox' or 'simt'")
     return {"auto": None, "tc": _lib.CONV_IMPL_TC, "simt": _lib.CONV_IMPL_SIMT, "halo": _lib.CONV_IMPL_HALO,
-            "halox": _lib.CONV_IMPL_HALOX}[v]
+            "halox": _lib.CONV_IMPL_HALOX, "tcx": _lib.CONV_IMPL_TCX}[v]
 
 
 def prefer_halox():
@@ -35,6 +35,22 @@ def prefer_halox():
     list qualifies.  Off by default: its plan geometry and lane-shift epilogue are checked on the CPU model
     (tests/test_halo_model_host.py); the kernel itself has not run on a B200 yet."""
     return os.environ.get("OCCDEPTH_HALOX", "0") == "1"
+
+
+def prefer_tcx():
+    """OCCDEPTH_TCX=1: in 'auto' mode use the x-packed per-tap kernel where the tap list qualifies (W taps -1,0,+1,
+    W stride 1, 3*Cout_pad <= 256).  Off by default, same status as OCCDEPTH_HALOX (tests/test_tc_model_host.py)."""
+    return os.environ.get("OCCDEPTH_TCX", "0") == "1"
+
+
+def tcx_eligible(taps, stride, Cout_pad):
+    if len(taps) % 3 or 3 * Cout_pad > 256 or stride[2] != 1:
+        return False
+    for i in range(0, len(taps), 3):
+        a, b, c = taps[i], taps[i + 1], taps[i + 2]
+        if not (a[:3] == b[:3] == c[:3] and (a[3], b[3], c[3]) == (-1, 0, 1)):
+            return False
+    return True
 
 
 def halox_eligible(taps, Cout_pad):
@@ -207,6 +223,8 @@ class ConvOp:
                     else _lib.CONV_IMPL_TC)
             if impl == _lib.CONV_IMPL_HALO and prefer_halox() and halox_eligible(taps, Cout_pad):
                 impl = _lib.CONV_IMPL_HALOX
+            if impl == _lib.CONV_IMPL_TC and prefer_tcx() and tcx_eligible(taps, stride, Cout_pad):
+                impl = _lib.CONV_IMPL_TCX
         d.impl = impl
         d.n_src = len(srcs)
         for i, s in enumerate(srcs):
@@ -249,6 +267,9 @@ class ConvOp:
         self.flops = 2 * B * OD * OH * OW * Cout * sum(srcs[t[0]].C for t in taps)
         h = C.c_void_p()
         rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
+        if rc != 0 and auto and d.impl == _lib.CONV_IMPL_TCX:
+            d.impl = _lib.CONV_IMPL_TC
+            rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
         if rc != 0 and auto and d.impl == _lib.CONV_IMPL_HALOX:
             d.impl = _lib.CONV_IMPL_HALO    # x-packed geometry did not fit: 27-tap halo kernel
             rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))

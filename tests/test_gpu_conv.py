@@ -69,3 +69,24 @@ def test_conv_halo_xpacked(case):
             pytest.skip(str(err))
         raise
     assert e <= TOL, (e, info)
+
+
+TCX_CASES = {
+    "x_2d_multi": dict(k=(1, 3, 3), Cin=40, Cout=48, dims=(1, 13, 70), B=2),
+    "x_3d_c16": dict(Cin=16, Cout=16, dims=(5, 7, 33)),
+    "x_1d_w_c64": dict(k=(1, 1, 3), Cin=64, Cout=80, dims=(3, 4, 61), act="leaky"),
+    "x_stride_hd": dict(Cin=24, Cout=32, dims=(6, 9, 31), stride=(2, 2, 1), res=False),
+    "x_big_2d": dict(k=(1, 3, 3), Cin=80, Cout=80, dims=(1, 90, 200), res=True),
+}
+
+
+@pytest.mark.parametrize("case", sorted(TCX_CASES))
+def test_conv_tc_xpacked(case):
+    """x-packed per-tap kernel (TCX); opt-in until it has been seen green on a B200 (CPU model:
+    tests/test_tc_model_host.py)"""
+    import os
+    from occdepth_b200 import _lib
+    if os.environ.get("OCCD_EXPERIMENTAL") != "1":
+        pytest.skip("x-packed per-tap kernel: set OCCD_EXPERIMENTAL=1 to run")
+    e, info = G.conv_case(_lib.CONV_IMPL_TCX, **TCX_CASES[case])
+    assert e <= TOL, (e, info)
