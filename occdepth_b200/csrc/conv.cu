@@ -915,6 +915,14 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
   if (stages > kMaxStages) stages = kMaxStages;
   const int groups_per_tile = (total_iters + group - 1) / group;
   if (stages > 2 * groups_per_tile) stages = 2 * groups_per_tile;
+  {
+    // experiment hook: OCCD_TC_STAGES_MIN=n keeps at least n stages (when they fit) so that the producer of a
+    // one-item-per-tile conv (1x1 layers) can run more than two tiles ahead
+    static const int min_stages = [] { const char* e = getenv("OCCD_TC_STAGES_MIN"); return e ? atoi(e) : 0; }();
+    const int fit = budget / (group * stage_bytes);
+    if (min_stages > stages) stages = min_stages < fit ? min_stages : fit;
+    if (stages > kMaxStages) stages = kMaxStages;
+  }
   if (stages < 1) stages = 1;
   t.stages = stages;
   pl->smem = (size_t)stages * group * stage_bytes + 16 * kMaxStages + 64 + 1024;  // + barriers + alignment slack

@@ -18,6 +18,8 @@ SWITCHES = {
     "tcx": {"OCCDEPTH_TCX": "1"},            # x-packed per-tap kernel (Cout <= 80 convs with W taps)
     "pdl": {"OCCD_PDL": "1"},                # programmatic dependent launch for the conv kernels
     "sestrip": {"OCCDEPTH_SE_IMPL": "strip"},  # SE gate fold, one CTA per 32-channel strip
+    "stages4": {"OCCD_TC_STAGES_MIN": "4"},   # >= 4 pipeline stages for one-item-per-tile convs (1x1 layers)
+    "stages8": {"OCCD_TC_STAGES_MIN": "8"},
     "dwdirect": {"OCCDEPTH_DW_IMPL": "direct"},  # the old register-window depthwise kernel (for reference)
 }
 
