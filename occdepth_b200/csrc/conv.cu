@@ -40,7 +40,7 @@ struct TcParams {
 // XP: x-packed variant (scheme described at conv_halo_kernel): the pipeline items are (source, dz, dy) groups
 // whose B operand stacks the three W taps (N_tile = 3 * Cout_pad), tiles are 32 wide with one halo column on each
 // side, and the epilogue adds the lane-shifted partial sums.
-template <int KC, bool XP>
+template <int KC, bool XP, bool WIDE>
 __global__ void __launch_bounds__(kTcThreads)
 conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -243,7 +243,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]);
-            conv_epilogue_row<16>(p.epi, b, od, oh, ow, n0 + c0, v);
+            conv_epilogue_row<16, WIDE>(p.epi, b, od, oh, ow, n0 + c0, v);
           }
           if (has_b) {
             tc::tmem_ld_wait16(rb);
@@ -252,7 +252,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
               float v[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]);
-              conv_epilogue_row<16>(p.epi, b, od, oh, ow, n0 + c0 + 16, v);
+              conv_epilogue_row<16, WIDE>(p.epi, b, od, oh, ow, n0 + c0 + 16, v);
             }
             if (c0 + 32 < c_end) tc::tmem_ld_wait16(ra);
           }
@@ -611,6 +611,17 @@ static int fill_epi(const occd_conv_desc* d, ConvEpi* e) {
   e->res2_cstride = d->res2_cstride; e->res2_coff = d->res2_coff; e->res2_post = d->res2_post;
   e->out1_mode = d->out1_mode; e->out1 = d->out1;
   e->out1_cstride = d->out1_cstride; e->out1_coff = d->out1_coff; e->out1_C = d->out1_C;
+  {
+    // experiment hook OCCD_EPI_WIDE=1: 256-bit epilogue loads/stores where every channels-last window involved is
+    // 32-byte aligned (buffers come from the caching allocator: 512-byte aligned bases)
+    static const int want = [] { const char* v = getenv("OCCD_EPI_WIDE"); return (v && atoi(v) == 1) ? 1 : 0; }();
+    auto ok = [](const void* p, int cstride, int coff) {
+      return !p || (cstride % 16 == 0 && coff % 16 == 0 && (reinterpret_cast<uintptr_t>(p) & 31u) == 0);
+    };
+    e->wide = want && ok(d->out0, d->out0_cstride, d->out0_coff) && ok(d->res1, d->res1_cstride, d->res1_coff) &&
+              ok(d->res2, d->res2_cstride, d->res2_coff) &&
+              (d->out1_mode != OCCD_OUT1_BF16_CL || ok(d->out1, d->out1_cstride, d->out1_coff));
+  }
   return 0;
 }
 
@@ -1106,24 +1117,24 @@ extern "C" int occd_conv_plan_info(const occd_conv_plan* pl, int* info) {
   return OCCD_OK;
 }
 
-template <int KC, bool XP>
+template <int KC, bool XP, bool WIDE>
 static int launch_tc(const occd_conv_plan* pl, cudaStream_t st) {
   static bool attr_set[64] = {false};  // per instantiation, per device (the attribute is per device)
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, XP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, XP, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
     attr_set[dev] = true;
   }
   if (pl->tc.pdl) {
-    cudaError_t e = launch_pdl(conv_tc_kernel<KC, XP>, pl->grid, kTcThreads, pl->smem, st, pl->tc, pl->tmA[0], pl->tmA[1],
+    cudaError_t e = launch_pdl(conv_tc_kernel<KC, XP, WIDE>, pl->grid, kTcThreads, pl->smem, st, pl->tc, pl->tmA[0], pl->tmA[1],
                                pl->tmA[2], pl->tmW);
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
     return OCCD_OK;
   }
-  conv_tc_kernel<KC, XP><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->tc, pl->tmA[0], pl->tmA[1], pl->tmA[2], pl->tmW);
+  conv_tc_kernel<KC, XP, WIDE><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->tc, pl->tmA[0], pl->tmA[1], pl->tmA[2], pl->tmW);
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
@@ -1174,15 +1185,22 @@ extern "C" int occd_conv_run(const occd_conv_plan* pl, void* stream) {
   }
   if (pl->impl == OCCD_CONV_IMPL_TCX) {
     switch (pl->kc) {
-      case 64: return launch_tc<64, true>(pl, st);
-      case 32: return launch_tc<32, true>(pl, st);
-      case 16: return launch_tc<16, true>(pl, st);
+      case 64: return launch_tc<64, true, false>(pl, st);
+      case 32: return launch_tc<32, true, false>(pl, st);
+      case 16: return launch_tc<16, true, false>(pl, st);
+    }
+  }
+  if (pl->tc.epi.wide) {   // OCCD_EPI_WIDE=1 and every window 32-byte aligned: 256-bit epilogue instance
+    switch (pl->kc) {
+      case 64: return launch_tc<64, false, true>(pl, st);
+      case 32: return launch_tc<32, false, true>(pl, st);
+      case 16: return launch_tc<16, false, true>(pl, st);
     }
   }
   switch (pl->kc) {
-    case 64: return launch_tc<64, false>(pl, st);
-    case 32: return launch_tc<32, false>(pl, st);
-    case 16: return launch_tc<16, false>(pl, st);
+    case 64: return launch_tc<64, false, false>(pl, st);
+    case 32: return launch_tc<32, false, false>(pl, st);
+    case 16: return launch_tc<16, false, false>(pl, st);
   }
   occd_set_last_error("occd_conv_run: bad plan");
   return OCCD_ERR_ARG;

@@ -6,6 +6,11 @@ ssc_logit with the default configuration's (relative error + arg-max agreement).
     python tools/ab_experiments.py halox tcx+halox  # chosen combinations
 
 Prints one line per configuration and writes gpurun_out/ab_experiments.json.
+
+Kernel-level parity of the variants first (each in its own process, the C-side switches are read once):
+    OCCD_EXPERIMENTAL=1 python -m pytest tests/test_gpu_conv.py tests/test_gpu_ops.py -q -m gpu
+    OCCD_EPI_WIDE=1 python -m pytest tests/test_gpu_conv.py -q -m gpu
+    OCCD_PDL=1 python -m pytest tests/test_gpu_conv.py tests/test_gpu_unet3d.py -q -m gpu
 """
 import json
 import os
@@ -18,6 +23,7 @@ SWITCHES = {
     "tcx": {"OCCDEPTH_TCX": "1"},            # x-packed per-tap kernel (Cout <= 80 convs with W taps)
     "pdl": {"OCCD_PDL": "1"},                # programmatic dependent launch for the conv kernels
     "sestrip": {"OCCDEPTH_SE_IMPL": "strip"},  # SE gate fold, one CTA per 32-channel strip
+    "epiwide": {"OCCD_EPI_WIDE": "1"},        # 256-bit epilogue loads/stores (per-tap kernel, aligned windows)
     "stages4": {"OCCD_TC_STAGES_MIN": "4"},   # >= 4 pipeline stages for one-item-per-tile convs (1x1 layers)
     "stages8": {"OCCD_TC_STAGES_MIN": "8"},
     "dwdirect": {"OCCDEPTH_DW_IMPL": "direct"},  # the old register-window depthwise kernel (for reference)
@@ -61,7 +67,7 @@ def run(name, env_extra, steps, dump):
 
 def main():
     import torch
-    names = sys.argv[1:] or list(SWITCHES) + ["halox+tcx+pdl+sestrip"]
+    names = sys.argv[1:] or list(SWITCHES) + ["halox+tcx+pdl+sestrip+epiwide"]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     base_dump = "/tmp/ab_default.pt"
     base, err = run("default", {}, 10, base_dump)
