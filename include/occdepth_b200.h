@@ -101,6 +101,8 @@ int occd_cl_to_planar(const void* in, int in_dtype, float* out, long long B, int
                               /* lane-shifted partials); taps in lexicographic (dz,dy,dx) order         */
 #define OCCD_CONV_IMPL_TCX 4  /* per-tap kernel with the same W-tap packing: (src,dz,dy) groups of dx =   */
                               /* -1,0,+1, W stride 1, 3*Cout_pad <= 256, tiles 32 wide (30 outputs)       */
+#define OCCD_CONV_IMPL_TCM2 5 /* per-tap kernel, two M tiles (2 x 128 positions) per weight tile: less      */
+                              /* operand traffic per MMA for wide layers; shared weights only              */
 #define OCCD_OUT1_NONE 0
 #define OCCD_OUT1_BF16_CL 1    /* pre-activation copy, channels-last bf16                          */
 #define OCCD_OUT1_F32_PLANAR 2 /* pre-activation copy, fp32 [B][C][positions] (reference layout)   */

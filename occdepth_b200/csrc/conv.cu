@@ -32,6 +32,7 @@ struct TcParams {
   int a_bytes, b_stride, b_bytes;
   int tmem_cols;
   int pdl;           // launched with programmatic stream serialization: wait for the producer grid after the prologue
+  int m2_sets;       // M2 kernel: 0 = not an M2 plan, else number of {D0, D1} accumulator sets in TMEM (1 | 2)
   long long* trace;  // optional [tile][8] clock64 stamps of CTA 0 (tools/conv_trace.py)
   signed char tap_src[OCCD_CONV_MAX_TAPS];
   short tap_dz[OCCD_CONV_MAX_TAPS], tap_dy[OCCD_CONV_MAX_TAPS], tap_dx[OCCD_CONV_MAX_TAPS];
@@ -262,6 +263,208 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       tc::fence_before_sync();
       tc::mbar_arrive(tmem_empty_bar + 8u * acc);  // this thread's TMEM reads of the buffer are done
       if (tracer && j < 64) p.trace[j * 8 + 6] = clock64();
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// M2 variant of the per-tap kernel: every pipeline item carries TWO consecutive M tiles (A0, A1: 2 x 128 positions)
+// and ONE weight tile B, and feeds two accumulators D0 += A0.B, D1 += A1.B.  The wide decoder convs are bound by
+// operand traffic L2 -> SM (ncu: 43 B/cycle/SM at 42 % tensor-pipe activity for 128x160 tiles, where full rate
+// would need 115 B/cycle); sharing B between two M tiles cuts that by (128+N)/(128+N/2) -- 1.38x at N = 160.
+// TMEM holds nsets x {D0, D1}: two sets (epilogue of pair j overlaps the MMAs of pair j+1) when 4*N_tile <= 512,
+// otherwise one.  All 16 epilogue warps work on every pair: group g drains M tile (g & 1), column half (g >> 1).
+// TcParams::a_bytes is the size of ONE A tile; an item's A region is 2 * a_bytes.
+template <int KC>
+__global__ void __launch_bounds__(kTcThreads)
+conv_tc_m2_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap tmA0,
+                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmW) {
+  constexpr int ROW_BYTES = KC * 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t item_a = 2u * (uint32_t)p.a_bytes;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_a + (uint32_t)(p.stages * p.group) * item_a;
+  const uint32_t bar_base = smem_b + (uint32_t)(p.stages * p.group) * p.b_stride;
+  const uint32_t full_bar = bar_base;
+  const uint32_t empty_bar = bar_base + 8u * kMaxStages;
+  const uint32_t tmem_full_bar = bar_base + 16u * kMaxStages;       // [2]
+  const uint32_t tmem_empty_bar = tmem_full_bar + 16u;              // [2]
+  const uint32_t tmem_slot = tmem_empty_bar + 16u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles_n = p.Cout_pad / p.N_tile;
+  const int num_pairs = ((p.num_m_tiles + 1) >> 1) * n_tiles_n;
+  const int nsets = p.m2_sets;                        // 1 or 2
+  const uint32_t set_stride = 2u * (uint32_t)p.N_tile;  // columns of one {D0, D1} set
+
+  int iters_per_tile = 0;
+  for (int i = 0; i < p.n_taps; ++i) iters_per_tile += p.n_kchunks[p.tap_src[i]];
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA0);
+    tc::prefetch_tmap(&tmW);
+    for (int s = 0; s < p.stages; ++s) {
+      tc::mbar_init(full_bar + 8u * s, 1);
+      tc::mbar_init(empty_bar + 8u * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(tmem_full_bar + 8u * a, 1);
+      tc::mbar_init(tmem_empty_bar + 8u * a, 512);  // all sixteen epilogue warps arrive
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (p.pdl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+
+  // M tile index -> (batch, tile origin); an index past the last tile decodes to b == B (TMA zero-fills, the
+  // epilogue masks it)
+  auto decode = [&](int mt, int& b, int& td, int& th, int& tw) {
+    int t = mt;
+    tw = t % p.tiles_w; t /= p.tiles_w;
+    th = t % p.tiles_h; t /= p.tiles_h;
+    td = t % p.tiles_d; t /= p.tiles_d;
+    b = t;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      const CUtensorMap* maps[3] = {&tmA0, &tmA1, &tmA2};
+      int s = 0;
+      uint32_t ph = 0;
+      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+        const int nt = pair % n_tiles_n;
+        const int mp = pair / n_tiles_n;
+        int b[2], td[2], th[2], tw[2];
+        decode(2 * mp, b[0], td[0], th[0], tw[0]);
+        decode(2 * mp + 1, b[1], td[1], th[1], tw[1]);
+        const int n0 = nt * p.N_tile;
+        int g = 0;
+        int remaining = iters_per_tile;
+        for (int tp = 0; tp < p.n_taps; ++tp) {
+          const int src = p.tap_src[tp];
+          const int wrow = b[0] * p.w_batch_rows + tp * p.Cout_pad + n0;
+          const int nk = p.n_kchunks[src];
+          for (int kc = 0; kc < nk; ++kc) {
+            if (g == 0) {
+              const int cnt = remaining < p.group ? remaining : p.group;
+              tc::mbar_wait(empty_bar + 8u * s, ph ^ 1u);
+              tc::mbar_expect_tx(full_bar + 8u * s, (uint32_t)(cnt * (2 * p.a_bytes + p.b_bytes)));
+            }
+            const uint32_t sa = smem_a + (uint32_t)(s * p.group + g) * item_a;
+            const uint32_t sb = smem_b + (uint32_t)(s * p.group + g) * p.b_stride;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              tc::tma_load_5d(sa + (uint32_t)h * p.a_bytes, maps[src], full_bar + 8u * s, kc * KC,
+                              tw[h] * p.TW * p.stride[2] + p.tap_dx[tp], th[h] * p.TH * p.stride[1] + p.tap_dy[tp],
+                              td[h] * p.TD * p.stride[0] + p.src_d0 + p.tap_dz[tp], b[h]);
+            tc::tma_load_2d(sb, &tmW, full_bar + 8u * s, kc * KC, wrow);
+            --remaining;
+            if (++g == p.group || remaining == 0) {
+              g = 0;
+              if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = tc::make_idesc_bf16(128, p.N_tile);
+      const uint64_t da0 = tc::make_sdesc(smem_a, ROW_BYTES);
+      const uint64_t db0 = tc::make_sdesc(smem_b, ROW_BYTES);
+      int s = 0;
+      uint32_t ph = 0;
+      int j = 0;
+      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++j) {
+        const uint32_t set = (uint32_t)(j % nsets);
+        const uint32_t use = (uint32_t)(j / nsets);
+        tc::mbar_wait(tmem_empty_bar + 8u * set, (use & 1u) ^ 1u);  // epilogue drained this set
+        tc::fence_after_sync();
+        const uint32_t d0 = tmem_base + set * set_stride;
+        const uint32_t d1 = d0 + (uint32_t)p.N_tile;
+        for (int it = 0; it < iters_per_tile;) {
+          tc::mbar_wait(full_bar + 8u * s, ph);
+          tc::fence_after_sync();
+          const int cnt = (iters_per_tile - it) < p.group ? (iters_per_tile - it) : p.group;
+          for (int g = 0; g < cnt; ++g, ++it) {
+            const uint64_t da = da0 + (uint64_t)((s * p.group + g) * (item_a >> 4));
+            const uint64_t da_1 = da + (uint64_t)(p.a_bytes >> 4);
+            const uint64_t db = db0 + (uint64_t)((s * p.group + g) * (p.b_stride >> 4));
+            if (it == 0) {
+              tc::mma_bf16_imm<0>(d0, da, db, idesc);
+#pragma unroll
+              for (int k = 1; k < KC / 16; ++k) tc::mma_bf16_imm<1>(d0, da + 2 * k, db + 2 * k, idesc);
+              tc::mma_bf16_imm<0>(d1, da_1, db, idesc);
+#pragma unroll
+              for (int k = 1; k < KC / 16; ++k) tc::mma_bf16_imm<1>(d1, da_1 + 2 * k, db + 2 * k, idesc);
+            } else {
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) tc::mma_bf16_imm<1>(d0, da + 2 * k, db + 2 * k, idesc);
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) tc::mma_bf16_imm<1>(d1, da_1 + 2 * k, db + 2 * k, idesc);
+            }
+          }
+          tc::mma_commit(empty_bar + 8u * s);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+        tc::mma_commit(tmem_full_bar + 8u * set);
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;
+    const int h = ((warp - 2) >> 2) & 1;     // which M tile of the pair
+    const int half = (warp - 2) >> 3;        // which half of the 16-column chunks
+    const int n_chunks = p.N_tile >> 4;
+    const int c_begin = half == 0 ? 0 : ((n_chunks + 1) >> 1) * 16;
+    const int c_end = half == 0 ? ((n_chunks + 1) >> 1) * 16 : p.N_tile;
+    const int row = q * 32 + lane;
+    const int rw = row % p.TW;
+    const int rh = (row / p.TW) % p.TH;
+    const int rd = row / (p.TW * p.TH);
+    int j = 0;
+    for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++j) {
+      const uint32_t set = (uint32_t)(j % nsets);
+      const uint32_t use = (uint32_t)(j / nsets);
+      const int nt = pair % n_tiles_n;
+      const int mp = pair / n_tiles_n;
+      int b, td, th, tw;
+      decode(2 * mp + h, b, td, th, tw);
+      const int od = td * p.TD + rd, oh = th * p.TH + rh, ow = tw * p.TW + rw;
+      const bool valid = b < p.epi.B && od < p.epi.OD && oh < p.epi.OH && ow < p.epi.OW;
+      const int n0 = nt * p.N_tile;
+      tc::mbar_wait(tmem_full_bar + 8u * set, use & 1u);
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + set * set_stride + (uint32_t)(h * p.N_tile) + ((uint32_t)(q * 32) << 16);
+      for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(taddr + (uint32_t)c0, v);
+        if (valid) conv_epilogue_row<16>(p.epi, b, od, oh, ow, n0 + c0, v);
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive(tmem_empty_bar + 8u * set);
     }
   }
   tc::fence_before_sync();
@@ -816,7 +1019,13 @@ static int build_halo_plan(const occd_conv_desc* d, occd_conv_plan* pl, bool xp)
 }
 
 // Per-tap (TC) plan: host arithmetic only (tests/host_emul/ runs it without a GPU); tc_encode builds the tensor maps.
-static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
+// mode: 0 = per-tap kernel, 1 = x-packed (TCX), 2 = two M tiles per weight tile (M2)
+static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, int mode) {
+  const bool xp = mode == 1, m2 = mode == 2;
+  if (m2 && d->weight_per_image) {
+    occd_set_last_error("occd_conv_plan_create(m2): per-image weight sets are not supported (a pair may span two images)");
+    return OCCD_ERR_UNSUPPORTED;
+  }
   int maxC = 0;
   for (int s = 0; s < d->n_src; ++s) maxC = d->src_C[s] > maxC ? d->src_C[s] : maxC;
   TcParams& t = pl->tc;
@@ -899,24 +1108,31 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
       best = n;
       if (m_tiles0 * (d->Cout_pad / n) >= n_sms) break;
     }
-    if (m_tiles0 * (d->Cout_pad / t.N_tile) < n_sms) t.N_tile = best;
+    if (!m2 && m_tiles0 * (d->Cout_pad / t.N_tile) < n_sms) t.N_tile = best;
   }
   if (xp) t.N_tile = 3 * d->Cout_pad;  // one N tile: the three taps' weights stacked
   t.tmem_cols = 32;
   while (t.tmem_cols < t.N_tile) t.tmem_cols *= 2;
   { const char* e = getenv("OCCD_CONV_TRACE_PTR"); t.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
   t.tmem_cols *= 2;  // two accumulators: the epilogue of tile j overlaps the MMAs of tile j+1
+  t.m2_sets = 0;
+  if (m2) {
+    // {D0, D1} per set; a second set (epilogue / MMA overlap across pairs) when it fits the 512 columns
+    t.m2_sets = 4 * t.N_tile <= 512 ? 2 : 1;
+    t.tmem_cols = 32;
+    while (t.tmem_cols < t.m2_sets * 2 * t.N_tile) t.tmem_cols *= 2;
+  }
   t.pdl = pdl_enabled();
   t.a_bytes = 128 * KC * 2;
   t.b_bytes = t.N_tile * KC * 2;
   t.b_stride = round_up(t.b_bytes, 1024);
-  const int stage_bytes = t.a_bytes + t.b_stride;
+  const int stage_bytes = (m2 ? 2 : 1) * t.a_bytes + t.b_stride;
   int total_iters = 0;
   for (int i = 0; i < t.n_taps; ++i) total_iters += t.n_kchunks[t.tap_src[i]];
   const int budget = 200 * 1024;  // persistent kernel: one CTA per SM owns the shared memory
   // (tap, k-chunk) items per pipeline stage: the single-thread producer/MMA hand-off costs ~0.25 us, so a stage
   // must carry >= ~512 tensor-pipe cycles of work (or up to 9 items) while leaving >= 3 stages in flight
-  const int mma_cycles_per_item = (KC / 16) * (128 * t.N_tile / 256);
+  const int mma_cycles_per_item = (m2 ? 2 : 1) * (KC / 16) * (128 * t.N_tile / 256);
   int group = (512 + mma_cycles_per_item - 1) / mma_cycles_per_item;
   if (group > 9) group = 9;
   if (group > total_iters) group = total_iters;
@@ -938,7 +1154,7 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
   t.stages = stages;
   pl->smem = (size_t)stages * group * stage_bytes + 16 * kMaxStages + 64 + 1024;  // + barriers + alignment slack
   const long long m_tiles = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w;
-  const long long all_tiles = m_tiles * (xp ? 1 : d->Cout_pad / t.N_tile);
+  const long long all_tiles = (m2 ? (m_tiles + 1) / 2 : m_tiles) * (xp ? 1 : d->Cout_pad / t.N_tile);
   if (all_tiles > 2147483647LL) {
     occd_set_last_error("occd_conv_plan_create: too many tiles");
     return OCCD_ERR_UNSUPPORTED;
@@ -1044,7 +1260,8 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
                    "occd_conv_plan_create: tap offset");
   }
   OCCD_CHECK_ARG(d->impl == OCCD_CONV_IMPL_TC || d->impl == OCCD_CONV_IMPL_SIMT || d->impl == OCCD_CONV_IMPL_HALO ||
-                 d->impl == OCCD_CONV_IMPL_HALOX || d->impl == OCCD_CONV_IMPL_TCX, "occd_conv_plan_create: impl");
+                 d->impl == OCCD_CONV_IMPL_HALOX || d->impl == OCCD_CONV_IMPL_TCX || d->impl == OCCD_CONV_IMPL_TCM2,
+                 "occd_conv_plan_create: impl");
   OCCD_CHECK_ARG(!d->weight_per_image || (d->impl != OCCD_CONV_IMPL_HALO && d->impl != OCCD_CONV_IMPL_HALOX),
                  "occd_conv_plan_create: per-image weights: TC or SIMT impl");
 
@@ -1085,7 +1302,7 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
 
   // ---------------- TC plan (per-tap kernel; TCX: three W taps per MMA) ----------------
   {
-    int rc = tc_geometry(d, pl, d->impl == OCCD_CONV_IMPL_TCX);
+    int rc = tc_geometry(d, pl, d->impl == OCCD_CONV_IMPL_TCX ? 1 : (d->impl == OCCD_CONV_IMPL_TCM2 ? 2 : 0));
     if (rc == OCCD_OK) rc = tc_encode(d, pl);
     if (rc != OCCD_OK) { delete pl; return rc; }
   }
@@ -1161,6 +1378,28 @@ static int launch_halo(const occd_conv_plan* pl, cudaStream_t st) {
   return OCCD_OK;
 }
 
+template <int KC>
+static int launch_tc_m2(const occd_conv_plan* pl, cudaStream_t st) {
+  static bool attr_set[64] = {false};  // per instantiation, per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_m2_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
+    attr_set[dev] = true;
+  }
+  if (pl->tc.pdl) {
+    cudaError_t e = launch_pdl(conv_tc_m2_kernel<KC>, pl->grid, kTcThreads, pl->smem, st, pl->tc, pl->tmA[0],
+                               pl->tmA[1], pl->tmA[2], pl->tmW);
+    if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
+    return OCCD_OK;
+  }
+  conv_tc_m2_kernel<KC><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->tc, pl->tmA[0], pl->tmA[1], pl->tmA[2], pl->tmW);
+  OCCD_CHECK_LAUNCH();
+  return OCCD_OK;
+}
+
 extern "C" int occd_conv_run(const occd_conv_plan* pl, void* stream) {
   OCCD_CHECK_ARG(pl != nullptr, "occd_conv_run: null plan");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1181,6 +1420,13 @@ extern "C" int occd_conv_run(const occd_conv_plan* pl, void* stream) {
       case 64: return launch_halo<64, true>(pl, st);
       case 32: return launch_halo<32, true>(pl, st);
       case 16: return launch_halo<16, true>(pl, st);
+    }
+  }
+  if (pl->impl == OCCD_CONV_IMPL_TCM2) {
+    switch (pl->kc) {
+      case 64: return launch_tc_m2<64>(pl, st);
+      case 32: return launch_tc_m2<32>(pl, st);
+      case 16: return launch_tc_m2<16>(pl, st);
     }
   }
   if (pl->impl == OCCD_CONV_IMPL_TCX) {

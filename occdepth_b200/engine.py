@@ -24,10 +24,27 @@ def default_impl():
     """'auto' (default): halo-tile tcgen05 kernel where the shape qualifies, else the per-tap tcgen05 kernel;
     'tc' / 'halo' / 'simt' force one implementation (simt = CUDA-core cross-check)."""
     v = os.environ.get("OCCDEPTH_CONV_IMPL", "auto").lower()
-    if v not in ("auto", "tc", "simt", "halo", "halox", "tcx"):
-        raise ValueError("OCCDEPTH_CONV_IMPL must be 'auto', 'tc', 'tcx', 'halo', 'halox' or 'simt'")
+    if v not in ("auto", "tc", "simt", "halo", "halox", "tcx", "tcm2"):
+        raise ValueError("OCCDEPTH_CONV_IMPL must be 'auto', 'tc', 'tcx', 'tcm2', 'halo', 'halox' or 'simt'")
     return {"auto": None, "tc": _lib.CONV_IMPL_TC, "simt": _lib.CONV_IMPL_SIMT, "halo": _lib.CONV_IMPL_HALO,
-            "halox": _lib.CONV_IMPL_HALOX, "tcx": _lib.CONV_IMPL_TCX}[v]
+            "halox": _lib.CONV_IMPL_HALOX, "tcx": _lib.CONV_IMPL_TCX, "tcm2": _lib.CONV_IMPL_TCM2}[v]
+
+
+def prefer_tcm2():
+    """OCCDEPTH_TCM2=1: in 'auto' mode run wide, large convs on the M2 kernel (two M tiles per weight tile).  Off by
+    default, same status as OCCDEPTH_HALOX / OCCDEPTH_TCX."""
+    return os.environ.get("OCCDEPTH_TCM2", "0") == "1"
+
+
+def tcm2_eligible(B, out_dims, Cout_pad, n_items, weight_per_image, n_sms=148):
+    """wide layers (N tile >= 128) with enough work that the halved tile count still fills the GPU"""
+    if weight_per_image or Cout_pad < 128 or n_items < 9:
+        return False
+    n_tile = max(n for n in range(16, min(256, Cout_pad) + 1, 16) if Cout_pad % n == 0)
+    if n_tile < 128:
+        return False
+    m_tiles = -(-(B * out_dims[0] * out_dims[1] * out_dims[2]) // 128)
+    return (m_tiles + 1) // 2 * (Cout_pad // n_tile) >= 2 * n_sms
 
 
 def prefer_halox():
@@ -225,6 +242,10 @@ class ConvOp:
                 impl = _lib.CONV_IMPL_HALOX
             if impl == _lib.CONV_IMPL_TC and prefer_tcx() and tcx_eligible(taps, stride, Cout_pad):
                 impl = _lib.CONV_IMPL_TCX
+            n_items = sum(-(-srcs[t[0]].C // KC) for t in taps)
+            if impl == _lib.CONV_IMPL_TC and prefer_tcm2() and tcm2_eligible(B, out_dims, Cout_pad, n_items,
+                                                                              weight_per_image):
+                impl = _lib.CONV_IMPL_TCM2
         d.impl = impl
         d.n_src = len(srcs)
         for i, s in enumerate(srcs):
@@ -267,7 +288,7 @@ class ConvOp:
         self.flops = 2 * B * OD * OH * OW * Cout * sum(srcs[t[0]].C for t in taps)
         h = C.c_void_p()
         rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
-        if rc != 0 and auto and d.impl == _lib.CONV_IMPL_TCX:
+        if rc != 0 and auto and d.impl in (_lib.CONV_IMPL_TCX, _lib.CONV_IMPL_TCM2):
             d.impl = _lib.CONV_IMPL_TC
             rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
         if rc != 0 and auto and d.impl == _lib.CONV_IMPL_HALOX:

@@ -14,10 +14,12 @@ extern "C" const char* tc_model_error() { return g_err; }
 // desc: src[s] -> float [B][ID][IH][IW][src_cstride], weight -> float [(B if per image)][n_taps][Cout_pad][Kpad],
 // bias -> float;  out: float [B][ODf][OHf][OWf][Cout], pre-filled by the caller
 // info (optional, 8 ints): TD TH TW N_tile n_items_per_tile stages group grid
-extern "C" int tc_model(const occd_conv_desc* d, int xp, float* out, int* info) {
+extern "C" int tc_model(const occd_conv_desc* d, int mode, float* out, int* info) {
+  const int xp = mode == 1 ? 1 : 0;
+  const bool m2 = mode == 2;
   occd_conv_plan pl;
   memset(&pl, 0, sizeof(pl));
-  const int rc = tc_geometry(d, &pl, xp != 0);
+  const int rc = tc_geometry(d, &pl, mode);  // 0 per-tap, 1 x-packed, 2 M2
   if (rc != OCCD_OK) return rc;
   const TcParams& p = pl.tc;
   const int KC = pl.kc;
@@ -29,12 +31,24 @@ extern "C" int tc_model(const occd_conv_desc* d, int xp, float* out, int* info) 
   }
   if (p.TD * p.TH * p.TW != 128) return 100;
   if (pl.smem > 227 * 1024 || p.stages < 1 || p.group < 1 || p.tmem_cols > 512 || 2 * p.N_tile > p.tmem_cols) return 101;
+  if (m2) {
+    // kernel-side carve-up: stages * group * (2 * a_bytes + b_stride) + barriers must fit what the host asked for
+    if (p.m2_sets < 1 || p.m2_sets > 2 || p.m2_sets * 2 * p.N_tile > p.tmem_cols) return 104;
+    if ((size_t)p.stages * p.group * (2 * p.a_bytes + p.b_stride) + 16 * kMaxStages + 64 + 1024 > pl.smem) return 105;
+    const long long pairs = ((long long)p.num_m_tiles + 1) / 2 * (p.Cout_pad / p.N_tile);
+    if ((long long)pl.grid.x > pairs) return 106;
+  } else if (p.m2_sets != 0) {
+    return 107;
+  }
   if (xp && (p.TW != 32 || p.TWv != 30 || p.N_tile != 3 * p.Cout_pad)) return 102;
   if (!out) return 0;
   const float* wgt = (const float*)d->weight;
   const float* bias = (const float*)d->bias;
   const int n_tiles_n = xp ? 1 : p.Cout_pad / p.N_tile;
-  const int num_tiles = p.num_m_tiles * n_tiles_n;
+  // M2: the kernel walks pairs (2*mp, 2*mp+1) of M tiles; per tile the arithmetic is the per-tap kernel's, except
+  // that an odd tile count adds one phantom tile (decodes to b == B: zero-filled loads, masked stores)
+  const int m_tiles_walked = m2 ? ((p.num_m_tiles + 1) / 2) * 2 : p.num_m_tiles;
+  const int num_tiles = m_tiles_walked * n_tiles_n;
   std::vector<float> acc((size_t)128 * p.N_tile), A((size_t)128 * KC);
   for (int tile = 0; tile < num_tiles; ++tile) {
     const int nt = tile % n_tiles_n;
@@ -50,7 +64,8 @@ extern "C" int tc_model(const occd_conv_desc* d, int xp, float* out, int* info) 
     for (int tp = 0; tp < p.n_taps; ++tp) {
       const int src = p.tap_src[tp];
       const int cw = iw0 + p.tap_dx[tp], ch = ih0 + p.tap_dy[tp], cd = id0 + p.tap_dz[tp];
-      const int wrow = b * p.w_batch_rows + (xp ? tp * p.N_tile : tp * p.Cout_pad + n0);
+      const int wrow = (m2 ? 0 : b * p.w_batch_rows) + (xp ? tp * p.N_tile : tp * p.Cout_pad + n0);
+      if (m2 && p.w_batch_rows != 0) return 108;
       const float* s = (const float*)d->src[src];
       const int C = d->src_C[src], cs = d->src_cstride[src], coff = d->src_coff[src];
       for (int kc = 0; kc < p.n_kchunks[src]; ++kc) {
@@ -82,7 +97,8 @@ extern "C" int tc_model(const occd_conv_desc* d, int xp, float* out, int* info) 
         const int rh = (row / p.TW) % p.TH;
         const int rd = row / (p.TW * p.TH);
         const int od = td * p.TD + rd, oh = th * p.TH + rh, ow = xp ? tw * 30 + rw - 1 : tw * p.TW + rw;
-        const bool valid = od < p.epi.OD && oh < p.epi.OH && ow < p.epi.OW && (!xp || (rw >= 1 && rw <= 30));
+        const bool valid = b < p.epi.B && od < p.epi.OD && oh < p.epi.OH && ow < p.epi.OW &&
+                           (!xp || (rw >= 1 && rw <= 30));
         if (xp && rw != lane) return 103;
         if (!valid) continue;
         const size_t pos = (((size_t)b * p.epi.ODf + ((size_t)od * p.epi.omul[0] + p.epi.oadd[0])) * p.epi.OHf +

@@ -90,3 +90,24 @@ def test_conv_tc_xpacked(case):
         pytest.skip("x-packed per-tap kernel: set OCCD_EXPERIMENTAL=1 to run")
     e, info = G.conv_case(_lib.CONV_IMPL_TCX, **TCX_CASES[case])
     assert e <= TOL, (e, info)
+
+
+M2_CASES = {
+    "m_2d_c160": dict(k=(1, 3, 3), Cin=160, Cout=160, dims=(1, 40, 90), res=True),       # N 160: one TMEM set
+    "m_2d_c64_n128": dict(k=(1, 3, 3), Cin=64, Cout=128, dims=(1, 33, 70), B=2),        # N 128: two sets
+    "m_3d_odd_tiles": dict(Cin=32, Cout=64, dims=(3, 9, 15)),                            # odd tile count: phantom tile
+    "m_1x1_n256": dict(k=(1, 1, 1), Cin=96, Cout=256, dims=(1, 30, 50), act="silu"),
+    "m_ntiles2": dict(k=(1, 3, 3), Cin=48, Cout=320, dims=(1, 20, 37)),                  # two N tiles of 160
+}
+
+
+@pytest.mark.parametrize("case", sorted(M2_CASES))
+def test_conv_tc_m2(case):
+    """M2 per-tap kernel (two M tiles per weight tile); opt-in until it has been seen green on a B200 (CPU model:
+    tests/test_tc_model_host.py)"""
+    import os
+    from occdepth_b200 import _lib
+    if os.environ.get("OCCD_EXPERIMENTAL") != "1":
+        pytest.skip("M2 per-tap kernel: set OCCD_EXPERIMENTAL=1 to run")
+    e, info = G.conv_case(_lib.CONV_IMPL_TCM2, **M2_CASES[case])
+    assert e <= TOL, (e, info)

@@ -33,7 +33,7 @@ def model(tmp_path_factory):
     return lib
 
 
-def run_model(lib, xs, w, bias, stride, pad, xp, per_image=False):
+def run_model(lib, xs, w, bias, stride, pad, mode, per_image=False):
     """xs: list of [B,Ci,D,H,W] sources (torch.cat along channels is what the conv sees); w [Cout, sum Ci, kd,kh,kw]
     (or [B, Cout, ...] when per_image)"""
     B, _, D, H, W = xs[0].shape
@@ -45,7 +45,7 @@ def run_model(lib, xs, w, bias, stride, pad, xp, per_image=False):
     KC = 64 if maxC > 32 else (32 if maxC > 16 else 16)
     Kpad = (maxC + KC - 1) // KC * KC
     d = _lib.ConvDesc()
-    d.impl = _lib.CONV_IMPL_TCX if xp else _lib.CONV_IMPL_TC
+    d.impl = {0: _lib.CONV_IMPL_TC, 1: _lib.CONV_IMPL_TCX, 2: _lib.CONV_IMPL_TCM2}[int(mode)]
     d.n_src = len(xs)
     keep = []
     for i, x in enumerate(xs):
@@ -86,7 +86,7 @@ def run_model(lib, xs, w, bias, stride, pad, xp, per_image=False):
     d.out0 = out.data_ptr()
     d.out0_cstride = (Cout + 7) // 8 * 8
     info = (C.c_int * 8)()
-    rc = lib.tc_model(C.byref(d), 1 if xp else 0, out.data_ptr(), info)
+    rc = lib.tc_model(C.byref(d), int(mode), out.data_ptr(), info)
     if rc != 0:
         return None, (rc, lib.tc_model_error().decode())
     keys = ("TD", "TH", "TW", "N_tile", "items", "stages", "group", "grid")
@@ -111,6 +111,26 @@ CASES = {
     "per_image_1x1": (2, [96], 48, (1, 6, 11), (1, 1, 1), (1, 1, 1), (0, 0, 0), True, False),
     "per_image_3x3": (2, [32], 16, (1, 6, 35), (1, 3, 3), (1, 1, 1), (0, 1, 1), True, True),
 }
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_tc_m2_plan_model_matches_conv3d(model, case):
+    """M2 plans (two M tiles per weight tile): pair walk incl. the phantom tile of an odd tile count, smem / TMEM
+    budget of the doubled A stage"""
+    B, Cins, Cout, dims, k, stride, pad, per_image, _ = CASES[case]
+    g = torch.Generator().manual_seed(sum(Cins) + Cout + dims[2] + 7)
+    xs = [torch.randn(B, c, *dims, generator=g) for c in Cins]
+    wshape = (Cout, sum(Cins), *k)
+    w = torch.randn(*((B,) + wshape if per_image else wshape), generator=g) / (sum(Cins) * k[0] * k[1] * k[2]) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    got, info = run_model(model, xs, w, bias, stride, pad, 2, per_image)
+    if per_image:
+        assert got is None and "m2" in info[1], info
+        return
+    assert got is not None, info
+    ref = reference(xs, w, bias, stride, pad, per_image)
+    assert torch.isfinite(got).all()
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4), float((got - ref).abs().max())
 
 
 @pytest.mark.parametrize("xp", [False, True])

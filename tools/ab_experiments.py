@@ -21,6 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SWITCHES = {
     "halox": {"OCCDEPTH_HALOX": "1"},        # x-packed halo kernel (head convs)
     "tcx": {"OCCDEPTH_TCX": "1"},            # x-packed per-tap kernel (Cout <= 80 convs with W taps)
+    "tcm2": {"OCCDEPTH_TCM2": "1"},          # two M tiles per weight tile for the wide decoder convs
     "pdl": {"OCCD_PDL": "1"},                # programmatic dependent launch for the conv kernels
     "sestrip": {"OCCDEPTH_SE_IMPL": "strip"},  # SE gate fold, one CTA per 32-channel strip
     "epiwide": {"OCCD_EPI_WIDE": "1"},        # 256-bit epilogue loads/stores (per-tap kernel, aligned windows)
@@ -67,7 +68,7 @@ def run(name, env_extra, steps, dump):
 
 def main():
     import torch
-    names = sys.argv[1:] or list(SWITCHES) + ["halox+tcx+pdl+sestrip+epiwide"]
+    names = sys.argv[1:] or list(SWITCHES) + ["halox+tcx+tcm2+pdl+sestrip+epiwide"]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     base_dump = "/tmp/ab_default.pt"
     base, err = run("default", {}, 10, base_dump)
