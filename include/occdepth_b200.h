@@ -211,6 +211,9 @@ int occd_scale_weights(const float* master, const float* gate, void* out, int ro
 /* F.interpolate(mode="bilinear", align_corners=True) of UpSampleBN.forward (unet2d.py:39-44)      */
 int occd_upsample_bilinear_ac(const void* in, void* out, int B, int h, int w, int OH, int OW, int C, int cs_in,
                               int in_off, int cs_out, int out_off, void* stream);
+/* same contract, one block row per output row (block-uniform vertical weights)                    */
+int occd_upsample_bilinear_rows(const void* in, void* out, int B, int h, int w, int OH, int OW, int C, int cs_in,
+                              int in_off, int cs_out, int out_off, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* FlospDepth (the "OAD" depth branch, configs with trans_2d_to_3d: "flosp_depth")                */

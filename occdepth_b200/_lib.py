@@ -113,6 +113,7 @@ SYMBOLS = {
     "occd_channel_scale": (C.c_int, [_vp, _vp, _ll, _ll, _i, _i, _vp]),
     "occd_virtual_view_fwd": (C.c_int, [_vp, _vp, _vp] + [_i] * 8 + [_f, _vp]),
     "occd_upsample_bilinear_ac": (C.c_int, [_vp, _vp] + [_i] * 10 + [_vp]),
+    "occd_upsample_bilinear_rows": (C.c_int, [_vp, _vp] + [_i] * 10 + [_vp]),
 }
 
 

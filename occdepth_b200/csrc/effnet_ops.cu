@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "dwconv_tiled.cuh"
 #include "se_fold_strip.cuh"
+#include "upsample_rows.cuh"
 #include "../../include/occdepth_b200.h"
 
 namespace {
@@ -354,8 +355,8 @@ extern "C" int occd_scale_weights(const float* master, const float* gate, void* 
   return OCCD_OK;
 }
 
-extern "C" int occd_upsample_bilinear_ac(const void* in, void* out, int B, int h, int w, int OH, int OW, int C,
-                                         int cs_in, int in_off, int cs_out, int out_off, void* stream) {
+static int upsample_impl(bool rows, const void* in, void* out, int B, int h, int w, int OH, int OW, int C, int cs_in,
+                         int in_off, int cs_out, int out_off, void* stream) {
   OCCD_CHECK_ARG(in && out && B > 0 && h > 0 && w > 0 && OH > 0 && OW > 0 && C > 0, "occd_upsample_bilinear_ac: args");
   OCCD_CHECK_ARG(cs_in % 8 == 0 && cs_out % 8 == 0 && in_off % 8 == 0 && out_off % 8 == 0,
                  "occd_upsample_bilinear_ac: alignment");
@@ -363,11 +364,40 @@ extern "C" int occd_upsample_bilinear_ac(const void* in, void* out, int B, int h
   OCCD_CHECK_ARG(in_off + CV * 8 <= cs_in && out_off + CV * 8 <= cs_out, "occd_upsample_bilinear_ac: channel window");
   const float sy = OH > 1 ? (float)(h - 1) / (float)(OH - 1) : 0.f;
   const float sx = OW > 1 ? (float)(w - 1) / (float)(OW - 1) : 0.f;
+  if (rows) {
+    OCCD_CHECK_ARG((long long)B * OH <= 65535, "occd_upsample_bilinear_rows: B*OH too large");
+    upr::Args a{(const __nv_bfloat16*)in, (__nv_bfloat16*)out, h, w, OH, OW, CV, cs_in, in_off, cs_out, out_off, sy, sx};
+    const int cvb = upr::choose_cvb(CV);
+    const int pxb = upr::kThreads / cvb;
+    dim3 grid((OW + pxb - 1) / pxb, (CV + cvb - 1) / cvb, B * OH);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (cvb) {
+      case 1: upr::upsample_rows_kernel<1><<<grid, upr::kThreads, 0, st>>>(a); break;
+      case 2: upr::upsample_rows_kernel<2><<<grid, upr::kThreads, 0, st>>>(a); break;
+      case 4: upr::upsample_rows_kernel<4><<<grid, upr::kThreads, 0, st>>>(a); break;
+      case 8: upr::upsample_rows_kernel<8><<<grid, upr::kThreads, 0, st>>>(a); break;
+      case 16: upr::upsample_rows_kernel<16><<<grid, upr::kThreads, 0, st>>>(a); break;
+      default: upr::upsample_rows_kernel<32><<<grid, upr::kThreads, 0, st>>>(a); break;
+    }
+    OCCD_CHECK_LAUNCH();
+    return OCCD_OK;
+  }
   const long long total = (long long)B * OH * OW * CV;
   upsample_bilinear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, h, w, OH, OW, CV, cs_in, in_off, cs_out, out_off, sy, sx);
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
+}
+
+extern "C" int occd_upsample_bilinear_ac(const void* in, void* out, int B, int h, int w, int OH, int OW, int C,
+                                         int cs_in, int in_off, int cs_out, int out_off, void* stream) {
+  return upsample_impl(false, in, out, B, h, w, OH, OW, C, cs_in, in_off, cs_out, out_off, stream);
+}
+
+// same contract, one block row per output row (block-uniform vertical weights, no per-thread div/mod chain)
+extern "C" int occd_upsample_bilinear_rows(const void* in, void* out, int B, int h, int w, int OH, int OW, int C,
+                                           int cs_in, int in_off, int cs_out, int out_off, void* stream) {
+  return upsample_impl(true, in, out, B, h, w, OH, OW, C, cs_in, in_off, cs_out, out_off, stream);
 }
 
 static int se_gate_fold_impl(bool strip, long long* pool, float inv_hw, const float* w1, const float* b1,

@@ -74,17 +74,20 @@ def test_se_gate_fold(variant):
     assert float((out.float().cpu() - want).abs().max()) <= 2 ** -7 * float(want.abs().max())
 
 
-def test_bilinear_align_corners():
+@pytest.mark.parametrize("variant", ["flat", "rows"])
+def test_bilinear_align_corners(variant):
     from occdepth_b200 import _lib
     L = _lib.lib()
+    if variant == "rows" and os.environ.get("OCCD_EXPERIMENTAL") != "1":
+        pytest.skip("rows resize: CPU-emulation tested (tests/test_upsample_host.py); first GPU run is opt-in")
+    fn = L.occd_upsample_bilinear_rows if variant == "rows" else L.occd_upsample_bilinear_ac
     g = torch.Generator().manual_seed(0)
     B, C, h, w, OH, OW = 2, 24, 7, 9, 12, 22
     x = _bf(torch.randn(B, C, h, w, generator=g))
     ref = F.interpolate(x, size=(OH, OW), mode="bilinear", align_corners=True)
     xc = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
     y = torch.zeros(B, OH, OW, C, dtype=torch.bfloat16, device="cuda")
-    assert L.occd_upsample_bilinear_ac(xc.data_ptr(), y.data_ptr(), B, h, w, OH, OW, C, C, 0, C, 0,
-                                       _lib.stream_ptr()) == 0
+    assert fn(xc.data_ptr(), y.data_ptr(), B, h, w, OH, OW, C, C, 0, C, 0, _lib.stream_ptr()) == 0
     got = y.float().cpu().permute(0, 3, 1, 2)
     assert float((got - ref).abs().max()) <= 2 ** -7 * float(ref.abs().max())
 

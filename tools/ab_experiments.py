@@ -24,6 +24,7 @@ SWITCHES = {
     "tcm2": {"OCCDEPTH_TCM2": "1"},          # two M tiles per weight tile for the wide decoder convs
     "pdl": {"OCCD_PDL": "1"},                # programmatic dependent launch for the conv kernels
     "sestrip": {"OCCDEPTH_SE_IMPL": "strip"},  # SE gate fold, one CTA per 32-channel strip
+    "uprows": {"OCCDEPTH_UPSAMPLE_IMPL": "rows"},  # bilinear resize, one block row per output row
     "epiwide": {"OCCD_EPI_WIDE": "1"},        # 256-bit epilogue loads/stores (per-tap kernel, aligned windows)
     "stages4": {"OCCD_TC_STAGES_MIN": "4"},   # >= 4 pipeline stages for one-item-per-tile convs (1x1 layers)
     "stages8": {"OCCD_TC_STAGES_MIN": "8"},
@@ -68,7 +69,7 @@ def run(name, env_extra, steps, dump):
 
 def main():
     import torch
-    names = sys.argv[1:] or list(SWITCHES) + ["halox+tcx+tcm2+pdl+sestrip+epiwide"]
+    names = sys.argv[1:] or list(SWITCHES) + ["halox+tcx+tcm2+pdl+sestrip+epiwide+uprows"]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     base_dump = "/tmp/ab_default.pt"
     base, err = run("default", {}, 10, base_dump)
