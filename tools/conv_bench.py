@@ -28,6 +28,9 @@ SHAPES = {
     "x_c64_n64": ((256, 256, 16), 64, 64, (3, 3, 3), 1, "relu"),
     "x_c64_n256": ((128, 128, 16), 64, 256, (3, 3, 3), 1, "relu"),
     "x_c16_n16": ((256, 256, 16), 16, 16, (3, 3, 3), 1, "relu"),
+    "b1_expand": ((1, 94, 686), 48, 288, (1, 1, 1), 1, "silu"),      # both views side by side (B = 2 in the net)
+    "bneck5_16_64": ((128, 128, 16), 16, 64, (1, 1, 1), 1, "relu"),
+    "up4_conv2": ((1, 94, 686), 320, 320, (1, 3, 3), 1, "leaky"),
     "l1_k1_64_16": ((128, 128, 16), 64, 16, (1, 1, 1), 1, "relu"),
     "l1_k113_16": ((128, 128, 16), 16, 16, (1, 1, 3), 1, "relu"),
 }
@@ -43,7 +46,7 @@ def main():
         w = torch.randn(co, ci, *k, device=dev) / (ci * k[0] * k[1] * k[2]) ** 0.5
         b = torch.randn(co, device=dev)
         pad = tuple(dl * (kk - 1) // 2 for kk in k)
-        impl = {"tc": 0, "simt": 1, "halo": 2}.get(os.environ.get("BENCH_IMPL", ""), None)
+        impl = {"tc": 0, "simt": 1, "halo": 2, "halox": 3, "tcx": 4, "tcm2": 5}.get(os.environ.get("BENCH_IMPL", ""), None)
         plan.conv(x, w, b, padding=pad, dilation=dl, act=act, name=n, impl=impl)
         for _ in range(3):
             plan.run()
