@@ -189,6 +189,46 @@ def run_b200(args):
         e1.record()
     barrier()
     ms_e2e = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    # ---- end-to-end, pipelined: the same per-step copies, but the D2H read of step i runs on a copy stream into
+    # double-buffered pinned host buffers while the forward of step i+1 runs (what a serving loop does).  No
+    # collective inside the try block: a rank that fails reports inf and every rank falls back to the sequential
+    # number above.
+    ms_pipe_local = float("inf")
+    pipe_err = None
+    if not slab:
+        try:
+            cs = torch.cuda.Stream(device=dev)
+            main = torch.cuda.current_stream(dev)
+            host_bufs = [logits_h, torch.empty(logits_h.shape, dtype=torch.float32).pin_memory()]
+
+            def pipe_step(i):
+                b = {"img": img_h.to(dev, non_blocking=True), "projected_pix_2": [pix_h], "fov_mask_2": [fov_h]}
+                res = m(b)["ssc_logit"]
+                cs.wait_stream(main)          # the forward (and its output copy) queued so far
+                res.record_stream(cs)
+                with torch.cuda.stream(cs):
+                    host_bufs[i & 1].copy_(res, non_blocking=True)
+
+            with torch.no_grad():
+                for i in range(3):
+                    pipe_step(i)
+                main.wait_stream(cs)
+                torch.cuda.synchronize()
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for i in range(args.steps):
+                    pipe_step(i)
+                main.wait_stream(cs)          # the last D2H read ends inside the timed region
+                p1.record()
+                torch.cuda.synchronize()
+            ms_pipe_local = p0.elapsed_time(p1)
+        except Exception as ex:  # noqa: BLE001
+            pipe_err = repr(ex)
+            torch.cuda.synchronize()
+    ms_pipe = parallel.max_over_ranks(ms_pipe_local, dev)
+    pipelined = ms_pipe != float("inf") and ms_pipe > 0
+    ms_e2e_best = min(ms_pipe, ms_e2e) if pipelined else ms_e2e
     # keep the GPU under the same load a little longer so that nvidia-smi (100 ms period) sees it, then stop
     with torch.no_grad():
         if slab:      # every rank must run the SAME number of forwards (each one is a set of NCCL exchanges)
@@ -247,8 +287,14 @@ def run_b200(args):
                        "partition": "x-slab of one frame + NCCL halo exchange" if slab else "frame replicas",
                        "l2": "per-step working set (weights + activations, >2 GB) exceeds the 126 MB L2; no flush",
                        "cuda_graph": os.environ.get("OCCDEPTH_CUDA_GRAPH", "1") == "1"},
-            "e2e": {"value": frames * N_OUT * args.steps / (ms_e2e * 1e-3), "unit": "voxels/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": frames * N_OUT * args.steps / (ms_e2e_best * 1e-3), "unit": "voxels/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_best / args.steps,
+                    "mode": ("pipelined: every step copies its inputs H2D and its logits D2H; the D2H read of step i "
+                             "(copy stream, double-buffered pinned host buffers) overlaps the forward of step i+1"
+                             if pipelined and ms_pipe <= ms_e2e else "sequential: H2D, forward, D2H back to back"),
+                    "sequential_ms_per_step": ms_e2e / args.steps,
+                    "pipelined_ms_per_step": ms_pipe / args.steps if pipelined else None,
+                    "pipelined_error": pipe_err},
             "gpu_launches": len(plan.ops) * args.steps,
             "clocks": sampler.summary(),
             "roofline": {"kernel": "conv_tc_kernel + conv_halo_kernel (tcgen05 implicit GEMM family, %d launches/step)" % sum(1 for n, t, f in prof if f > 0),
