@@ -84,3 +84,24 @@ def test_occdepth_config2_plan(simt, monkeypatch):
     assert tuple(out["ssc_logit"].shape) == (1, 20, 256, 256, 32)
     assert img.dims == (2, 1, bench.IMG_H, bench.IMG_W) and tuple(pix.shape) == (1, 2, N, 1, 2)
     assert len(plan.ops) < 500      # both views batched, SE + projection batched over images
+
+
+def test_variant_eligibility_rules():
+    """host-side selection rules of the opt-in conv variants (engine.py) on the shapes they were written for"""
+    from occdepth_b200 import engine as E
+    t333 = [(0, a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)]
+    t333_d2 = [(0, 2 * a, 2 * b, 2 * c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)]
+    t311 = [(0, a, 0, 0) for a in (-1, 0, 1)]
+    two_src = [(s, 0, b, c) for s in (0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)]
+    assert E.halox_eligible(t333, 32) and E.halox_eligible(t333_d2, 32)
+    assert not E.halox_eligible(t333, 96)                    # 3 * 96 > 256
+    assert not E.halox_eligible(t311, 32)                    # no W taps
+    assert E.tcx_eligible(t333, (1, 1, 1), 80) and E.tcx_eligible(two_src, (1, 1, 1), 80)
+    assert not E.tcx_eligible(t333_d2, (1, 1, 1), 32)        # W dilation 2: per-tap kernel has no sub-grids
+    assert not E.tcx_eligible(t333, (1, 1, 2), 32) and not E.tcx_eligible(t333, (1, 1, 1), 96)
+    # M2: wide layers with enough pairs to fill the GPU twice (up2 / up4 of the 1370x376 decoder), not the 24x86 stage
+    assert E.tcm2_eligible(2, (1, 188, 685), 160, 27, False)
+    assert E.tcm2_eligible(2, (1, 94, 343), 320, 45, False)
+    assert not E.tcm2_eligible(2, (1, 24, 86), 1280, 396, False)
+    assert not E.tcm2_eligible(2, (1, 188, 685), 160, 27, True)    # per-image weight sets
+    assert not E.tcm2_eligible(2, (1, 376, 1370), 80, 9, False)    # narrow: that is TCX territory
