@@ -1141,7 +1141,16 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, int mode) {
   int stages = budget / (group * stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   const int groups_per_tile = (total_iters + group - 1) / group;
-  if (stages > 2 * groups_per_tile) stages = 2 * groups_per_tile;
+  {
+    // Ring depth: two tiles' worth of stage groups, but never fewer than 8 stages when they fit -- a conv with one
+    // item per tile (1x1 layers, 16-channel bottleneck convs) otherwise keeps only two TMA loads in flight and runs
+    // at two tiles per load latency (~0.75 us per tile in the round-1 plan profile).  OCCD_TC_STAGES_LEGACY=1
+    // restores the old "2 x groups per tile" rule for A/B runs.
+    static const bool legacy = [] { const char* e = getenv("OCCD_TC_STAGES_LEGACY"); return e && atoi(e) == 1; }();
+    int cap = 2 * groups_per_tile;
+    if (!legacy && cap < 8) cap = 8;
+    if (stages > cap) stages = cap;
+  }
   {
     // experiment hook: OCCD_TC_STAGES_MIN=n keeps at least n stages (when they fit) so that the producer of a
     // one-item-per-tile conv (1x1 layers) can run more than two tiles ahead

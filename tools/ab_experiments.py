@@ -26,8 +26,8 @@ SWITCHES = {
     "sestrip": {"OCCDEPTH_SE_IMPL": "strip"},  # SE gate fold, one CTA per 32-channel strip
     "uprows": {"OCCDEPTH_UPSAMPLE_IMPL": "rows"},  # bilinear resize, one block row per output row
     "epiwide": {"OCCD_EPI_WIDE": "1"},        # 256-bit epilogue loads/stores (per-tap kernel, aligned windows)
-    "stages4": {"OCCD_TC_STAGES_MIN": "4"},   # >= 4 pipeline stages for one-item-per-tile convs (1x1 layers)
-    "stages8": {"OCCD_TC_STAGES_MIN": "8"},
+    "stageslegacy": {"OCCD_TC_STAGES_LEGACY": "1"},  # old ring depth rule (2 x groups per tile) for reference
+    "stages16": {"OCCD_TC_STAGES_MIN": "16"},
     "dwdirect": {"OCCDEPTH_DW_IMPL": "direct"},  # the old register-window depthwise kernel (for reference)
 }
 

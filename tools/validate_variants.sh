@@ -7,6 +7,6 @@ run() { name=$1; shift; echo "== $name"; ( "$@" ) > gpurun_out/variants_$name.tx
 run tests_experimental env OCCD_EXPERIMENTAL=1 timeout 420 python -m pytest tests/test_gpu_conv.py tests/test_gpu_ops.py -q -m gpu
 run tests_epiwide env OCCD_EPI_WIDE=1 timeout 240 python -m pytest tests/test_gpu_conv.py tests/test_gpu_unet3d.py -q -m gpu
 run tests_pdl env OCCD_PDL=1 timeout 240 python -m pytest tests/test_gpu_conv.py tests/test_gpu_unet3d.py tests/test_gpu_net2d.py -q -m gpu
-run tests_stages env OCCD_TC_STAGES_MIN=6 timeout 240 python -m pytest tests/test_gpu_conv.py -q -m gpu
+run tests_stages env OCCD_TC_STAGES_MIN=16 timeout 240 python -m pytest tests/test_gpu_conv.py -q -m gpu
 run ab timeout 900 python tools/ab_experiments.py "$@"
 cat gpurun_out/variants_ab.txt
