@@ -661,7 +661,9 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
       tc::mbar_wait(tfull_bar + 8u * set, use & 1u);
       tc::fence_after_sync();
       if (tracer && j < 64) p.trace[j * 8 + 5] = clock64();
-      for (int m = half; m < p.nM; m += 2) {
+      // one group per M tile; with a single M tile (x-packed plans) the two groups split its channels instead
+      const bool split_c = XP && p.nM == 1 && (p.CP & 31) == 0;
+      for (int m = split_c ? 0 : half; m < p.nM; m += split_c ? 1 : 2) {
         const int R = p.R0 + m * 128 + q * 32 + lane;
         const int pw = R % p.PW;
         const int phh = (R / p.PW) % p.PH;
@@ -674,7 +676,9 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
                                ((uint32_t)(q * 32) << 16);
         if constexpr (XP) {
           // lane == pw (PW == 32, R0 a multiple of 32): neighbours along W are the neighbouring lanes
-          for (int c0 = 0; c0 < p.CP; c0 += 16) {
+          const int cb = split_c ? half * (p.CP >> 1) : 0;
+          const int ce = split_c ? cb + (p.CP >> 1) : p.CP;
+          for (int c0 = cb; c0 < ce; c0 += 16) {
             float lo[16], v[16], hi[16];
             tc::tmem_ld16(taddr + (uint32_t)c0, lo);
             tc::tmem_ld16(taddr + (uint32_t)(p.CP + c0), v);
@@ -927,6 +931,9 @@ static int halo_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
   const int nW = xp ? (sW + 29) / 30 : (sW + 61) / 62;
   const int BW = xp ? 30 : (sW + nW - 1) / nW;
   long long best_cost = -1;
+  // x-packed tiles finish their MMAs in ~1.5 k cycles per M tile, about one TMA round trip: ask for a ring of at
+  // least 3 stages first (min_stages pass 3), and only if no tile shape allows that accept 2
+  for (int min_stages = xp ? 3 : 2; min_stages >= 2 && best_cost < 0; --min_stages)
   for (int BD = 1; BD <= (hal[0] ? 4 : 1); ++BD)
     for (int BH = 1; BH <= sH && BH <= 96; ++BH) {
       const int PD = BD + 2 * hal[0], PH = BH + 2 * hal[1], PW = BW + 2 * hal[2];
@@ -939,7 +946,7 @@ static int halo_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
       int rows_alloc = PD * PH * PW;
       if (R0 + nM * 128 + R0 > rows_alloc) rows_alloc = R0 + nM * 128 + R0;
       const int stage = round_up(rows_alloc * row_bytes, 1024);
-      if (2 * stage > smem_total) continue;
+      if (min_stages * stage > smem_total) continue;
       if (2 * BD * BH * BW < nM * 128) continue;  // < 50 % useful MMA rows: the per-tap kernel is the better choice
       const long long tiles = (long long)((sD + BD - 1) / BD) * ((sH + BH - 1) / BH) * nW;
       const long long cost = tiles * nM * 1000 + tiles;  // MMA work first, then tile count
