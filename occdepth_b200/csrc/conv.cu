@@ -1209,7 +1209,7 @@ static int tc_encode(const occd_conv_desc* d, occd_conv_plan* pl) {
     if (r != CUDA_SUCCESS) {
       char msg[160];
       snprintf(msg, sizeof(msg), "occd_conv_plan_create: cuTensorMapEncodeTiled(source %d) failed with %d", s, (int)r);
-        occd_set_last_error(msg);
+      occd_set_last_error(msg);
       return OCCD_ERR_CUDA;
     }
   }
@@ -1226,13 +1226,12 @@ static int tc_encode(const occd_conv_desc* d, occd_conv_plan* pl) {
     if (r != CUDA_SUCCESS) {
       char msg[160];
       snprintf(msg, sizeof(msg), "occd_conv_plan_create: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
-        occd_set_last_error(msg);
+      occd_set_last_error(msg);
       return OCCD_ERR_CUDA;
     }
   }
   return OCCD_OK;
 }
-
 
 extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** out) {
   OCCD_CHECK_ARG(d && out, "occd_conv_plan_create: null argument");
