@@ -105,3 +105,20 @@ def test_variant_eligibility_rules():
     assert not E.tcm2_eligible(2, (1, 24, 86), 1280, 396, False)
     assert not E.tcm2_eligible(2, (1, 188, 685), 160, 27, True)    # per-image weight sets
     assert not E.tcm2_eligible(2, (1, 376, 1370), 80, 9, False)    # narrow: that is TCX territory
+
+
+@pytest.mark.parametrize("flags", [{}, {"OCCDEPTH_HALOX": "1", "OCCDEPTH_TCX": "1", "OCCDEPTH_TCM2": "1"}])
+def test_auto_impl_selection_reaches_tensor_map_encode(monkeypatch, flags):
+    """'auto' mode (the GPU default) on the CPU: selection rules + plan geometry run; the first thing that needs a
+    driver is cuTensorMapEncodeTiled, and the product must say so instead of falling back to anything"""
+    from occdepth_b200.engine import CL, Plan
+    monkeypatch.delenv("OCCDEPTH_CONV_IMPL", raising=False)
+    for k, v in flags.items():
+        monkeypatch.setenv(k, v)
+    shapes = [((4, 8, 40), 32, 32, (3, 3, 3)), ((1, 40, 90), 160, 160, (1, 3, 3)), ((1, 20, 30), 48, 288, (1, 1, 1)),
+              ((1, 188, 685), 80, 80, (1, 3, 3))]
+    for dims, ci, co, k in shapes:
+        plan = Plan(torch.device("cpu"))
+        x = CL(torch.zeros(2, dims[0], dims[1], dims[2], (ci + 7) // 8 * 8, dtype=torch.bfloat16), ci)
+        with pytest.raises(RuntimeError, match="cuTensorMapEncodeTiled unavailable"):
+            plan.conv(x, torch.randn(co, ci, *k), torch.randn(co), padding=tuple(kk // 2 for kk in k))
