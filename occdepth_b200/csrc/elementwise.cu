@@ -54,7 +54,34 @@ __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ in, __nv_
       *reinterpret_cast<const uint4*>(in + pos * in_cs + in_off + v * 8);
 }
 
+// class map of the caller-side post-processing (scripts/generate_output.py:94-95: softmax -> argmax -> uint16):
+// softmax is monotonic, so the class is the FIRST index of the largest logit (np.argmax tie rule)
+__global__ void argmax_classes_kernel(const float* __restrict__ in, unsigned short* __restrict__ out, int C,
+                                      long long S, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long b = i / S, s = i - b * S;
+  const float* p = in + b * C * S + s;
+  float best = p[0];
+  int arg = 0;
+  for (int c = 1; c < C; ++c) {
+    const float v = p[(long long)c * S];
+    if (v > best) { best = v; arg = c; }
+  }
+  out[i] = (unsigned short)arg;
+}
+
 }  // namespace
+
+extern "C" int occd_argmax_classes(const float* in, void* out, long long B, int C, long long S, void* stream) {
+  OCCD_CHECK_ARG(in && out && B > 0 && C > 0 && C <= 65535 && S > 0, "occd_argmax_classes: args");
+  const long long total = B * S;
+  OCCD_CHECK_ARG((total + 255) / 256 <= 2147483647LL, "occd_argmax_classes: too many positions");
+  argmax_classes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      in, (unsigned short*)out, C, S, total);
+  OCCD_CHECK_LAUNCH();
+  return OCCD_OK;
+}
 
 extern "C" int occd_softmax_planar_to_cl(const float* in, void* out, long long B, int C, long long S, int cstride,
                                          int coff, void* stream) {

@@ -238,5 +238,27 @@ class OccDepth(_Base, B200Module):
             res["depth_pred"] = self.flosp_depth.depth_prob().clone()          # OccDepth.py:374-375
         return res
 
+    @staticmethod
+    def class_map(ssc_logit):
+        """uint16 class per voxel from the fp32 logits [B, C, X, Y, Z] on the GPU -- what the reference's callers
+        compute on the host after copying all logits back (`np.argmax(torch.softmax(pred["ssc_logit"], 1).cpu(),
+        1).astype(np.uint16)`, scripts/generate_output.py:94-97; eval.py does the same).  168 MB of logits shrink to
+        a 4 MB map before the device->host read."""
+        from .. import _lib
+        if not (ssc_logit.is_cuda and ssc_logit.dtype == torch.float32 and ssc_logit.dim() == 5):
+            raise RuntimeError("OccDepth.class_map: expected CUDA fp32 logits [B, C, X, Y, Z]")
+        x = ssc_logit.contiguous()
+        B, Cn = x.shape[:2]
+        S = x[0, 0].numel()
+        out = torch.empty((B,) + tuple(x.shape[2:]), dtype=torch.uint16, device=x.device)
+        _lib.check(_lib.lib().occd_argmax_classes(x.data_ptr(), out.data_ptr(), B, Cn, S, _lib.stream_ptr()),
+                   "occd_argmax_classes")
+        return out
+
+    def predict(self, batch):
+        """forward + class map: returns (y_pred uint16 [B, X, Y, Z], the forward's output dict)"""
+        res = self.forward(batch)
+        return self.class_map(res["ssc_logit"]), res
+
     def step(self, *a, **k):
         raise NotImplementedError("occdepth_b200 implements OccDepth.forward only (training is out of scope)")

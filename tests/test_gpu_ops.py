@@ -124,3 +124,23 @@ def test_softmax_planar_and_fc():
     assert L.occd_fc_fwd(inp.cuda().data_ptr(), w.cuda().data_ptr(), b.cuda().data_ptr(), o.data_ptr(), 4, 33, 20,
                          _lib.ACT_RELU, _lib.stream_ptr()) == 0
     assert float((o.cpu() - F.relu(F.linear(inp, w, b))).abs().max()) <= 1e-5
+
+
+def test_class_map_matches_host_postprocessing():
+    """OccDepth.class_map vs the reference callers' host-side post-processing (generate_output.py:94-97)"""
+    import numpy as np
+    from occdepth_b200.models.OccDepth import OccDepth
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(2, 20, 17, 9, 5, generator=g) * 3
+    logits[0, 7, 3, 2, 1] = logits[0, 4, 3, 2, 1] = 50.0             # an exact tie: the first index wins
+    want = np.argmax(torch.softmax(logits, dim=1).numpy(), axis=1).astype(np.uint16)
+    got = OccDepth.class_map(logits.cuda()).cpu().numpy()
+    assert got.dtype == np.uint16 and got.shape == want.shape
+    assert got[0, 3, 2, 1] == 4
+    # softmax may merge logits that differ by < 1 ulp of the sum; everywhere else the maps are identical
+    diff = got != want
+    assert diff.mean() < 1e-4
+    if diff.any():
+        p = torch.softmax(logits, dim=1).numpy()
+        b, x, y, z = np.nonzero(diff)
+        assert np.all(p[b, got[diff], x, y, z] == p[b, want[diff], x, y, z])
