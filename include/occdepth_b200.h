@@ -183,6 +183,19 @@ int occd_copy_channels(const void* in, void* out, long long positions, int C, in
                        int out_cstride, int out_coff, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
+/* Data pipeline: voxel-centre -> pixel indices on the device, bit for bit what     */
+/* occdepth/data/utils/helpers.py:94-169 `vox2pix` returns (vox2world fusion.py:201-217, rigid_transform */
+/* :518-522 in float64 with OpenBLAS' sequential-FMA dot order, cam2allpixs :236-343).                 */
+/* HOST pointers: cam_E 4x4 row-major (first 3 rows used), float64 or -- pose_is_f32 != 0 -- float32: */
+/* the reference multiplies in the pose's own precision; cam_k 3x3 float32 row-major (the reference's   */
+/* intr.astype(float32)), vox_origin 3 float32, pattern P x 2 int (dx, dy).                             */
+/* DEVICE pointers: pix int64 [N][P][2] (x, y), fov bool [N][P], pix_z [N] in the pose's precision or   */
+/* NULL; N = X*Y*Z voxels in C order.                                                                  */
+int occd_vox2pix_fwd(const void* cam_E, int pose_is_f32, const float* cam_k, const float* vox_origin,
+                     double voxel_size, int X, int Y, int Z, int img_W, int img_H, const int* pattern, int P,
+                     long long* pix, unsigned char* fov, void* pix_z, void* stream);
+
+/* -------------------------------------------------------------------------------------------- */
 /* EfficientNet / decoder bandwidth kernels (channels-last bf16, 2-D)                             */
 /* depthwise KxK (K = 3|5) conv + folded BN + activation; optionally accumulates the per-channel    */
 /* spatial SUM of the output into pool[B][C] (squeeze of geffnet SqueezeExcite) as 64-bit FIXED-    */

@@ -5,6 +5,8 @@ Nothing under `occdepth_b200/` may import this package; only `tests/`, `__graft_
 
 * `functional.py`  plain-PyTorch fp32 restatement (state_dict-driven, functional style) of every reference
                    function on the hot path, each citing the reference file:line it follows
+* `projection.py`  numpy restatement of the data pipeline's voxel -> pixel projection (`vox2pix`), pinned bit for bit
+                   against the reference's numba implementation
 * `effnet.py`      geffnet-shaped `tf_efficientnet_b*_ns` definition (the reference fetches it with
                    torch.hub at run time; un-vendored, see DESIGN.md "oracle")
 * `synth.py`       re-export of /synthetic.py: seeded synthetic inputs / weights / `vox2pix` restatement

@@ -69,6 +69,49 @@ def gen_occdepth(ref):
                os.path.join(OUT, "occdepth_small.pt"))
 
 
+def vox2pix_cases():
+    """(name, cam_E, cam_k, vox_origin, voxel_size, img_W, img_H, scene_size, pattern_id): a KITTI-like rig with a
+    slightly rotated pose (so every term of the pose matrix matters), an NYU-like one, and a camera INSIDE the volume
+    (voxels behind it and one column of centres in the camera plane: z <= 0, division by zero)"""
+    import math
+    import numpy as np
+
+    def rot(ax, a):
+        c, s = math.cos(a), math.sin(a)
+        R = np.eye(3)
+        i, j = [(1, 2), (0, 2), (0, 1)][ax]
+        R[i, i] = c; R[j, j] = c; R[i, j] = -s; R[j, i] = s
+        return R
+    base = np.array([[0, -1, 0], [0, 0, -1], [1, 0, 0.0]])
+    E1 = np.eye(4)
+    E1[:3, :3] = rot(0, 0.03) @ rot(1, -0.02) @ rot(2, 0.01) @ base
+    E1[:3, 3] = [0.011, -0.083, -0.271]
+    K1 = np.array([[707.0912, 0, 601.8873], [0, 707.0912, 183.1104], [0, 0, 1.0]])
+    E2 = np.eye(4)
+    E2[:3, :3] = rot(0, -0.4) @ rot(2, 0.7)
+    E2[:3, 3] = [0.3, -0.2, 1.1]
+    K2 = np.array([[518.8579, 0, 320.0], [0, 518.8579, 240.0], [0, 0, 1.0]])
+    E3 = np.eye(4)
+    E3[:3, :3] = base
+    E3[:3, 3] = [0.0, 0.0, -0.75]         # cam z = lidar x - 0.75: the centres at x = 0.75 lie exactly in the camera plane
+    return [("kitti_p0", E1, K1, np.array([0, -6.4, -2.0]), 0.4, 1220, 370, (12.8, 12.8, 3.2), 0),
+            ("kitti_p3", E1, K1, np.array([0, -6.4, -2.0]), 0.8, 1220, 370, (12.8, 12.8, 3.2), 3),
+            ("nyu_p8", E2.astype(np.float32), K2, np.array([-1.2, -1.0, 0.1]), 0.16, 640, 480, (2.4, 2.4, 1.44), 8),
+            ("plane_p1", E3, K1, np.array([0.0, -2.0, -1.0]), 0.5, 1220, 370, (4.0, 4.0, 2.0), 1)]
+
+
+def gen_vox2pix():
+    helpers = ref_import.data_helpers()
+    out = {}
+    for name, E, K, org, vs, W, H, scene, pid in vox2pix_cases():
+        pix, fov, z = helpers.vox2pix(E, K, org, vs, W, H, scene, pid)
+        out[name] = dict(cam_E=torch.from_numpy(E.copy()), cam_k=torch.from_numpy(K.copy()),
+                         vox_origin=torch.from_numpy(org.copy()), voxel_size=vs, img_W=W, img_H=H,
+                         scene_size=scene, pattern_id=pid, pix=torch.from_numpy(pix), fov=torch.from_numpy(fov),
+                         pix_z=torch.from_numpy(z))
+    torch.save(out, os.path.join(OUT, "vox2pix.pt"))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_import.modules()
@@ -76,6 +119,7 @@ def main():
     gen_sfa(ref)
     gen_unet3d(ref)
     gen_occdepth(ref)
+    gen_vox2pix()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

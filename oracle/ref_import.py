@@ -59,6 +59,17 @@ def modules():
     return ns
 
 
+def data_helpers():
+    """The reference's projection helpers (occdepth/data/utils/helpers.py, numba-compiled fusion.py); needs numba,
+    and the `skimage` shim for an import on the mesh-export path that the projection never touches."""
+    _install()
+    import warnings
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import occdepth.data.utils.helpers as helpers
+    return helpers
+
+
 @contextlib.contextmanager
 def quiet():
     with contextlib.redirect_stdout(io.StringIO()):

@@ -144,3 +144,18 @@ def test_class_map_matches_host_postprocessing():
         p = torch.softmax(logits, dim=1).numpy()
         b, x, y, z = np.nonzero(diff)
         assert np.all(p[b, got[diff], x, y, z] == p[b, want[diff], x, y, z])
+
+
+def test_vox2pix_device_matches_reference_outputs():
+    """occdepth_b200.data.vox2pix (occd_vox2pix_fwd) vs the committed outputs of the reference's numba vox2pix:
+    indices, FOV mask and depth bit for bit (tests/golden/vox2pix.pt, oracle/gen_golden.py)"""
+    import numpy as np
+    from occdepth_b200.data import vox2pix
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vox2pix.pt"))
+    for name, c in gold.items():
+        pix, fov, z = vox2pix(c["cam_E"].numpy(), c["cam_k"].numpy(), c["vox_origin"].numpy(), c["voxel_size"],
+                              c["img_W"], c["img_H"], c["scene_size"], c["pattern_id"])
+        assert pix.is_cuda and pix.dtype == torch.int64 and fov.dtype == torch.bool and z.dtype == c["pix_z"].dtype
+        assert torch.equal(pix.cpu(), c["pix"]), name
+        assert torch.equal(fov.cpu(), c["fov"]), name
+        assert np.array_equal(z.cpu().numpy(), c["pix_z"].numpy(), equal_nan=True), name

@@ -182,3 +182,16 @@ def test_occdepth_forward_nyu_virtual_view(ref):
     assert set(got.keys()) == set(want.keys())
     for k in want:
         _close(got[k], want[k], rtol=2e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("pattern_id", [0, 1, 3, 6, 8])
+def test_vox2pix_against_the_numba_reference(pattern_id):
+    """oracle/projection.py vs occdepth.data.utils.helpers.vox2pix itself (numba-compiled), bit for bit"""
+    import numpy as np
+    from oracle import gen_golden, projection
+    helpers = ref_import.data_helpers()
+    for name, E, K, org, vs, W, H, scene, _ in gen_golden.vox2pix_cases():
+        want = helpers.vox2pix(E, K, org, vs, W, H, scene, pattern_id)
+        got = projection.vox2pix(E, K, org, vs, W, H, scene, pattern_id)
+        for g, w in zip(got, want):
+            assert g.dtype == w.dtype and np.array_equal(g, w, equal_nan=(g.dtype.kind == "f")), name
