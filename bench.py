@@ -226,22 +226,43 @@ def run_b200(args):
         except Exception as ex:  # noqa: BLE001
             pipe_err = repr(ex)
             torch.cuda.synchronize()
-    # ---- end-to-end with the callers' post-processing on the GPU: the reference's scripts copy
-    # all logits back only to arg-max them on the host (generate_output.py:94-97); OccDepth.predict returns the
-    # uint16 class map, so the per-step D2H read is 4 MB instead of 168 MB.  Reported next to, not instead of, e2e.
+    # ---- end-to-end of the widened path: per step the host supplies the image and the
+    # calibration only -- the projection indices are generated on the device (occdepth_b200.data.vox2pix, the data
+    # pipeline's numba job) and the reference callers' softmax/argmax post-processing (generate_output.py:94-97) runs
+    # on the device too (OccDepth.predict), so the D2H read is the 4 MB uint16 class map instead of 168 MB of logits.
+    # Reported next to, not instead of, `e2e`.
     ms_cls_local = float("inf")
     cls_err = None
     d2h_cls = 0
     if not slab:
         try:
+            import numpy as np
+            import synthetic as synth
+            from occdepth_b200.data import vox2pix as vox2pix_dev
+            Kc, Tc = synth.kitti_calib(IMG_W, IMG_H)
+            scene_m = tuple(v * 0.2 for v in FULL)
+            origin = np.array([0.0, -scene_m[1] / 2.0, -2.0])
+
+            def indices_on_device():
+                pv, fv = [], []
+                for T in Tc:
+                    p, f, _ = vox2pix_dev(T, Kc, origin, 0.4, IMG_W, IMG_H, scene_m, 0, device=dev)
+                    pv.append(p)
+                    fv.append(f)
+                return torch.stack(pv), torch.stack(fv)
+
             with torch.no_grad():
+                p_dev, f_dev = indices_on_device()
+                if not (torch.equal(p_dev.cpu(), pix) and torch.equal(f_dev.cpu(), fov)):
+                    raise RuntimeError("device vox2pix differs from the host indices")
                 cls_h = None
                 for it in range(3 + args.steps):
                     if it == 3:
                         torch.cuda.synchronize()
                         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         c0.record()
-                    b = {"img": img_h.to(dev, non_blocking=True), "projected_pix_2": [pix_h], "fov_mask_2": [fov_h]}
+                    p_dev, f_dev = indices_on_device()
+                    b = {"img": img_h.to(dev, non_blocking=True), "projected_pix_2": [p_dev], "fov_mask_2": [f_dev]}
                     y, _ = m.predict(b)
                     if cls_h is None:
                         cls_h = torch.empty(y.shape, dtype=y.dtype).pin_memory()
@@ -324,10 +345,12 @@ def run_b200(args):
                     "pipelined_ms_per_step": ms_pipe / args.steps if pipelined else None,
                     "pipelined_error": pipe_err},
             "e2e_classes": ({"value": frames * N_OUT * args.steps / (ms_cls * 1e-3), "unit": "voxels/s",
-                             "ms_per_step": ms_cls / args.steps, "h2d_bytes_per_step": h2d,
+                             "ms_per_step": ms_cls / args.steps, "h2d_bytes_per_step": img_h.numel() * 4,
                              "d2h_bytes_per_step": d2h_cls,
-                             "what": "OccDepth.predict: forward + arg-max class map on the GPU, uint16 map read back "
-                                     "(the reference callers' post-processing, generate_output.py:94-97)"}
+                             "what": "image + calibration in, class map out: projection indices generated on the "
+                                     "device (occdepth_b200.data.vox2pix = helpers.py:94-169), forward, arg-max class "
+                                     "map on the device (OccDepth.predict = generate_output.py:94-97), uint16 map "
+                                     "read back"}
                             if ms_cls != float("inf") and ms_cls > 0 else {"error": cls_err}),
             "gpu_launches": len(plan.ops) * args.steps,
             "clocks": sampler.summary(),

@@ -43,10 +43,9 @@ def vox2pix(cam_E, cam_k, vox_origin, voxel_size, img_W, img_H, scene_size):
     vol_dim = np.ceil(np.asarray(scene_size, dtype=np.float64) / voxel_size).astype(int)
     xv, yv, zv = np.meshgrid(range(vol_dim[0]), range(vol_dim[1]), range(vol_dim[2]), indexing="ij")
     vox = np.stack([xv.reshape(-1), yv.reshape(-1), zv.reshape(-1)], 1).astype(np.float32)
-    # fusion.py:201-217 vox2world (float32 arithmetic)
+    # fusion.py:201-217 vox2world: float32 origin / coordinates, float64 scalar voxel size, stored as float32
     vo = vox_origin.astype(np.float32)
-    vs = np.float32(voxel_size)
-    pts = vo[None, :] + vs * vox + vs * np.float32(0.5)
+    pts = (vo[None, :].astype(np.float64) + voxel_size * vox.astype(np.float64) + voxel_size * 0.5).astype(np.float32)
     # fusion.py rigid_transform: [pts 1] @ E^T
     E = np.asarray(cam_E)
     pts_h = np.hstack([pts, np.ones((len(pts), 1), dtype=np.float32)])
