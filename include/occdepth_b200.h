@@ -176,8 +176,10 @@ int occd_cl_transpose(const void* in, void* out, int B, int P, int C, int cstrid
                       long long out_bstride, void* stream);
 /* class map of the callers' post-processing: uint16 out[b][s] = first index of the largest of the   */
 /* C planar fp32 logits in[b][c][s] (np.argmax(softmax(ssc_logit), 1).astype(uint16),               */
-/* scripts/generate_output.py:94-97; softmax is monotonic, so it is never evaluated)                */
-int occd_argmax_classes(const float* in, void* out, long long B, int C, long long S, void* stream);
+/* scripts/generate_output.py:94-97; softmax is monotonic, so it is never evaluated).  lut (HOST      */
+/* pointer, C ints, C <= 64) or NULL: out = uint16(lut[class]), the inv_map remap of                  */
+/* scripts/generate_kitti_submission.py:79 (data/semantic_kitti/io_data.py:99-113)                    */
+int occd_argmax_classes(const float* in, void* out, long long B, int C, long long S, const int* lut, void* stream);
 /* copy a channel window (C % 8 == 0) between channels-last buffers (torch.cat of CRP3D.py:90)    */
 int occd_copy_channels(const void* in, void* out, long long positions, int C, int in_cstride, int in_coff,
                        int out_cstride, int out_coff, void* stream);

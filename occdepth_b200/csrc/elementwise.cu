@@ -55,9 +55,16 @@ __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ in, __nv_
 }
 
 // class map of the caller-side post-processing (scripts/generate_output.py:94-95: softmax -> argmax -> uint16):
-// softmax is monotonic, so the class is the FIRST index of the largest logit (np.argmax tie rule)
+// softmax is monotonic, so the class is the FIRST index of the largest logit (np.argmax tie rule).  Optional
+// label remap inv_map[class] of the submission writer (scripts/generate_kitti_submission.py:79).
+constexpr int kMaxLut = 64;
+struct ClassLut {
+  int use;
+  unsigned short v[kMaxLut];
+};
+
 __global__ void argmax_classes_kernel(const float* __restrict__ in, unsigned short* __restrict__ out, int C,
-                                      long long S, long long total) {
+                                      long long S, long long total, const ClassLut lut) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long b = i / S, s = i - b * S;
@@ -68,17 +75,22 @@ __global__ void argmax_classes_kernel(const float* __restrict__ in, unsigned sho
     const float v = p[(long long)c * S];
     if (v > best) { best = v; arg = c; }
   }
-  out[i] = (unsigned short)arg;
+  out[i] = lut.use ? lut.v[arg] : (unsigned short)arg;
 }
 
 }  // namespace
 
-extern "C" int occd_argmax_classes(const float* in, void* out, long long B, int C, long long S, void* stream) {
+extern "C" int occd_argmax_classes(const float* in, void* out, long long B, int C, long long S, const int* lut,
+                                   void* stream) {
   OCCD_CHECK_ARG(in && out && B > 0 && C > 0 && C <= 65535 && S > 0, "occd_argmax_classes: args");
+  OCCD_CHECK_ARG(!lut || C <= kMaxLut, "occd_argmax_classes: a label remap supports at most 64 classes");
   const long long total = B * S;
   OCCD_CHECK_ARG((total + 255) / 256 <= 2147483647LL, "occd_argmax_classes: too many positions");
+  ClassLut l;
+  l.use = lut ? 1 : 0;
+  for (int c = 0; c < kMaxLut; ++c) l.v[c] = (lut && c < C) ? (unsigned short)lut[c] : 0;  // .astype(np.uint16)
   argmax_classes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      in, (unsigned short*)out, C, S, total);
+      in, (unsigned short*)out, C, S, total, l);
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }

@@ -239,11 +239,13 @@ class OccDepth(_Base, B200Module):
         return res
 
     @staticmethod
-    def class_map(ssc_logit):
+    def class_map(ssc_logit, inv_map=None):
         """uint16 class per voxel from the fp32 logits [B, C, X, Y, Z] on the GPU -- what the reference's callers
         compute on the host after copying all logits back (`np.argmax(torch.softmax(pred["ssc_logit"], 1).cpu(),
         1).astype(np.uint16)`, scripts/generate_output.py:94-97; eval.py does the same).  168 MB of logits shrink to
-        a 4 MB map before the device->host read."""
+        a 4 MB map before the device->host read.  `inv_map` (int array of C label ids, io_data.get_inv_map) applies the
+        submission writer's remap `inv_map[y_pred].astype(np.uint16)` (generate_kitti_submission.py:79) in the same
+        launch."""
         from .. import _lib
         if not (ssc_logit.is_cuda and ssc_logit.dtype == torch.float32 and ssc_logit.dim() == 5):
             raise RuntimeError("OccDepth.class_map: expected CUDA fp32 logits [B, C, X, Y, Z]")
@@ -251,14 +253,21 @@ class OccDepth(_Base, B200Module):
         B, Cn = x.shape[:2]
         S = x[0, 0].numel()
         out = torch.empty((B,) + tuple(x.shape[2:]), dtype=torch.uint16, device=x.device)
-        _lib.check(_lib.lib().occd_argmax_classes(x.data_ptr(), out.data_ptr(), B, Cn, S, _lib.stream_ptr()),
+        lut = None
+        if inv_map is not None:
+            import numpy as np
+            lut = np.ascontiguousarray(np.asarray(inv_map).astype(np.int32))
+            if lut.shape != (Cn,):
+                raise ValueError("OccDepth.class_map: inv_map must hold one label id per class")
+        _lib.check(_lib.lib().occd_argmax_classes(x.data_ptr(), out.data_ptr(), B, Cn, S,
+                                                  None if lut is None else lut.ctypes.data, _lib.stream_ptr()),
                    "occd_argmax_classes")
         return out
 
-    def predict(self, batch):
+    def predict(self, batch, inv_map=None):
         """forward + class map: returns (y_pred uint16 [B, X, Y, Z], the forward's output dict)"""
         res = self.forward(batch)
-        return self.class_map(res["ssc_logit"]), res
+        return self.class_map(res["ssc_logit"], inv_map), res
 
     def step(self, *a, **k):
         raise NotImplementedError("occdepth_b200 implements OccDepth.forward only (training is out of scope)")

@@ -26,6 +26,10 @@ def test_class_map_matches_host_postprocessing():
         p = torch.softmax(logits, dim=1).numpy()
         b, x, y, z = np.nonzero(diff)
         assert np.all(p[b, got[diff], x, y, z] == p[b, want[diff], x, y, z])
+    # the submission writer's label remap (generate_kitti_submission.py:79) in the same launch
+    inv_map = np.array([0, 10, 11, 15, 18, 20, 30, 31, 32, 40, 44, 48, 49, 50, 51, 70, 71, 72, 80, 81], dtype=np.int32)
+    sub = OccDepth.class_map(logits.cuda(), inv_map).cpu().numpy()
+    assert np.array_equal(sub, inv_map[got.reshape(-1)].astype(np.uint16).reshape(got.shape))
 
 
 def test_vox2pix_device_matches_reference_outputs():
