@@ -197,6 +197,12 @@ int occd_vox2pix_fwd(const void* cam_E, int pose_is_f32, const float* cam_k, con
                      double voxel_size, int X, int Y, int Z, int img_W, int img_H, const int* pattern, int P,
                      long long* pix, unsigned char* fov, void* pix_z, void* stream);
 
+/* uint8 RGB HWC image [H0][W0][3] (device) -> float32 CHW [3][H][W] of the top-left H x W crop:     */
+/* ((u8 / 255) - mean[c]) / std[c] in float32 = np.array(img, float32) / 255.0, crop, ToTensor,        */
+/* Normalize of the datasets (data/semantic_kitti/kitti_dataset.py:164-171,376-402); mean/std: HOST    */
+int occd_normalize_rgb_u8(const void* in, float* out, int H0, int W0, int H, int W, const float* mean,
+                          const float* stdv, void* stream);
+
 /* -------------------------------------------------------------------------------------------- */
 /* EfficientNet / decoder bandwidth kernels (channels-last bf16, 2-D)                             */
 /* depthwise KxK (K = 3|5) conv + folded BN + activation; optionally accumulates the per-channel    */

@@ -100,6 +100,7 @@ SYMBOLS = {
     "occd_conv_plan_info": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "occd_softmax_planar_to_cl": (C.c_int, [_vp, _vp, _ll, _i, _ll, _i, _i, _vp]),
     "occd_argmax_classes": (C.c_int, [_vp, _vp, _ll, _i, _ll, _vp, _vp]),
+    "occd_normalize_rgb_u8": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "occd_vox2pix_fwd": (C.c_int, [_vp, _i, _vp, _vp, C.c_double, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "occd_cl_transpose": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _vp]),
     "occd_copy_channels": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),

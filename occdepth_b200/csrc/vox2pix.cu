@@ -1,7 +1,9 @@
+// Data-pipeline kernels.
 // occd_vox2pix_fwd: the data pipeline's voxel -> pixel index generation on the device.
 // replaces occdepth/data/utils/helpers.py:94-169 (vox2pix) as called per view and per scale by the datasets
 // (data/semantic_kitti/kitti_dataset.py, data/NYU/nyu_dataset.py).
 #include "vox2pix.cuh"
+#include "normalize_rgb.cuh"
 #include "../../include/occdepth_b200.h"
 
 namespace {
@@ -38,4 +40,19 @@ extern "C" int occd_vox2pix_fwd(const void* cam_E, int pose_is_f32, const float*
                                   pix_z, st)
                      : run<double>(cam_E, cam_k, vox_origin, voxel_size, X, Y, Z, img_W, img_H, pattern, P, pix, fov,
                                    pix_z, st);
+}
+
+// occd_normalize_rgb_u8: uint8 HWC image -> cropped, normalised float32 CHW (the datasets' `normalize_rgb`,
+// data/semantic_kitti/kitti_dataset.py:164-171,376-402)
+extern "C" int occd_normalize_rgb_u8(const void* in, float* out, int H0, int W0, int H, int W, const float* mean,
+                                     const float* stdv, void* stream) {
+  OCCD_CHECK_ARG(in && out && mean && stdv, "occd_normalize_rgb_u8: null argument");
+  OCCD_CHECK_ARG(H > 0 && W > 0 && H <= H0 && W <= W0, "occd_normalize_rgb_u8: the crop must lie inside the image");
+  nrm::Args a;
+  a.in = (const unsigned char*)in; a.out = out; a.W0 = W0; a.H = H; a.W = W;
+  for (int c = 0; c < 3; ++c) { a.mean[c] = mean[c]; a.stdv[c] = stdv[c]; }
+  const long long total = (long long)H * W;
+  nrm::normalize_rgb_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, total);
+  OCCD_CHECK_LAUNCH();
+  return OCCD_OK;
 }

@@ -64,3 +64,30 @@ def vox2pix(cam_E, cam_k, vox_origin, voxel_size, img_W, img_H, scene_size, patt
                                          fov.data_ptr(), pix_z.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "occd_vox2pix_fwd")
     return pix, fov, pix_z
+
+
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)     # kitti_dataset.py:167-169
+
+
+def normalize_rgb(img_u8, img_H, img_W, mean=IMAGENET_MEAN, std=IMAGENET_STD, device=None):
+    """The datasets' image pre-processing on the GPU: uint8 RGB (H0, W0, 3) array / tensor (host or device) ->
+    float32 (3, img_H, img_W) CUDA tensor equal, bit for bit, to
+    `normalize_rgb((np.array(img, np.float32) / 255.0)[:img_H, :img_W])` of kitti_dataset.py:376-402
+    (ToTensor + Normalize).  The host->device copy is the uint8 image (4x smaller than the float tensor)."""
+    dev = torch.device("cuda" if device is None else device)
+    if dev.type != "cuda" or not torch.cuda.is_available():
+        raise RuntimeError("occdepth_b200.data.normalize_rgb runs on CUDA (sm_100a) only -- there is no CPU fallback")
+    t = torch.as_tensor(np.asarray(img_u8) if not isinstance(img_u8, torch.Tensor) else img_u8)
+    if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
+        raise ValueError("normalize_rgb: expected a uint8 (H, W, 3) RGB image")
+    t = t.contiguous().to(dev, non_blocking=True)
+    H0, W0 = int(t.shape[0]), int(t.shape[1])
+    m32 = np.ascontiguousarray(np.asarray(mean, dtype=np.float32))
+    s32 = np.ascontiguousarray(np.asarray(std, dtype=np.float32))
+    with torch.cuda.device(dev):
+        out = torch.empty(3, int(img_H), int(img_W), dtype=torch.float32, device=dev)
+        rc = _lib.lib().occd_normalize_rgb_u8(t.data_ptr(), out.data_ptr(), H0, W0, int(img_H), int(img_W),
+                                              m32.ctypes.data_as(C.c_void_p), s32.ctypes.data_as(C.c_void_p),
+                                              _lib.stream_ptr())
+        _lib.check(rc, "occd_normalize_rgb_u8")
+    return out

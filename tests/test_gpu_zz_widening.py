@@ -45,3 +45,19 @@ def test_vox2pix_device_matches_reference_outputs():
         assert torch.equal(pix.cpu(), c["pix"]), name
         assert torch.equal(fov.cpu(), c["fov"]), name
         assert np.array_equal(z.cpu().numpy(), c["pix_z"].numpy(), equal_nan=True), name
+
+
+def test_normalize_rgb_device_matches_torchvision():
+    """occdepth_b200.data.normalize_rgb vs the datasets' ToTensor + Normalize (kitti_dataset.py:164-171,376-402)"""
+    import numpy as np
+    from torchvision import transforms
+    from occdepth_b200.data import IMAGENET_MEAN, IMAGENET_STD, normalize_rgb
+    g = np.random.default_rng(1)
+    img = g.integers(0, 256, size=(40, 61, 3), dtype=np.uint8)
+    img[0, :256 % 61] = 0
+    H, W = 37, 50
+    ref = transforms.Compose([transforms.ToTensor(), transforms.Normalize(mean=list(IMAGENET_MEAN), std=list(IMAGENET_STD))])(
+        (np.array(img, dtype=np.float32) / 255.0)[:H, :W, :])
+    got = normalize_rgb(img, H, W)
+    assert got.is_cuda and got.dtype == torch.float32 and tuple(got.shape) == (3, H, W)
+    assert torch.equal(got.cpu(), ref)
