@@ -5,7 +5,8 @@ ssc_logit with the default configuration's (relative error + arg-max agreement).
     python tools/ab_experiments.py                  # every single switch + all together
     python tools/ab_experiments.py halox tcx+halox  # chosen combinations
 
-Prints one line per configuration and writes gpurun_out/ab_experiments.json.
+Prints one line per configuration and writes gpurun_out/ab_experiments.json.  AB_PROFILE=1 adds a per-op-group
+CUDA-event profile (Plan.profile) of every configuration to the JSON.
 
 Kernel-level parity of the variants first (each in its own process, the C-side switches are read once):
     OCCD_EXPERIMENTAL=1 python -m pytest tests/test_gpu_conv.py tests/test_gpu_ops.py -q -m gpu
@@ -52,14 +53,22 @@ with torch.no_grad():
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / %(steps)d
 torch.save(out["ssc_logit"].float().cpu(), %(dump)r)
-print("AB_RESULT " + json.dumps({"ms": ms}))
+groups = {}
+if %(profile)d:
+    import re
+    plan = list(m._plans().values())[0][0]
+    plan.profile()
+    for n, t, f in plan.profile():
+        k = re.sub(r"\d+", "#", n)
+        groups[k] = round(groups.get(k, 0.0) + t, 4)
+print("AB_RESULT " + json.dumps({"ms": ms, "profile_ms": groups}))
 """
 
 
 def run(name, env_extra, steps, dump):
     env = dict(os.environ)
     env.update(env_extra)
-    code = WORKER % {"root": ROOT, "steps": steps, "dump": dump}
+    code = WORKER % {"root": ROOT, "steps": steps, "dump": dump, "profile": 1 if os.environ.get("AB_PROFILE") == "1" else 0}
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     for line in r.stdout.splitlines():
         if line.startswith("AB_RESULT "):
