@@ -238,8 +238,12 @@ def run_b200(args):
         try:
             import numpy as np
             import synthetic as synth
-            from occdepth_b200.data import vox2pix as vox2pix_dev
+            from occdepth_b200.data import normalize_rgb as normalize_rgb_dev, vox2pix as vox2pix_dev
             Kc, Tc = synth.kitti_calib(IMG_W, IMG_H)
+            # camera frames are uint8: the image crosses PCIe as uint8 and is normalised on the device
+            # (occdepth_b200.data.normalize_rgb = the datasets' /255 + ToTensor + Normalize)
+            u8_h = torch.randint(0, 256, (2, IMG_H, IMG_W, 3), dtype=torch.uint8,
+                                 generator=torch.Generator().manual_seed(7)).pin_memory()
             scene_m = tuple(v * 0.2 for v in FULL)
             origin = np.array([0.0, -scene_m[1] / 2.0, -2.0])
 
@@ -262,7 +266,9 @@ def run_b200(args):
                         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         c0.record()
                     p_dev, f_dev = indices_on_device()
-                    b = {"img": img_h.to(dev, non_blocking=True), "projected_pix_2": [p_dev], "fov_mask_2": [f_dev]}
+                    u8_d = u8_h.to(dev, non_blocking=True)
+                    img_d = torch.stack([normalize_rgb_dev(u8_d[v], IMG_H, IMG_W, device=dev) for v in range(2)])[None]
+                    b = {"img": img_d, "projected_pix_2": [p_dev], "fov_mask_2": [f_dev]}
                     y, _ = m.predict(b)
                     if cls_h is None:
                         cls_h = torch.empty(y.shape, dtype=y.dtype).pin_memory()
@@ -345,10 +351,11 @@ def run_b200(args):
                     "pipelined_ms_per_step": ms_pipe / args.steps if pipelined else None,
                     "pipelined_error": pipe_err},
             "e2e_classes": ({"value": frames * N_OUT * args.steps / (ms_cls * 1e-3), "unit": "voxels/s",
-                             "ms_per_step": ms_cls / args.steps, "h2d_bytes_per_step": img_h.numel() * 4,
+                             "ms_per_step": ms_cls / args.steps, "h2d_bytes_per_step": 2 * IMG_H * IMG_W * 3,
                              "d2h_bytes_per_step": d2h_cls,
-                             "what": "image + calibration in, class map out: projection indices generated on the "
-                                     "device (occdepth_b200.data.vox2pix = helpers.py:94-169), forward, arg-max class "
+                             "what": "uint8 stereo frame + calibration in, class map out: normalisation on the device "
+                                     "(occdepth_b200.data.normalize_rgb = kitti_dataset.py:376-402), projection indices "
+                                     "generated on the device (occdepth_b200.data.vox2pix = helpers.py:94-169), forward, arg-max class "
                                      "map on the device (OccDepth.predict = generate_output.py:94-97), uint16 map "
                                      "read back"}
                             if ms_cls != float("inf") and ms_cls > 0 else {"error": cls_err}),
