@@ -122,3 +122,21 @@ def test_auto_impl_selection_reaches_tensor_map_encode(monkeypatch, flags):
         x = CL(torch.zeros(2, dims[0], dims[1], dims[2], (ci + 7) // 8 * 8, dtype=torch.bfloat16), ci)
         with pytest.raises(RuntimeError, match="cuTensorMapEncodeTiled unavailable"):
             plan.conv(x, torch.randn(co, ci, *k), torch.randn(co), padding=tuple(kk // 2 for kk in k))
+
+
+def test_widened_rows_fail_loudly_without_cuda():
+    """no CPU fallback anywhere: the data-pipeline and post-processing entry points refuse to run without a GPU"""
+    import numpy as np
+    from occdepth_b200 import data
+    from occdepth_b200.models.OccDepth import OccDepth
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        data.vox2pix(np.eye(4), np.eye(3), np.zeros(3), 0.4, 64, 48, (3.2, 3.2, 1.6), 0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        data.normalize_rgb(np.zeros((4, 4, 3), dtype=np.uint8), 4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        OccDepth.class_map(torch.zeros(1, 20, 2, 2, 2))
+    # host-side helpers shared with the tests are plain numpy
+    assert tuple(data.volume_dims(np.array([0, -25.6, -2.0]), 0.4, (51.2, 51.2, 6.4))) == (128, 128, 16)
+    assert [len(p) for p in data.PIXEL_PATTERNS] == [1, 5, 5, 9, 9, 13, 25, 8, 21]
