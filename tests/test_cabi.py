@@ -43,3 +43,38 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, os.path.join(dp, f)
+
+
+def _prototypes():
+    """name -> list of parameter C types, parsed from include/occdepth_b200.h (comments stripped)"""
+    src = open(os.path.join(ROOT, "include", "occdepth_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char\s*\*)\s*(occd_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        params = " ".join(m.group(2).split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        protos[m.group(1)] = plist
+    return protos
+
+
+def _ctype_class(p):
+    """coarse class of a C parameter declaration"""
+    if "*" in p:
+        return "ptr"
+    base = " ".join(p.split()[:-1])       # drop the parameter name
+    return {"int": "int", "long long": "ll", "float": "float", "double": "double"}.get(base.replace("const ", ""), base)
+
+
+def test_ctypes_bindings_match_the_header_prototypes():
+    """arity and parameter classes of every ctypes binding (occdepth_b200/_lib.py SYMBOLS) against the header: a
+    drifted binding would silently shift arguments on the way into the library"""
+    protos = _prototypes()
+    assert set(protos) == set(_declared())
+    cls = {C.c_void_p: "ptr", C.c_int: "int", C.c_longlong: "ll", C.c_float: "float", C.c_double: "double"}
+    for name, params in protos.items():
+        _, argtypes = _lib.SYMBOLS[name]
+        assert len(argtypes) == len(params), (name, len(argtypes), params)
+        for a, p in zip(argtypes, params):
+            want = _ctype_class(p)
+            got = cls.get(a, "ptr")            # POINTER(struct) / POINTER(c_int) / c_char_p are pointers
+            assert got == want, (name, p, a)
