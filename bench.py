@@ -7,6 +7,10 @@
 Workload (BASELINE.json configs[1]): synthetic 1370x376 stereo pair, tf_efficientnet_b7_ns 2D backbone,
 Stereo-SFA lift to 128x128x16 / 64 ch, 3D UNet + CRP + cascade head -> 256x256x32 voxel logits (20 classes).
 A step = one OccDepth.forward over one frame per GPU (frames are independent: replicas, weak scaling).
+
+The headline (`value`, `e2e`, `roofline`) is measured in the reference-precision mode: TF32 tensor-core operands,
+fp32 accumulation, fp32 activations holding TF32 values (`dtype: "tf32"`) -- the arithmetic PyTorch itself uses for the
+reference's fp32 nn.Conv*d on CUDA.  The bf16 mode is reported beside it as `throughput_mode` with its own tolerance.
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -26,6 +30,9 @@ N_OUT = FULL[0] * FULL[1] * FULL[2]
 PROJECT_RES = ["1", "2", "4", "8"]
 WORKLOAD = ("configs[1]: 1370x376 stereo, tf_efficientnet_b7_ns, flosp lift to 128x128x16/64ch, "
             "UNet3D+CRP+cascade head -> 256x256x32x20 logits, B=1 per GPU")
+# stated parity of the two arithmetic modes vs the CPU fp32 oracle at this configuration (tests/test_gpu_config2.py,
+# profiles/r02_config2_parity_*.json): max-abs logit diff relative to max |logit|, arg-max agreement
+TOLERANCE = {"tf32": {"rel": 1.5e-3, "argmax": 0.998}, "bf16": {"rel": 1.4e-2, "argmax": 0.985}}
 
 
 def make_cfg():
@@ -87,18 +94,25 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def cpu_forward_seconds(steps=1, warmup=0, threads=None):
-    """the reference algorithm (oracle/functional.py, pinned against /root/reference) on the host cores"""
-    import torch
-    from oracle import functional as OF      # the ONLY leg of bench.py that executes oracle/ code
-    if threads:
-        torch.set_num_threads(threads)
+def oracle_inputs(device=None):
+    """state dict + batch + cfg of the workload for oracle/functional.py (the reference algorithm)"""
     m = build_model()
-    sd = {k: v for k, v in m.state_dict().items()}
+    sd = {k: (v if device is None else v.to(device)) for k, v in m.state_dict().items()}
     img, pix, fov = make_inputs()
-    batch = {"img": img, "projected_pix_2": [pix], "fov_mask_2": [fov]}
+    if device is not None:
+        img, pix, fov = img.to(device), pix.to(device), fov.to(device)
     cfg = dict(make_cfg())
     cfg["project_res"] = PROJECT_RES
+    return sd, {"img": img, "projected_pix_2": [pix], "fov_mask_2": [fov]}, cfg
+
+
+def cpu_forward_seconds(steps=1, warmup=0):
+    """the reference algorithm (oracle/functional.py, pinned against /root/reference) on ALL host cores.
+    torchrun exports OMP_NUM_THREADS=1: the thread count is set explicitly."""
+    import torch
+    from oracle import functional as OF      # bench.py executes oracle/ code only in the baseline legs
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd, batch, cfg = oracle_inputs()
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
@@ -129,6 +143,92 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def eager_cuda_baseline(dev, steps=3):
+    """The honest GPU competitor: the reference algorithm (oracle/functional.py = the same ATen / cuDNN /
+    cuBLAS library calls the reference's modules make, caller loop scripts/generate_output.py:88-93) under eager CUDA
+    on this GPU, TF32 allowed (PyTorch's conv default) and not allowed.  Outside every timed region of the repo's arm."""
+    import torch
+    from oracle import functional as OF
+    res = {}
+    sd, batch, cfg = oracle_inputs(dev)
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        for name, tf32 in (("tf32_allowed", True), ("fp32_only", False)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cudnn.benchmark = True
+            with torch.no_grad():
+                for _ in range(2):
+                    OF.occdepth_forward(sd, batch, cfg)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    OF.occdepth_forward(sd, batch, cfg)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            res[name] = {"ms_per_step": ms, "value": N_OUT / (ms * 1e-3), "unit": "voxels/s"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = old
+        del sd, batch
+        torch.cuda.empty_cache()
+    res["what"] = ("reference algorithm (oracle/functional.py: ATen/cuDNN/cuBLAS eager, fp32 NCHW tensors, device-resident "
+                   "inputs, cudnn.benchmark on), %d forwards after 2 warm-ups, CUDA events" % steps)
+    return res
+
+
+def tf32_matmul_peak(dev, seconds=2.0):
+    """TF32 tensor-core roofline denominator, measured the way MEASURED_PEAKS.json measures bf16 (the driver file has
+    no TF32 entry): torch.matmul fp32 with allow_tf32, 8192^3, best of 10 (burst) and back to back (sustained)."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_end, iters = time.time() + seconds, 0
+        e0.record()
+        while time.time() < t_end:
+            for _ in range(10):
+                a @ b
+            iters += 10
+            torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        return {"burst": best, "sustained": iters * 2 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def time_forwards(m, batch, steps, barrier, dev):
+    """K forwards bracketed by barrier + synchronize, CUDA events, max over ranks -> ms for all K steps"""
+    import torch
+    from occdepth_b200 import parallel
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    with torch.no_grad():
+        for _ in range(steps):
+            out = m(batch)
+    e1.record()
+    barrier()
+    return parallel.max_over_ranks(e0.elapsed_time(e1), dev), out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -137,17 +237,17 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     parallel.init("nccl", dev)
-    m = build_model().to(dev)
-    slab = args.partition == "slab" and world > 1
-    img, pix, fov = make_inputs(seed=0 if slab else rank)
-    if slab:
-        # BASELINE.json configs[2]: ONE frame, voxel grid split along X over the ranks, NCCL halo exchange at the
-        # 3-D conv boundaries (strong scaling); the default is one independent frame per rank (weak scaling)
+    prec = args.precision
+    m = build_model().to(dev).set_precision(prec)
+    slab_only = args.partition == "slab" and world > 1      # legacy switch: slab mode as the headline
+    img, pix, fov = make_inputs(seed=0 if slab_only else rank)
+    if slab_only:
         m.enable_slab_parallel(parallel.SlabContext(halo=3))
+    warm = max(args.warmup, 3)
     # ---- device-resident arm ----
     batch_dev = {"img": img.to(dev), "projected_pix_2": [pix.to(dev)], "fov_mask_2": [fov.to(dev)]}
     with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(warm):
             out = m(batch_dev)
     torch.cuda.synchronize()
 
@@ -158,15 +258,7 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    with torch.no_grad():
-        for _ in range(args.steps):
-            out = m(batch_dev)
-    e1.record()
-    barrier()
-    ms_total = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms_total, out = time_forwards(m, batch_dev, args.steps, barrier, dev)
 
     # ---- end-to-end arm: host buffers, H2D of the inputs and D2H of the logits inside the timed region ----
     img_h, pix_h, fov_h = img.pin_memory(), pix.pin_memory(), fov.pin_memory()
@@ -179,6 +271,7 @@ def run_b200(args):
         o = m(b)
         logits_h.copy_(o["ssc_logit"], non_blocking=True)
 
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.no_grad():
         for _ in range(3):
             e2e_step()
@@ -196,7 +289,7 @@ def run_b200(args):
     # number above.
     ms_pipe_local = float("inf")
     pipe_err = None
-    if not slab:
+    if not slab_only:
         try:
             cs = torch.cuda.Stream(device=dev)
             main = torch.cuda.current_stream(dev)
@@ -234,7 +327,7 @@ def run_b200(args):
     ms_cls_local = float("inf")
     cls_err = None
     d2h_cls = 0
-    if not slab:
+    if not slab_only:
         try:
             import numpy as np
             import synthetic as synth
@@ -286,7 +379,7 @@ def run_b200(args):
     ms_e2e_best = min(ms_pipe, ms_e2e) if pipelined else ms_e2e
     # keep the GPU under the same load a little longer so that nvidia-smi (100 ms period) sees it, then stop
     with torch.no_grad():
-        if slab:      # every rank must run the SAME number of forwards (each one is a set of NCCL exchanges)
+        if slab_only:      # every rank must run the SAME number of forwards (each one is a set of NCCL exchanges)
             for _ in range(40):
                 m(batch_dev)
         else:
@@ -296,12 +389,41 @@ def run_b200(args):
         torch.cuda.synchronize()
     sampler.stop_flag = True
 
+    # ---- per-kernel profile pass (rank 0, outside the timed regions): shares + roofline of the dominant kernel ----
+    prof, n_ops = [], 0
+    if rank == 0 and not slab_only:
+        plan = list(m._plans().values())[0][0]
+        n_ops = len(plan.ops)
+        prof = (plan.profile(), plan.profile())[1]
+    elif rank == 0:
+        n_ops = len(list(m._plans().values())[0][0].ops)
+    ref_logits = out["ssc_logit"].clone() if not slab_only else None
+
+    # ---- throughput mode (bf16 operands and activations): same workload, device-resident, all ranks ----
+    other = {}
+    if not slab_only and not args.no_modes:
+        alt = "bf16" if prec == "tf32" else "tf32"
+        m.set_precision(alt)
+        with torch.no_grad():
+            for _ in range(3):
+                o2 = m(batch_dev)
+        torch.cuda.synchronize()
+        ms_alt, o2 = time_forwards(m, batch_dev, args.steps, barrier, dev)
+        a, b_ = o2["ssc_logit"], ref_logits
+        other = {"dtype": alt, "ms_per_step": ms_alt / args.steps,
+                 "value": world * N_OUT * args.steps / (ms_alt * 1e-3), "unit": "voxels/s",
+                 "rel_diff_vs_headline_mode": float((a - b_).abs().max() / b_.abs().max()),
+                 "argmax_agreement_vs_headline_mode": float((a.argmax(1) == b_.argmax(1)).float().mean()),
+                 "stated_tolerance_vs_fp32_oracle": TOLERANCE[alt]}
+        m.set_precision(prec)
+
+    # ---- X-slab partition of ONE frame over all ranks (BASELINE.json configs[2]; strong scaling) ----
+    slab = None
+    if world > 1 and not slab_only and not args.no_slab:
+        slab = run_slab_block(m, dev, world, rank, args, barrier)
+
     line = None
     if rank == 0:
-        plan = list(m._plans().values())[0][0]
-        # per-kernel profile pass (outside the timed regions): shares + roofline of the dominant kernel
-        # (not in slab mode: the plan contains NCCL ops that every rank would have to enter together)
-        prof = [] if slab else (plan.profile(), plan.profile())[1]
         conv_ms = sum(t for n, t, f in prof if f > 0)
         conv_fl = sum(f for n, t, f in prof if f > 0)
         lift_ms = sum(t for n, t, f in prof if n == "sfa_lift")
@@ -311,35 +433,48 @@ def run_b200(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:  # noqa: BLE001
             pass
-        tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
-        hpeak = peaks.get("hbm_gbs", 6650.0)
         src = "measured" if peaks else "fallback"
-        # lift algorithmic bytes (SURVEY 8d formula with the element sizes actually used: bf16 features / output)
+        hpeak = peaks.get("hbm_gbs", 6650.0)
+        if prec == "tf32":
+            tp = tf32_matmul_peak(dev)
+            tpeak = tp["sustained"]
+            tsrc = ("measured in this run (torch.matmul fp32, allow_tf32, 8192^3: sustained %.0f / burst %.0f TFLOP/s; "
+                    "MEASURED_PEAKS.json has no TF32 entry, its bf16 sustained figure is %.0f)"
+                    % (tp["sustained"], tp["burst"], peaks.get("bf16_tflops_sustained", float("nan"))))
+        else:
+            tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
+            tsrc = src + " bf16_tflops_sustained"
+        esize = 4 if prec == "tf32" else 2
+        # lift algorithmic bytes (SURVEY 8d formula with the element size actually moved)
+        import synthetic as synth
         U = 0
         for s in (1, 2, 4, 8):
-            import synthetic as synth
             h, w = synth.feature_hw(IMG_H, IMG_W, s)
             for v in range(2):
                 idx = (pix[v, :, 0, 1] // s) * w + (pix[v, :, 0, 0] // s)
                 U += int(torch.unique(idx[fov[v, :, 0]]).numel())
         N1 = pix.shape[1]
-        lift_bytes = U * 64 * 2 + 2 * N1 * 17 + N1 * 64 * 2
+        lift_bytes = U * 64 * esize + 2 * N1 * 17 + N1 * 64 * esize
         ach_t = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         ach_h = lift_bytes / (lift_ms * 1e-3) / 1e9 if lift_ms > 0 else 0.0
-        frames = 1 if slab else world
+        frames = 1 if slab_only else world
         value = frames * N_OUT * args.steps / (ms_total * 1e-3)
-        cpu = None
-        if world == 1 and not args.no_cpu:
-            times, cores = cpu_forward_seconds(1, 0)
-            cpu = {"value": N_OUT / times[0], "unit": "voxels/s", "cores": cores, "kind": "port",
-                   "sample": "1 full forward of the workload (oracle/functional.py, PyTorch CPU fp32), %.1f s" % times[0]}
+        ncu = {}
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(prec, {})
+        except Exception:  # noqa: BLE001
+            pass
         line = {
             "metric": "forward voxels/sec", "value": value, "unit": "voxels/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "strong" if slab else "weak", "vs_baseline": None, "dtype": "bf16",
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "strong" if slab_only else "weak", "vs_baseline": None, "dtype": prec,
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step": frames,
-                       "partition": "x-slab of one frame + NCCL halo exchange" if slab else "frame replicas",
+                       "partition": "x-slab of one frame + NCCL halo exchange" if slab_only else "frame replicas",
+                       "precision": {"mode": prec, "operands": "TF32 (tcgen05 kind::tf32)" if prec == "tf32" else "bf16 (tcgen05 kind::f16)",
+                                     "accumulate": "fp32 (TMEM)", "activations": "fp32 holding TF32 values" if prec == "tf32" else "bf16",
+                                     "stated_tolerance_vs_fp32_oracle": TOLERANCE[prec],
+                                     "backbone_parity": "EfficientNet oracle pinned vs torchvision, unpinned vs geffnet (un-vendored)"},
                        "l2": "per-step working set (weights + activations, >2 GB) exceeds the 126 MB L2; no flush",
                        "cuda_graph": os.environ.get("OCCDEPTH_CUDA_GRAPH", "1") == "1"},
             "e2e": {"value": frames * N_OUT * args.steps / (ms_e2e_best * 1e-3), "unit": "voxels/s",
@@ -359,27 +494,39 @@ def run_b200(args):
                                      "map on the device (OccDepth.predict = generate_output.py:94-97), uint16 map "
                                      "read back"}
                             if ms_cls != float("inf") and ms_cls > 0 else {"error": cls_err}),
-            "gpu_launches": len(plan.ops) * args.steps,
+            "gpu_launches": n_ops * args.steps,
             "clocks": sampler.summary(),
             "roofline": {"kernel": "conv_tc_kernel + conv_halo_kernel (tcgen05 implicit GEMM family, %d launches/step)" % sum(1 for n, t, f in prof if f > 0),
                          "bound": "tensor", "achieved": ach_t, "peak": tpeak, "unit": "TFLOP/s",
-                         "frac": ach_t / tpeak if prof else None, "traffic": None, "peak_source": src + " bf16_tflops_sustained",
+                         "frac": ach_t / tpeak if prof else None, "traffic": ncu.get("conv_family_dram_bytes"),
+                         "peak_source": tsrc,
                          "note": "achieved = sum of algorithmic FLOPs (2*MACs of the reference convs) / sum of the family's "
-                                 "launch durations (CUDA events, back-to-back); per-shape ncu traffic: profiles/r01_ncu_summary.md",
+                                 "launch durations (CUDA events, back-to-back); traffic = sum over the family of ncu "
+                                 "dram__bytes_read+write per launch (profiles/ncu_traffic.json)",
                          "share_of_step": conv_ms / tot_ms if tot_ms else None,
                          "algorithmic_flops_per_step": conv_fl},
-            "roofline_lift": {"kernel": "sfa_lift_kernel", "bound": "hbm", "achieved": ach_h, "peak": hpeak,
-                              "unit": "GB/s", "frac": ach_h / hpeak, "traffic": 76079360,   # ncu r01b_lift: dram read+write
+            "roofline_lift": {"kernel": "sfa_lift_p1_kernel", "bound": "hbm", "achieved": ach_h, "peak": hpeak,
+                              "unit": "GB/s", "frac": ach_h / hpeak, "traffic": ncu.get("lift_dram_bytes"),
                               "peak_source": src + " hbm_gbs",
                               "algorithmic_bytes": lift_bytes, "ms": lift_ms,
                               "share_of_step": lift_ms / tot_ms if tot_ms else None},
             "profile_ms": {"convs": conv_ms, "lift": lift_ms, "other": tot_ms - conv_ms - lift_ms, "sum": tot_ms},
         }
-        if cpu:
-            line["cpu_baseline"] = cpu
+        if other:
+            line["throughput_mode" if other["dtype"] == "bf16" else "reference_precision_mode"] = other
+        if slab is not None:
+            line["slab"] = slab
+        if world == 1 and not args.no_cpu:
+            try:
+                line["cuda_reference"] = eager_cuda_baseline(dev)
+            except Exception as ex:  # noqa: BLE001
+                line["cuda_reference"] = {"error": repr(ex)}
+            times, cores = cpu_forward_seconds(1, 0)
+            line["cpu_baseline"] = {"value": N_OUT / times[0], "unit": "voxels/s", "cores": cores, "kind": "port",
+                                    "sample": "1 full forward of the workload (oracle/functional.py, PyTorch CPU fp32), %.1f s" % times[0]}
         if args.dump_profile:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-            with open(os.path.join(ROOT, "gpurun_out", "plan_profile.json"), "w") as f:
+            with open(os.path.join(ROOT, "gpurun_out", "plan_profile_%s.json" % prec), "w") as f:
                 json.dump([{"name": n, "ms": t, "flops": fl} for n, t, fl in prof], f)
     if world > 1:
         dist.barrier()
@@ -388,15 +535,60 @@ def run_b200(args):
         print(json.dumps(line))
 
 
+def run_slab_block(m, dev, world, rank, args, barrier):
+    """BASELINE.json configs[2]: ONE frame (seed 0 on every rank), voxel grid split along X over the ranks, halo
+    exchange at the 3-D conv boundaries (strong scaling).  Returns the `slab` block of the JSON line (all ranks take
+    part; the dict is meaningful on rank 0)."""
+    import torch
+    from occdepth_b200 import parallel
+    img, pix, fov = make_inputs(seed=0)
+    batch = {"img": img.to(dev), "projected_pix_2": [pix.to(dev)], "fov_mask_2": [fov.to(dev)]}
+    with torch.no_grad():
+        for _ in range(3):
+            full = m(batch)
+        ms_1, full = time_forwards(m, batch, args.steps, barrier, dev)       # un-partitioned, same frame on every rank
+        full_logits = full["ssc_logit"].clone()
+        ctx = parallel.SlabContext(halo=3)
+        m.enable_slab_parallel(ctx)
+        try:
+            for _ in range(3):
+                part = m(batch)
+            ms_s, part = time_forwards(m, batch, args.steps, barrier, dev)
+            X = full_logits.shape[2] // world
+            mine = full_logits[:, :, rank * X:(rank + 1) * X]
+            rel = float((part["ssc_logit"] - mine).abs().max() / full_logits.abs().max())
+            rel = parallel.max_over_ranks(rel, dev)
+            plan = list(m._plans().values())[0][0]
+            xbytes = sum(getattr(op, "bytes", 0) for op in plan.ops if getattr(op, "name", "") == "halo_exchange")
+            n_ex = sum(1 for op in plan.ops if getattr(op, "name", "") == "halo_exchange")
+            res = {"ms_per_frame": ms_s / args.steps, "ms_per_frame_1gpu_same_run": ms_1 / args.steps,
+                   "speedup_vs_1gpu": ms_1 / ms_s, "strong_scaling_efficiency": ms_1 / ms_s / world,
+                   "value": N_OUT * args.steps / (ms_s * 1e-3), "unit": "voxels/s", "scaling": "strong",
+                   "halo_exchanges_per_frame": n_ex, "halo_bytes_sent_per_rank_per_frame": xbytes,
+                   "rel_diff_vs_unpartitioned": rel, "partition": ctx.describe() if hasattr(ctx, "describe") else
+                   "X-slab of the voxel grid over %d ranks, halo 3" % world}
+        except Exception as ex:  # noqa: BLE001
+            res = {"error": repr(ex)}
+        finally:
+            m.__dict__.pop("slab_ctx", None)
+            m.invalidate_plans()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--precision", default=os.environ.get("OCCDEPTH_PRECISION", "tf32"), choices=["tf32", "bf16"],
+                    help="arithmetic mode of the headline numbers (default: tf32, the reference-precision mode)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / cuda_reference legs")
+    ap.add_argument("--no-modes", action="store_true", help="skip the second precision mode block")
+    ap.add_argument("--no-slab", action="store_true", help="skip the slab block at N > 1")
     ap.add_argument("--partition", default="frames", choices=["frames", "slab"],
-                    help="frames: one frame per GPU (default, weak scaling); slab: one frame, X-slab partition")
+                    help="frames: one frame per GPU (default, weak scaling; N > 1 adds a `slab` block); slab: the "
+                         "X-slab partition of one frame as the headline")
     ap.add_argument("--dump-profile", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -18,8 +18,15 @@
 extern "C" {
 #endif
 
-#define OCCD_ABI_VERSION 1
+#define OCCD_ABI_VERSION 2
 
+/* Activation / GEMM-operand element types.  Every kernel that touches channels-last activations takes one of:    */
+/*   OCCD_DTYPE_F32  : fp32 storage holding TF32-representable values (each store rounds to the 10-bit TF32        */
+/*                     mantissa, round-to-nearest-away); convolutions run as tcgen05 kind::tf32 with fp32          */
+/*                     accumulation -- the reference-precision mode (the reference's fp32 nn.Conv*d under PyTorch's */
+/*                     CUDA default, TF32 tensor cores)                                                             */
+/*   OCCD_DTYPE_BF16 : bf16 storage, tcgen05 kind::f16 -- the throughput mode                                       */
+/* One channel "vector" is 8 consecutive channels (32 / 16 bytes): cstride, coff and C are multiples of 8.         */
 #define OCCD_DTYPE_F32 0
 #define OCCD_DTYPE_BF16 1
 
@@ -37,6 +44,7 @@ const char* occd_last_error(void);
 #define OCCD_SFA_OUT_F32_PLANAR 0 /* [C][N]   == reference (C,X,Y,Z) fp32                  */
 #define OCCD_SFA_OUT_BF16_CL 1    /* [N][cstride] bf16 channels-last (feeds the 3D net)    */
 #define OCCD_SFA_OUT_F32_CL 2     /* [N][cstride] fp32 channels-last                       */
+#define OCCD_SFA_OUT_TF32_CL 3    /* [N][cstride] fp32 channels-last, values rounded to TF32 (feeds the 3D net) */
 
 typedef struct {
   const void* feat[OCCD_SFA_MAX_SCALES]; /* per scale: [V][h][w][C] channels-last, feat_dtype      */
@@ -96,15 +104,12 @@ int occd_cl_to_planar(const void* in, int in_dtype, float* out, long long B, int
 #define OCCD_CONV_IMPL_HALO 2 /* tcgen05, halo tile loaded once + row-shifted smem views per tap:    */
                               /* stride-1 {-d,0,d}-tap convs, Cin <= 64, resident weights; returns  */
                               /* OCCD_ERR_UNSUPPORTED from plan_create when the shape does not fit   */
-#define OCCD_CONV_IMPL_HALOX 3 /* halo tile, the three W taps of each (dz,dy) pair packed into ONE MMA */
-                              /* (N = 3*Cout_pad <= 256, box 32 positions wide, epilogue sums the      */
-                              /* lane-shifted partials); taps in lexicographic (dz,dy,dx) order         */
-#define OCCD_CONV_IMPL_TCX 4  /* per-tap kernel with the same W-tap packing: (src,dz,dy) groups of dx =   */
-                              /* -1,0,+1, W stride 1, 3*Cout_pad <= 256, tiles 32 wide (30 outputs)       */
-#define OCCD_CONV_IMPL_TCM2 5 /* per-tap kernel, two M tiles (2 x 128 positions) per weight tile: less      */
-                              /* operand traffic per MMA for wide layers; shared weights only              */
+#define OCCD_CONV_IMPL_TCX 4  /* per-tap kernel, the three W taps of each (src,dz,dy) group packed into    */
+                              /* ONE MMA (N = 3*Cout_pad <= 256): taps ordered as groups of dx = -1,0,+1,   */
+                              /* W stride 1, tiles 32 wide (30 outputs), epilogue sums lane-shifted partials */
 #define OCCD_OUT1_NONE 0
-#define OCCD_OUT1_BF16_CL 1    /* pre-activation copy, channels-last bf16                          */
+#define OCCD_OUT1_CL 1         /* pre-activation copy, channels-last in the plan's dtype            */
+#define OCCD_OUT1_BF16_CL OCCD_OUT1_CL
 #define OCCD_OUT1_F32_PLANAR 2 /* pre-activation copy, fp32 [B][C][positions] (reference layout)   */
 
 typedef struct {
@@ -114,7 +119,9 @@ typedef struct {
 
 typedef struct {
   int impl; /* OCCD_CONV_IMPL_*                                                                   */
-  /* sources: channels-last bf16 [B][ID][IH][IW][cstride], channels [coff, coff+C) are read        */
+  int dtype; /* OCCD_DTYPE_*: element type of sources, weights, out0, res1, res2 and a channels-last */
+             /* out1.  F32 = TF32 operands (K chunk 32/16/8 channels), BF16 (K chunk 64/32/16)       */
+  /* sources: channels-last [B][ID][IH][IW][cstride], channels [coff, coff+C) are read             */
   int n_src;
   const void* src[OCCD_CONV_MAX_SRC];
   int src_C[OCCD_CONV_MAX_SRC];
@@ -127,7 +134,8 @@ typedef struct {
   int stride[3];     /* (sd, sh, sw)                                                               */
   int n_taps;
   occd_conv_tap taps[OCCD_CONV_MAX_TAPS];
-  /* weights: bf16 [n_taps][Cout_pad][Kpad], K contiguous, zero padded; bias fp32 [Cout_pad]        */
+  /* weights: dtype [n_taps][Cout_pad][Kpad], K contiguous, zero padded (F32: pre-rounded to TF32);  */
+  /* bias fp32 [Cout_pad]                                                                           */
   const void* weight;
   const float* bias;
   int Cout, Cout_pad, Kpad;
@@ -137,12 +145,14 @@ typedef struct {
   int OD, OH, OW;
   int omul[3], oadd[3];
   int ODf, OHf, OWf; /* full output grid (== OD,OH,OW unless omul != 1)                            */
-  /* out0: channels-last bf16.  v = acc + bias + res1 (+ res2 if !res2_post); out1 = v;             */
+  /* out0: channels-last.  v = acc + bias + res1 (+ res2 if !res2_post); out1 = v;                  */
   /*       out0 = act(v) (+ res2 if res2_post)                                                      */
   void* out0;
   int out0_cstride, out0_coff;
   int act;
-  const void* res1; /* channels-last bf16 on the full output grid, or NULL                         */
+  int out0_exact;   /* 1: F32 plans store out0 without the TF32 rounding (a tensor that is only ever */
+                    /* a residual input, never a GEMM operand); no effect for BF16                   */
+  const void* res1; /* channels-last on the full output grid, or NULL                              */
   int res1_cstride, res1_coff;
   const void* res2;
   int res2_cstride, res2_coff;
@@ -163,16 +173,19 @@ int occd_conv_plan_destroy(occd_conv_plan* plan);
 int occd_conv_run(const occd_conv_plan* plan, void* stream);
 /* introspection for tests / profiling: tile box (TD,TH,TW), N tile, K chunk, stages, grid          */
 int occd_conv_plan_info(const occd_conv_plan* plan, int* info8);
+/* debug: plans created while a device buffer ([64][8] int64) is set stamp per-role clock64 values of CTA 0  */
+/* into it (tools/conv_trace.py); NULL switches tracing off                                               */
+int occd_conv_debug_trace(long long* device_buf);
 
 /* -------------------------------------------------------------------------------------------- */
 /* small channels-last helpers                                                                   */
-/* nn.Softmax(dim=1) over C<=32 planar fp32 channels, written as a bf16 channel window (the      */
-/* torch.cat([x_in, softmax(x_occ)]) of modules.py:168-171)                                        */
-int occd_softmax_planar_to_cl(const float* in, void* out, long long B, int C, long long S, int cstride,
+/* nn.Softmax(dim=1) over C<=32 planar fp32 channels, written as a channels-last channel window   */
+/* of element type `dtype` (the torch.cat([x_in, softmax(x_occ)]) of modules.py:168-171)           */
+int occd_softmax_planar_to_cl(const float* in, void* out, int dtype, long long B, int C, long long S, int cstride,
                               int coff, void* stream);
 /* out[b][c][p] = in[b][p][coff+c]: turns a channels-last activation into a K-major GEMM weight  */
 /* (the mega-context operand of torch.bmm, CRP3D.py:62-63,81); out rows have leading dim ldo      */
-int occd_cl_transpose(const void* in, void* out, int B, int P, int C, int cstride, int coff, int ldo,
+int occd_cl_transpose(const void* in, void* out, int dtype, int B, int P, int C, int cstride, int coff, int ldo,
                       long long out_bstride, void* stream);
 /* class map of the callers' post-processing: uint16 out[b][s] = first index of the largest of the   */
 /* C planar fp32 logits in[b][c][s] (np.argmax(softmax(ssc_logit), 1).astype(uint16),               */
@@ -181,8 +194,8 @@ int occd_cl_transpose(const void* in, void* out, int B, int P, int C, int cstrid
 /* scripts/generate_kitti_submission.py:79 (data/semantic_kitti/io_data.py:99-113)                    */
 int occd_argmax_classes(const float* in, void* out, long long B, int C, long long S, const int* lut, void* stream);
 /* copy a channel window (C % 8 == 0) between channels-last buffers (torch.cat of CRP3D.py:90)    */
-int occd_copy_channels(const void* in, void* out, long long positions, int C, int in_cstride, int in_coff,
-                       int out_cstride, int out_coff, void* stream);
+int occd_copy_channels(const void* in, void* out, int dtype, long long positions, int C, int in_cstride,
+                       int in_coff, int out_cstride, int out_coff, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* Data pipeline: voxel-centre -> pixel indices on the device, bit for bit what     */
@@ -204,41 +217,35 @@ int occd_normalize_rgb_u8(const void* in, float* out, int H0, int W0, int H, int
                           const float* stdv, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
-/* EfficientNet / decoder bandwidth kernels (channels-last bf16, 2-D)                             */
+/* EfficientNet / decoder bandwidth kernels (channels-last 2-D maps of element type `dtype`)       */
 /* depthwise KxK (K = 3|5) conv + folded BN + activation; optionally accumulates the per-channel    */
 /* spatial SUM of the output into pool[B][C] (squeeze of geffnet SqueezeExcite) as 64-bit FIXED-    */
 /* POINT integers in units of 2^-24 (integer atomics: bit-reproducible); explicit top/left padding  */
 /* implements TF "SAME" (bottom/right implied by OH/OW). w: fp32 [K*K][C].                          */
-int occd_dwconv2d_fwd(const void* in, const float* w, const float* bias, void* out, long long* pool, int B, int H,
-                      int W, int OH, int OW, int C, int cs_in, int cs_out, int K, int stride, int pad_top,
-                      int pad_left, int act, void* stream);
+int occd_dwconv2d_fwd(const void* in, const float* w, const float* bias, void* out, long long* pool, int dtype,
+                      int B, int H, int W, int OH, int OW, int C, int cs_in, int cs_out, int K, int stride,
+                      int pad_top, int pad_left, int act, void* stream);
 /* same contract, shared-memory-tiled variant: one zero-filled input halo tile per CTA staged with    */
 /* cp.async, FMA loop out of shared memory (results equal up to fp32 summation order)                */
-int occd_dwconv2d_tiled_fwd(const void* in, const float* w, const float* bias, void* out, long long* pool, int B,
-                            int H, int W, int OH, int OW, int C, int cs_in, int cs_out, int K, int stride,
+int occd_dwconv2d_tiled_fwd(const void* in, const float* w, const float* bias, void* out, long long* pool, int dtype,
+                            int B, int H, int W, int OH, int OW, int C, int cs_in, int cs_out, int K, int stride,
                             int pad_top, int pad_left, int act, void* stream);
 /* gate[b][c] = sigmoid(W2 silu(W1 (pool[b] 2^-24 / HW) + b1) + b2); zeroes pool. w1 [R][C],       */
 /* w2t [R][C]; `gate` must hold B*C + B*R floats (the hidden layer is staged behind the gates)     */
 int occd_se_gate_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
                      const float* b2, float* gate, int B, int C, int R, void* stream);
 /* fused path: squeeze-excite MLP + gate folded into one projection-weight set per image:          */
-/* wout[b][row][k] = bf16(master[row][k] * gate[b][k]); hidden: B*R floats of scratch; zeroes pool  */
+/* wout[b][row][k] = wdtype(master[row][k] * gate[b][k]) (bf16 / TF32-rounded fp32 GEMM weights);   */
+/* hidden: B*R floats of scratch; zeroes pool                                                       */
 int occd_se_gate_fold_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
-                          const float* b2, float* hidden, const float* master, void* wout, int B, int C, int R,
-                          int rows, int Kpad, void* stream);
-/* same contract; the fold is decomposed into one CTA per 32-channel strip so each gate is evaluated once */
-int occd_se_gate_fold_strip_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
-                                const float* b2, float* hidden, const float* master, void* wout, int B, int C,
-                                int R, int rows, int Kpad, void* stream);
-/* out[row][k] = bf16(master[row][k] * gate[k]): folds x * gate into the next 1x1 conv's weights   */
-int occd_scale_weights(const float* master, const float* gate, void* out, int rows, int Kpad, int C,
+                          const float* b2, float* hidden, const float* master, void* wout, int wdtype, int B, int C,
+                          int R, int rows, int Kpad, void* stream);
+/* out[row][k] = wdtype(master[row][k] * gate[k]): folds x * gate into the next 1x1 conv's weights */
+int occd_scale_weights(const float* master, const float* gate, void* out, int wdtype, int rows, int Kpad, int C,
                        void* stream);
 /* F.interpolate(mode="bilinear", align_corners=True) of UpSampleBN.forward (unet2d.py:39-44)      */
-int occd_upsample_bilinear_ac(const void* in, void* out, int B, int h, int w, int OH, int OW, int C, int cs_in,
-                              int in_off, int cs_out, int out_off, void* stream);
-/* same contract, one block row per output row (block-uniform vertical weights)                    */
-int occd_upsample_bilinear_rows(const void* in, void* out, int B, int h, int w, int OH, int OW, int C, int cs_in,
-                              int in_off, int cs_out, int out_off, void* stream);
+int occd_upsample_bilinear_ac(const void* in, void* out, int dtype, int B, int h, int w, int OH, int OW, int C,
+                              int cs_in, int in_off, int cs_out, int out_off, void* stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* FlospDepth (the "OAD" depth branch, configs with trans_2d_to_3d: "flosp_depth")                */
@@ -257,12 +264,13 @@ int occd_softmax_planar(const float* in, float* out, long long B, int C, long lo
 int occd_fc_fwd(const float* in, const float* w, const float* bias, float* out, int B, int n_in, int n_out,
                 int act, void* stream);
 /* x[b][pos][c] *= gate[b][c] in place (SELayer: x * gate(x_se), flosp_depth.py:195-199)            */
-int occd_channel_scale(void* x, const float* gate, long long B, long long S, int C, int cstride, void* stream);
+int occd_channel_scale(void* x, const float* gate, int dtype, long long B, long long S, int C, int cstride,
+                       void* stream);
 
 /* virtual right view for single-view RGB-D inputs: OccDepth.generate_virtual_img (OccDepth.py:233-260). */
-/* in/out: channels-last bf16 [B][h][w][cs]; depth: fp32 [dh][dw] of batch item 0; bf_scale = bf / scale_2d  */
-int occd_virtual_view_fwd(const void* in, void* out, const float* depth, int B, int h, int w, int C, int cs_in,
-                          int cs_out, int dh, int dw, float bf_scale, void* stream);
+/* in/out: channels-last [B][h][w][cs] of `dtype`; depth: fp32 [dh][dw] of batch item 0; bf_scale = bf / scale_2d */
+int occd_virtual_view_fwd(const void* in, void* out, const float* depth, int dtype, int B, int h, int w, int C,
+                          int cs_in, int cs_out, int dh, int dw, float bf_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ _LIB = None
 
 MAX_SCALES = 4
 DTYPE_F32, DTYPE_BF16 = 0, 1
-SFA_OUT_F32_PLANAR, SFA_OUT_BF16_CL, SFA_OUT_F32_CL = 0, 1, 2
+SFA_OUT_F32_PLANAR, SFA_OUT_BF16_CL, SFA_OUT_F32_CL, SFA_OUT_TF32_CL = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SILU, ACT_SIGMOID = 0, 1, 2, 3, 4
 
 
@@ -43,8 +43,8 @@ class SfaParams(C.Structure):
 
 
 CONV_MAX_TAPS, CONV_MAX_SRC = 81, 3
-CONV_IMPL_TC, CONV_IMPL_SIMT, CONV_IMPL_HALO, CONV_IMPL_HALOX, CONV_IMPL_TCX, CONV_IMPL_TCM2 = 0, 1, 2, 3, 4, 5
-OUT1_NONE, OUT1_BF16_CL, OUT1_F32_PLANAR = 0, 1, 2
+CONV_IMPL_TC, CONV_IMPL_SIMT, CONV_IMPL_HALO, CONV_IMPL_TCX = 0, 1, 2, 4
+OUT1_NONE, OUT1_CL, OUT1_F32_PLANAR = 0, 1, 2
 
 
 class ConvTap(C.Structure):
@@ -54,6 +54,7 @@ class ConvTap(C.Structure):
 class ConvDesc(C.Structure):
     _fields_ = [
         ("impl", C.c_int),
+        ("dtype", C.c_int),
         ("n_src", C.c_int),
         ("src", C.c_void_p * CONV_MAX_SRC),
         ("src_C", C.c_int * CONV_MAX_SRC),
@@ -74,6 +75,7 @@ class ConvDesc(C.Structure):
         ("out0", C.c_void_p),
         ("out0_cstride", C.c_int), ("out0_coff", C.c_int),
         ("act", C.c_int),
+        ("out0_exact", C.c_int),
         ("res1", C.c_void_p),
         ("res1_cstride", C.c_int), ("res1_coff", C.c_int),
         ("res2", C.c_void_p),
@@ -98,25 +100,24 @@ SYMBOLS = {
     "occd_conv_plan_destroy": (C.c_int, [_vp]),
     "occd_conv_run": (C.c_int, [_vp, _vp]),
     "occd_conv_plan_info": (C.c_int, [_vp, C.POINTER(C.c_int)]),
-    "occd_softmax_planar_to_cl": (C.c_int, [_vp, _vp, _ll, _i, _ll, _i, _i, _vp]),
+    "occd_conv_debug_trace": (C.c_int, [_vp]),
+    "occd_softmax_planar_to_cl": (C.c_int, [_vp, _vp, _i, _ll, _i, _ll, _i, _i, _vp]),
     "occd_argmax_classes": (C.c_int, [_vp, _vp, _ll, _i, _ll, _vp, _vp]),
     "occd_normalize_rgb_u8": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "occd_vox2pix_fwd": (C.c_int, [_vp, _i, _vp, _vp, C.c_double, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
-    "occd_cl_transpose": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _vp]),
-    "occd_copy_channels": (C.c_int, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
-    "occd_dwconv2d_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp] + [_i] * 13 + [_vp]),
-    "occd_dwconv2d_tiled_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp] + [_i] * 13 + [_vp]),
+    "occd_cl_transpose": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _ll, _vp]),
+    "occd_copy_channels": (C.c_int, [_vp, _vp, _i, _ll, _i, _i, _i, _i, _i, _vp]),
+    "occd_dwconv2d_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp] + [_i] * 14 + [_vp]),
+    "occd_dwconv2d_tiled_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp] + [_i] * 14 + [_vp]),
     "occd_se_gate_fwd": (C.c_int, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "occd_se_gate_fold_fwd": (C.c_int, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "occd_se_gate_fold_strip_fwd": (C.c_int, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "occd_scale_weights": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "occd_se_gate_fold_fwd": (C.c_int, [_vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "occd_scale_weights": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "occd_frustum_sample_fwd": (C.c_int, [_vp, _vp] + [_i] * 7 + [_f] * 4 + [_i, _vp, _i, _vp]),
     "occd_softmax_planar": (C.c_int, [_vp, _vp, _ll, _i, _ll, _vp]),
     "occd_fc_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "occd_channel_scale": (C.c_int, [_vp, _vp, _ll, _ll, _i, _i, _vp]),
-    "occd_virtual_view_fwd": (C.c_int, [_vp, _vp, _vp] + [_i] * 8 + [_f, _vp]),
-    "occd_upsample_bilinear_ac": (C.c_int, [_vp, _vp] + [_i] * 10 + [_vp]),
-    "occd_upsample_bilinear_rows": (C.c_int, [_vp, _vp] + [_i] * 10 + [_vp]),
+    "occd_channel_scale": (C.c_int, [_vp, _vp, _i, _ll, _ll, _i, _i, _vp]),
+    "occd_virtual_view_fwd": (C.c_int, [_vp, _vp, _vp] + [_i] * 9 + [_f, _vp]),
+    "occd_upsample_bilinear_ac": (C.c_int, [_vp, _vp] + [_i] * 11 + [_vp]),
 }
 
 

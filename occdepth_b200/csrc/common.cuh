@@ -92,4 +92,95 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   return r;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Activation element types.  Two precision modes share every kernel (template parameter T):
+//   __nv_bfloat16 : bf16 storage, tcgen05 kind::f16 operands ("bf16" throughput mode)
+//   float         : fp32 storage holding TF32-representable values (10-bit mantissa, round-to-nearest-away at every
+//                   store), tcgen05 kind::tf32 operands -- the reference-precision mode: the reference's convolutions
+//                   are fp32 nn.Conv*d (modules.py:158-175, DDR.py:111-139) which PyTorch itself runs as TF32 on CUDA
+// One "vector" is always 8 consecutive channels: 16 bytes of bf16 or 32 bytes of fp32.
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ void ld256_f(const float* p, float* f) {
+  uint32_t r[8];
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void ld256_nc_f(const float* p, float* f) {
+  uint32_t r[8];
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void st256_f(float* p, const float* f) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(__float_as_uint(f[0])),
+               "r"(__float_as_uint(f[1])), "r"(__float_as_uint(f[2])), "r"(__float_as_uint(f[3])),
+               "r"(__float_as_uint(f[4])), "r"(__float_as_uint(f[5])), "r"(__float_as_uint(f[6])),
+               "r"(__float_as_uint(f[7]))
+               : "memory");
+}
+
+template <typename T> struct Elem;
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr int kDtype = 1;  // OCCD_DTYPE_BF16
+  // what the consumer of a stored value reads back
+  static __device__ __forceinline__ float rnd(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+  static __device__ __forceinline__ __nv_bfloat16 cvt(float v) { return __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ float up(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* f) {
+    unpack8(*reinterpret_cast<const uint4*>(p), f);
+  }
+  static __device__ __forceinline__ void ld8_nc(const __nv_bfloat16* p, float* f) {
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f);
+  }
+  static __device__ __forceinline__ void st8(__nv_bfloat16* p, const float* f) {
+    *reinterpret_cast<uint4*>(p) = pack8(f);
+  }
+  static __device__ __forceinline__ void st8_exact(__nv_bfloat16* p, const float* f) { st8(p, f); }
+  // st8 that also returns the stored (rounded) values
+  static __device__ __forceinline__ void st8_rb(__nv_bfloat16* p, float* f) {
+    const uint4 u = pack8(f);
+    *reinterpret_cast<uint4*>(p) = u;
+    unpack8(u, f);
+  }
+};
+template <> struct Elem<float> {
+  static constexpr int kDtype = 0;  // OCCD_DTYPE_F32 (TF32-valued)
+  static __device__ __forceinline__ float rnd(float v) { return round_tf32(v); }
+  static __device__ __forceinline__ float cvt(float v) { return round_tf32(v); }
+  static __device__ __forceinline__ float up(float v) { return v; }
+  static __device__ __forceinline__ void ld8(const float* p, float* f) { ld256_f(p, f); }
+  static __device__ __forceinline__ void ld8_nc(const float* p, float* f) { ld256_nc_f(p, f); }
+  static __device__ __forceinline__ void st8(float* p, const float* f) {
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = round_tf32(f[i]);
+    st256_f(p, r);
+  }
+  static __device__ __forceinline__ void st8_exact(float* p, const float* f) { st256_f(p, f); }
+  static __device__ __forceinline__ void st8_rb(float* p, float* f) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = round_tf32(f[i]);
+    st256_f(p, f);
+  }
+};
+
+// host-side dispatch over the activation dtype of a C-ABI call (OCCD_DTYPE_F32 | OCCD_DTYPE_BF16)
+#define OCCD_DISPATCH_DTYPE(dtype, T, ...)                                   \
+  do {                                                                       \
+    if ((dtype) == 1) { using T = __nv_bfloat16; __VA_ARGS__; }              \
+    else if ((dtype) == 0) { using T = float; __VA_ARGS__; }                 \
+    else { occd_set_last_error("unsupported activation dtype"); return OCCD_ERR_ARG; } \
+  } while (0)
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

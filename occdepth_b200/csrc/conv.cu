@@ -1,8 +1,12 @@
 // Generalised N-d convolution as implicit GEMM.
 //   TC path  : TMA (5-D tiled tensor maps, zero-filled halos, traversal strides) -> swizzled smem ->
 //              tcgen05.mma (M=128 positions x N<=256 channels, fp32 accumulators in TMEM) ->
-//              tcgen05.ld epilogue (bias + residuals + activation, bf16 channels-last / fp32 planar stores)
+//              tcgen05.ld epilogue (bias + residuals + activation, channels-last / fp32 planar stores)
 //   SIMT path: CUDA-core direct convolution with identical semantics (cross-check and odd shapes)
+// Two operand types share every kernel (template parameter T, see Elem<T> / tc::Mma<T>):
+//   float (TF32 values, tcgen05 kind::tf32, K chunk = 32 / 16 / 8 channels)  -- reference-precision mode
+//   __nv_bfloat16 (tcgen05 kind::f16, K chunk = 64 / 32 / 16 channels)       -- throughput mode
+// A K chunk is always one swizzled smem row of RB = 128 / 64 / 32 bytes; one tcgen05.mma consumes 32 bytes of it.
 // See include/occdepth_b200.h for the reference call sequences this replaces.
 #include "conv_common.cuh"
 #include "conv_tc.cuh"
@@ -32,16 +36,18 @@ struct TcParams {
   int a_bytes, b_stride, b_bytes;
   int tmem_cols;
   int pdl;           // launched with programmatic stream serialization: wait for the producer grid after the prologue
-  int m2_sets;       // M2 kernel: 0 = not an M2 plan, else number of {D0, D1} accumulator sets in TMEM (1 | 2)
-  long long* trace;  // optional [tile][8] clock64 stamps of CTA 0 (tools/conv_trace.py)
+  long long* trace;  // optional [tile][8] clock64 stamps of CTA 0 (occd_conv_debug_trace, tools/conv_trace.py)
   signed char tap_src[OCCD_CONV_MAX_TAPS];
   short tap_dz[OCCD_CONV_MAX_TAPS], tap_dy[OCCD_CONV_MAX_TAPS], tap_dx[OCCD_CONV_MAX_TAPS];
 };
 
-// XP: x-packed variant (scheme described at conv_halo_kernel): the pipeline items are (source, dz, dy) groups
-// whose B operand stacks the three W taps (N_tile = 3 * Cout_pad), tiles are 32 wide with one halo column on each
-// side, and the epilogue adds the lane-shifted partial sums.
-template <int KC, bool XP, bool WIDE>
+// XP: x-packed variant: the pipeline items are (source, dz, dy) groups whose B operand stacks the three W taps
+// (N_tile = 3 * Cout_pad: with taps in lexicographic order that is 3 consecutive tap slices of the ordinary weight
+// tensor), tiles are 32 wide with one halo column on each side so that one smem row == one TMEM lane == one lane of
+// an epilogue warp, and the epilogue forms out[r] = Q_0[r-1] + Q_1[r] + Q_2[r+1] from the three column groups with
+// two warp shuffles per channel.  One A fetch then feeds 3x the output columns (measured on B200, round 2: the
+// Cout = 80 decoder convs 0.154 -> 0.102 ms).
+template <typename T, int RB, bool XP>
 __global__ void __launch_bounds__(kTcThreads)
 conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap tmA0,
                const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -52,7 +58,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   //   warps 2-17       : four epilogue groups of 4 warps: group g drains accumulator (g & 1) -- even / odd
   //                      tiles -- and column half (g >> 1) of it: TMEM -> regs -> global while the MMAs of the
   //                      following tiles run (the epilogue is latency bound: 16 warps keep the SM's LSU busy)
-  constexpr int ROW_BYTES = KC * 2;
+  constexpr int KCH = RB / (int)sizeof(T);  // channels per K chunk
+  constexpr int NMMA = RB / 32;             // tcgen05.mma instructions per chunk (32 bytes of K each)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16-byte aligned: round the base up to 1024 (swizzle atom alignment)
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -137,8 +144,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
             }
             const uint32_t sa = smem_a + (uint32_t)(s * p.group + g) * p.a_bytes;
             const uint32_t sb = smem_b + (uint32_t)(s * p.group + g) * p.b_stride;
-            tc::tma_load_5d(sa, maps[src], full_bar + 8u * s, kc * KC, cw, ch, cd, b);
-            tc::tma_load_2d(sb, &tmW, full_bar + 8u * s, kc * KC, wrow);
+            tc::tma_load_5d(sa, maps[src], full_bar + 8u * s, kc * KCH, cw, ch, cd, b);
+            tc::tma_load_2d(sb, &tmW, full_bar + 8u * s, kc * KCH, wrow);
             --remaining;
             if (++g == p.group || remaining == 0) {
               g = 0;
@@ -152,9 +159,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      const uint32_t idesc = tc::make_idesc_bf16(128, p.N_tile);
-      const uint64_t da0 = tc::make_sdesc(smem_a, ROW_BYTES);
-      const uint64_t db0 = tc::make_sdesc(smem_b, ROW_BYTES);
+      const uint32_t idesc = tc::Mma<T>::idesc(128, p.N_tile);
+      const uint64_t da0 = tc::make_sdesc(smem_a, RB);
+      const uint64_t db0 = tc::make_sdesc(smem_b, RB);
       int s = 0;
       uint32_t ph = 0;
       int j = 0;
@@ -171,10 +178,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
           for (int g = 0; g < cnt; ++g, ++it) {
             const uint64_t da = da0 + (uint64_t)((s * p.group + g) * (p.a_bytes >> 4));
             const uint64_t db = db0 + (uint64_t)((s * p.group + g) * (p.b_stride >> 4));
-            if (it == 0) tc::mma_bf16_imm<0>(d_tmem, da, db, idesc);
-            else tc::mma_bf16_imm<1>(d_tmem, da, db, idesc);
+            if (it == 0) tc::Mma<T>::template issue<0>(d_tmem, da, db, idesc);
+            else tc::Mma<T>::template issue<1>(d_tmem, da, db, idesc);
 #pragma unroll
-            for (int k = 1; k < KC / 16; ++k) tc::mma_bf16_imm<1>(d_tmem, da + 2 * k, db + 2 * k, idesc);
+            for (int k = 1; k < NMMA; ++k) tc::Mma<T>::template issue<1>(d_tmem, da + 2 * k, db + 2 * k, idesc);
           }
           tc::mma_commit(empty_bar + 8u * s);  // frees the smem stage when these MMAs retire
           if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -229,7 +236,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             v[i] += __shfl_up_sync(0xffffffffu, lo[i], 1) + __shfl_down_sync(0xffffffffu, hi[i], 1);
-          if (valid) conv_epilogue_row<16>(p.epi, b, od, oh, ow, c0, v);
+          if (valid) conv_epilogue_row<T, 16>(p.epi, b, od, oh, ow, c0, v);
         }
       } else {
       // software-pipelined: the tcgen05.ld of the next 16 columns is in flight while these 16 are stored
@@ -244,7 +251,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]);
-            conv_epilogue_row<16, WIDE>(p.epi, b, od, oh, ow, n0 + c0, v);
+            conv_epilogue_row<T, 16>(p.epi, b, od, oh, ow, n0 + c0, v);
           }
           if (has_b) {
             tc::tmem_ld_wait16(rb);
@@ -253,7 +260,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
               float v[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]);
-              conv_epilogue_row<16, WIDE>(p.epi, b, od, oh, ow, n0 + c0 + 16, v);
+              conv_epilogue_row<T, 16>(p.epi, b, od, oh, ow, n0 + c0 + 16, v);
             }
             if (c0 + 32 < c_end) tc::tmem_ld_wait16(ra);
           }
@@ -274,217 +281,16 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
 }
 
 // ------------------------------------------------------------------------------------------------
-// M2 variant of the per-tap kernel: every pipeline item carries TWO consecutive M tiles (A0, A1: 2 x 128 positions)
-// and ONE weight tile B, and feeds two accumulators D0 += A0.B, D1 += A1.B.  The wide decoder convs are bound by
-// operand traffic L2 -> SM (ncu: 43 B/cycle/SM at 42 % tensor-pipe activity for 128x160 tiles, where full rate
-// would need 115 B/cycle); sharing B between two M tiles cuts that by (128+N)/(128+N/2) -- 1.38x at N = 160.
-// TMEM holds nsets x {D0, D1}: two sets (epilogue of pair j overlaps the MMAs of pair j+1) when 4*N_tile <= 512,
-// otherwise one.  All 16 epilogue warps work on every pair: group g drains M tile (g & 1), column half (g >> 1).
-// TcParams::a_bytes is the size of ONE A tile; an item's A region is 2 * a_bytes.
-template <int KC>
-__global__ void __launch_bounds__(kTcThreads)
-conv_tc_m2_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap tmA0,
-                  const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                  const __grid_constant__ CUtensorMap tmW) {
-  constexpr int ROW_BYTES = KC * 2;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t item_a = 2u * (uint32_t)p.a_bytes;
-  const uint32_t smem_a = smem_base;
-  const uint32_t smem_b = smem_a + (uint32_t)(p.stages * p.group) * item_a;
-  const uint32_t bar_base = smem_b + (uint32_t)(p.stages * p.group) * p.b_stride;
-  const uint32_t full_bar = bar_base;
-  const uint32_t empty_bar = bar_base + 8u * kMaxStages;
-  const uint32_t tmem_full_bar = bar_base + 16u * kMaxStages;       // [2]
-  const uint32_t tmem_empty_bar = tmem_full_bar + 16u;              // [2]
-  const uint32_t tmem_slot = tmem_empty_bar + 16u;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int n_tiles_n = p.Cout_pad / p.N_tile;
-  const int num_pairs = ((p.num_m_tiles + 1) >> 1) * n_tiles_n;
-  const int nsets = p.m2_sets;                        // 1 or 2
-  const uint32_t set_stride = 2u * (uint32_t)p.N_tile;  // columns of one {D0, D1} set
-
-  int iters_per_tile = 0;
-  for (int i = 0; i < p.n_taps; ++i) iters_per_tile += p.n_kchunks[p.tap_src[i]];
-
-  if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&tmA0);
-    tc::prefetch_tmap(&tmW);
-    for (int s = 0; s < p.stages; ++s) {
-      tc::mbar_init(full_bar + 8u * s, 1);
-      tc::mbar_init(empty_bar + 8u * s, 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      tc::mbar_init(tmem_full_bar + 8u * a, 1);
-      tc::mbar_init(tmem_empty_bar + 8u * a, 512);  // all sixteen epilogue warps arrive
-    }
-    tc::fence_barrier_init();
-  }
-  if (warp == 1) {
-    __syncwarp();
-    tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  }
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  if (p.pdl) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  }
-
-  // M tile index -> (batch, tile origin); an index past the last tile decodes to b == B (TMA zero-fills, the
-  // epilogue masks it)
-  auto decode = [&](int mt, int& b, int& td, int& th, int& tw) {
-    int t = mt;
-    tw = t % p.tiles_w; t /= p.tiles_w;
-    th = t % p.tiles_h; t /= p.tiles_h;
-    td = t % p.tiles_d; t /= p.tiles_d;
-    b = t;
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      const CUtensorMap* maps[3] = {&tmA0, &tmA1, &tmA2};
-      int s = 0;
-      uint32_t ph = 0;
-      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-        const int nt = pair % n_tiles_n;
-        const int mp = pair / n_tiles_n;
-        int b[2], td[2], th[2], tw[2];
-        decode(2 * mp, b[0], td[0], th[0], tw[0]);
-        decode(2 * mp + 1, b[1], td[1], th[1], tw[1]);
-        const int n0 = nt * p.N_tile;
-        int g = 0;
-        int remaining = iters_per_tile;
-        for (int tp = 0; tp < p.n_taps; ++tp) {
-          const int src = p.tap_src[tp];
-          const int wrow = b[0] * p.w_batch_rows + tp * p.Cout_pad + n0;
-          const int nk = p.n_kchunks[src];
-          for (int kc = 0; kc < nk; ++kc) {
-            if (g == 0) {
-              const int cnt = remaining < p.group ? remaining : p.group;
-              tc::mbar_wait(empty_bar + 8u * s, ph ^ 1u);
-              tc::mbar_expect_tx(full_bar + 8u * s, (uint32_t)(cnt * (2 * p.a_bytes + p.b_bytes)));
-            }
-            const uint32_t sa = smem_a + (uint32_t)(s * p.group + g) * item_a;
-            const uint32_t sb = smem_b + (uint32_t)(s * p.group + g) * p.b_stride;
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-              tc::tma_load_5d(sa + (uint32_t)h * p.a_bytes, maps[src], full_bar + 8u * s, kc * KC,
-                              tw[h] * p.TW * p.stride[2] + p.tap_dx[tp], th[h] * p.TH * p.stride[1] + p.tap_dy[tp],
-                              td[h] * p.TD * p.stride[0] + p.src_d0 + p.tap_dz[tp], b[h]);
-            tc::tma_load_2d(sb, &tmW, full_bar + 8u * s, kc * KC, wrow);
-            --remaining;
-            if (++g == p.group || remaining == 0) {
-              g = 0;
-              if (++s == p.stages) { s = 0; ph ^= 1u; }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = tc::make_idesc_bf16(128, p.N_tile);
-      const uint64_t da0 = tc::make_sdesc(smem_a, ROW_BYTES);
-      const uint64_t db0 = tc::make_sdesc(smem_b, ROW_BYTES);
-      int s = 0;
-      uint32_t ph = 0;
-      int j = 0;
-      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++j) {
-        const uint32_t set = (uint32_t)(j % nsets);
-        const uint32_t use = (uint32_t)(j / nsets);
-        tc::mbar_wait(tmem_empty_bar + 8u * set, (use & 1u) ^ 1u);  // epilogue drained this set
-        tc::fence_after_sync();
-        const uint32_t d0 = tmem_base + set * set_stride;
-        const uint32_t d1 = d0 + (uint32_t)p.N_tile;
-        for (int it = 0; it < iters_per_tile;) {
-          tc::mbar_wait(full_bar + 8u * s, ph);
-          tc::fence_after_sync();
-          const int cnt = (iters_per_tile - it) < p.group ? (iters_per_tile - it) : p.group;
-          for (int g = 0; g < cnt; ++g, ++it) {
-            const uint64_t da = da0 + (uint64_t)((s * p.group + g) * (item_a >> 4));
-            const uint64_t da_1 = da + (uint64_t)(p.a_bytes >> 4);
-            const uint64_t db = db0 + (uint64_t)((s * p.group + g) * (p.b_stride >> 4));
-            if (it == 0) {
-              tc::mma_bf16_imm<0>(d0, da, db, idesc);
-#pragma unroll
-              for (int k = 1; k < KC / 16; ++k) tc::mma_bf16_imm<1>(d0, da + 2 * k, db + 2 * k, idesc);
-              tc::mma_bf16_imm<0>(d1, da_1, db, idesc);
-#pragma unroll
-              for (int k = 1; k < KC / 16; ++k) tc::mma_bf16_imm<1>(d1, da_1 + 2 * k, db + 2 * k, idesc);
-            } else {
-#pragma unroll
-              for (int k = 0; k < KC / 16; ++k) tc::mma_bf16_imm<1>(d0, da + 2 * k, db + 2 * k, idesc);
-#pragma unroll
-              for (int k = 0; k < KC / 16; ++k) tc::mma_bf16_imm<1>(d1, da_1 + 2 * k, db + 2 * k, idesc);
-            }
-          }
-          tc::mma_commit(empty_bar + 8u * s);
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
-        }
-        tc::mma_commit(tmem_full_bar + 8u * set);
-      }
-    }
-  } else {
-    // ===== epilogue =====
-    const int q = warp & 3;
-    const int h = ((warp - 2) >> 2) & 1;     // which M tile of the pair
-    const int half = (warp - 2) >> 3;        // which half of the 16-column chunks
-    const int n_chunks = p.N_tile >> 4;
-    const int c_begin = half == 0 ? 0 : ((n_chunks + 1) >> 1) * 16;
-    const int c_end = half == 0 ? ((n_chunks + 1) >> 1) * 16 : p.N_tile;
-    const int row = q * 32 + lane;
-    const int rw = row % p.TW;
-    const int rh = (row / p.TW) % p.TH;
-    const int rd = row / (p.TW * p.TH);
-    int j = 0;
-    for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, ++j) {
-      const uint32_t set = (uint32_t)(j % nsets);
-      const uint32_t use = (uint32_t)(j / nsets);
-      const int nt = pair % n_tiles_n;
-      const int mp = pair / n_tiles_n;
-      int b, td, th, tw;
-      decode(2 * mp + h, b, td, th, tw);
-      const int od = td * p.TD + rd, oh = th * p.TH + rh, ow = tw * p.TW + rw;
-      const bool valid = b < p.epi.B && od < p.epi.OD && oh < p.epi.OH && ow < p.epi.OW;
-      const int n0 = nt * p.N_tile;
-      tc::mbar_wait(tmem_full_bar + 8u * set, use & 1u);
-      tc::fence_after_sync();
-      const uint32_t taddr = tmem_base + set * set_stride + (uint32_t)(h * p.N_tile) + ((uint32_t)(q * 32) << 16);
-      for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-        float v[16];
-        tc::tmem_ld16(taddr + (uint32_t)c0, v);
-        if (valid) conv_epilogue_row<16>(p.epi, b, od, oh, ow, n0 + c0, v);
-      }
-      tc::fence_before_sync();
-      tc::mbar_arrive(tmem_empty_bar + 8u * set);
-    }
-  }
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Halo-tile variant for stride-1 3x3x3 convolutions with few channels (the full-resolution head):
 // the per-tap TMA boxes of conv_tc_kernel re-load every input row 27 times and the TMA unit (~1.5 cycles per
 // box row) becomes the limiter.  Here each CTA tile loads ONE zero-filled halo box (PD x PH x PW positions,
-// rows of KC channels) per k-chunk and feeds all 27 taps from row-shifted views of that box: with smem rows
+// rows of one K chunk) and feeds all 27 taps from row-shifted views of that box: with smem rows
 // linearised as r = (pd*PH + ph)*PW + pw, the A operand of tap (a,b,c) for output rows [R, R+128) is simply
 // rows [R + (a*PH + b)*PW + c, ...) -- a different UMMA start address, same data.  Rows that fall in the
 // halo produce garbage accumulator rows that the epilogue never stores.  Dilation d runs the same scheme on
 // the d^3 sub-sampled grids (TMA traversal stride d), so the halo is always one position.  Weights for all
-// taps stay resident in shared memory.
+// taps stay resident in shared memory.  The swizzled row-shifted UMMA start addresses use base-offset 0 (measured on
+// B200: the XOR swizzle follows absolute smem address bits for both TMA and UMMA).
 struct HaloParams {
   ConvEpi epi;
   int d;                      // dilation (== padding)
@@ -499,29 +305,17 @@ struct HaloParams {
   int stages;
   int n_taps;
   int N_tile, tmem_cols, set_stride;
-  int bo_mode;                // UMMA descriptor base-offset convention for row-shifted swizzled views
   int b_stride, w_bytes;
   int tap_off16[27];          // (R0 + (a*PH + b)*PW + c) * row_bytes / 16: A-descriptor advance per tap
-  int CP;                     // x-packed variant: output channels (padded) per W tap, N_tile == 3 * CP
   int pdl;                    // see TcParams::pdl
   long long* trace;
 };
 
-//
-// XP ("x-packed") variant: tcgen05.mma at N <= 128 is bound by a ~79-cycle floor per M128xK16 instruction, not by
-// the tensor pipe, so a 32-channel conv leaves 3/4 of the MMA time unused.  With the halo box exactly 32 positions
-// wide (30 outputs + 2 halo columns) one smem row == one TMEM lane == one lane of an epilogue warp, and the three
-// taps along W of one (dz, dy) pair can share ONE instruction: its B operand is the three taps' weights stacked
-// along N (N = 3 * CP; with taps in lexicographic order that is 3 consecutive tap slices of the ordinary weight
-// tensor, no re-layout), its A operand the un-shifted rows.  The accumulator then holds
-//   Q_c[r] = sum_{a,b} W[a][b][c] . in[r + (a*PH + b)*PW]     (c = 0,1,2)
-// and the epilogue forms out[r] = Q_0[r-1] + Q_1[r] + Q_2[r+1] with two warp shuffles per channel: 9 MMA groups
-// instead of 27, every A start address a multiple of 32 rows (whole swizzle atoms).
-template <int KC, bool XP>
+template <typename T, int RB>
 __global__ void __launch_bounds__(kTcThreads)
 conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ CUtensorMap tmA,
                  const __grid_constant__ CUtensorMap tmW) {
-  constexpr int ROW_BYTES = KC * 2;
+  constexpr int NMMA = RB / 32;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_w = smem_base;                                   // [n_taps][b_stride] resident weights
@@ -564,8 +358,6 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (p.pdl) {
-    // programmatic dependent launch: everything above (barrier init, TMEM alloc, tensor-map prefetch) overlapped
-    // the tail of the producer grid; its results are only touched below this point
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
@@ -585,7 +377,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer: resident weights once, then one halo box per tile =====
-      tc::mbar_expect_tx(w_bar, (uint32_t)(p.n_taps * p.N_tile * ROW_BYTES));
+      tc::mbar_expect_tx(w_bar, (uint32_t)(p.n_taps * p.N_tile * RB));
       for (int tp = 0; tp < p.n_taps; ++tp)
         tc::tma_load_2d(smem_w + (uint32_t)tp * p.b_stride, &tmW, w_bar, 0, tp * p.N_tile);
       int s = 0;
@@ -604,8 +396,8 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      const uint32_t idesc = tc::make_idesc_bf16(128, p.N_tile);
-      const uint64_t db_w = tc::make_sdesc(smem_w, ROW_BYTES);
+      const uint32_t idesc = tc::Mma<T>::idesc(128, p.N_tile);
+      const uint64_t db_w = tc::make_sdesc(smem_w, RB);
       const int w_step16 = p.b_stride / 16;
       tc::mbar_wait(w_bar, 0);
       int s = 0;
@@ -620,22 +412,22 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
         if (p.trace && blockIdx.x == 0 && j < 64) p.trace[j * 8 + 2] = clock64();
         // descriptors advance by plain 64-bit adds on the 16-byte-unit address field (smem < 256 KB: no carry out
         // of the 14-bit field), so the issue loop is ~4 instructions per tcgen05.mma
-        const uint64_t da_stage = tc::make_sdesc(smem_a + (uint32_t)s * p.a_stage_bytes, ROW_BYTES);
+        const uint64_t da_stage = tc::make_sdesc(smem_a + (uint32_t)s * p.a_stage_bytes, RB);
         for (int m = 0; m < p.nM; ++m) {
           const uint32_t d_tmem = tmem_base + set * (uint32_t)p.set_stride + (uint32_t)(m * p.N_tile);
-          const uint64_t da_m = da_stage + (uint64_t)(m * (128 * ROW_BYTES / 16));
+          const uint64_t da_m = da_stage + (uint64_t)(m * (128 * RB / 16));
           {
             const uint64_t da = da_m + (uint64_t)p.tap_off16[0];
-            tc::mma_bf16_imm<0>(d_tmem, da, db_w, idesc);
+            tc::Mma<T>::template issue<0>(d_tmem, da, db_w, idesc);
 #pragma unroll
-            for (int k = 1; k < KC / 16; ++k) tc::mma_bf16_imm<1>(d_tmem, da + 2 * k, db_w + 2 * k, idesc);
+            for (int k = 1; k < NMMA; ++k) tc::Mma<T>::template issue<1>(d_tmem, da + 2 * k, db_w + 2 * k, idesc);
           }
 #pragma unroll 3
           for (int tp = 1; tp < p.n_taps; ++tp) {
             const uint64_t da = da_m + (uint64_t)p.tap_off16[tp];
             const uint64_t db = db_w + (uint64_t)(tp * w_step16);
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k) tc::mma_bf16_imm<1>(d_tmem, da + 2 * k, db + 2 * k, idesc);
+            for (int k = 0; k < NMMA; ++k) tc::Mma<T>::template issue<1>(d_tmem, da + 2 * k, db + 2 * k, idesc);
           }
         }
         tc::mma_commit(empty_bar + 8u * s);
@@ -661,9 +453,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
       tc::mbar_wait(tfull_bar + 8u * set, use & 1u);
       tc::fence_after_sync();
       if (tracer && j < 64) p.trace[j * 8 + 5] = clock64();
-      // one group per M tile; with a single M tile (x-packed plans) the two groups split its channels instead
-      const bool split_c = XP && p.nM == 1 && (p.CP & 31) == 0;
-      for (int m = split_c ? 0 : half; m < p.nM; m += split_c ? 1 : 2) {
+      for (int m = half; m < p.nM; m += 2) {   // one epilogue group per M tile parity
         const int R = p.R0 + m * 128 + q * 32 + lane;
         const int pw = R % p.PW;
         const int phh = (R / p.PW) % p.PH;
@@ -674,26 +464,10 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
                            pw < p.hw + p.BW && od < p.D && oh < p.H && ow < p.W;
         const uint32_t taddr = tmem_base + set * (uint32_t)p.set_stride + (uint32_t)(m * p.N_tile) +
                                ((uint32_t)(q * 32) << 16);
-        if constexpr (XP) {
-          // lane == pw (PW == 32, R0 a multiple of 32): neighbours along W are the neighbouring lanes
-          const int cb = split_c ? half * (p.CP >> 1) : 0;
-          const int ce = split_c ? cb + (p.CP >> 1) : p.CP;
-          for (int c0 = cb; c0 < ce; c0 += 16) {
-            float lo[16], v[16], hi[16];
-            tc::tmem_ld16(taddr + (uint32_t)c0, lo);
-            tc::tmem_ld16(taddr + (uint32_t)(p.CP + c0), v);
-            tc::tmem_ld16(taddr + (uint32_t)(2 * p.CP + c0), hi);
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              v[i] += __shfl_up_sync(0xffffffffu, lo[i], 1) + __shfl_down_sync(0xffffffffu, hi[i], 1);
-            if (valid) conv_epilogue_row<16>(p.epi, b, od, oh, ow, c0, v);
-          }
-        } else {
-          for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
-            float v[16];
-            tc::tmem_ld16(taddr + (uint32_t)c0, v);
-            if (valid) conv_epilogue_row<16>(p.epi, b, od, oh, ow, c0, v);
-          }
+        for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(taddr + (uint32_t)c0, v);
+          if (valid) conv_epilogue_row<T, 16>(p.epi, b, od, oh, ow, c0, v);
         }
       }
       tc::fence_before_sync();
@@ -714,17 +488,18 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
 struct SimtParams {
   ConvEpi epi;
   int n_src, n_taps;
-  const __nv_bfloat16* src[OCCD_CONV_MAX_SRC];
+  const void* src[OCCD_CONV_MAX_SRC];
   int src_C[OCCD_CONV_MAX_SRC], src_cstride[OCCD_CONV_MAX_SRC], src_coff[OCCD_CONV_MAX_SRC];
   int ID, IH, IW, src_d0;
   int stride[3];
-  const __nv_bfloat16* weight;
+  const void* weight;
   int Cout_pad, Kpad;
   int w_batch_rows;
   signed char tap_src[OCCD_CONV_MAX_TAPS];
   short tap_dz[OCCD_CONV_MAX_TAPS], tap_dy[OCCD_CONV_MAX_TAPS], tap_dx[OCCD_CONV_MAX_TAPS];
 };
 
+template <typename T>
 __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ SimtParams p) {
   const int ngroups = p.epi.Cout_store / 8;
   const long long total = (long long)p.epi.B * p.epi.OD * p.epi.OH * p.epi.OW * ngroups;
@@ -745,13 +520,14 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ 
     const int ih = oh * p.stride[1] + p.tap_dy[tp];
     const int iw = ow * p.stride[2] + p.tap_dx[tp];
     if (id < 0 || id >= p.ID || ih < 0 || ih >= p.IH || iw < 0 || iw >= p.IW) continue;
-    const __nv_bfloat16* in =
-        p.src[s] + ((((long long)b * p.ID + id) * p.IH + ih) * p.IW + iw) * p.src_cstride[s] + p.src_coff[s];
-    const __nv_bfloat16* w = p.weight + ((long long)b * p.w_batch_rows + (long long)tp * p.Cout_pad + g * 8) * p.Kpad;
+    const T* in = reinterpret_cast<const T*>(p.src[s]) +
+                  ((((long long)b * p.ID + id) * p.IH + ih) * p.IW + iw) * p.src_cstride[s] + p.src_coff[s];
+    const T* w = reinterpret_cast<const T*>(p.weight) +
+                 ((long long)b * p.w_batch_rows + (long long)tp * p.Cout_pad + g * 8) * p.Kpad;
     const int C = p.src_C[s];
     for (int c = 0; c < C; c += 8) {
       float x[8];
-      unpack8(*reinterpret_cast<const uint4*>(in + c), x);
+      Elem<T>::ld8(in + c, x);
       if (c + 8 > C) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -760,13 +536,13 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ 
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float wv[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(w + (long long)j * p.Kpad + c)), wv);
+        Elem<T>::ld8_nc(w + (long long)j * p.Kpad + c, wv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[j] = fmaf(x[i], wv[i], acc[j]);
       }
     }
   }
-  conv_epilogue_row<8>(p.epi, b, od, oh, ow, g * 8, acc);
+  conv_epilogue_row<T, 8>(p.epi, b, od, oh, ow, g * 8, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -788,11 +564,31 @@ EncodeTiledFn get_encode_fn() {
 
 int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+// K chunk (channels) for a source of C channels: the smallest swizzled row (32 / 64 / 128 bytes) that holds it,
+// else the 128-byte row
+int chunk_channels(int C, int esize) {
+  for (int rb = 32; rb <= 128; rb *= 2)
+    if (C <= rb / esize) return rb / esize;
+  return 128 / esize;
+}
+
+long long* g_trace_buf = nullptr;
+
 }  // namespace
+
+// debug hook (tools/conv_trace.py): plans created while a buffer is set record per-role clock64 stamps of CTA 0
+// into it ([64 tiles][8] int64, device memory owned by the caller); NULL switches tracing off again
+extern "C" int occd_conv_debug_trace(long long* device_buf) {
+  g_trace_buf = device_buf;
+  return OCCD_OK;
+}
 
 struct occd_conv_plan {
   int impl;
-  int kc;
+  int dtype;
+  int esize;
+  int kc;   // channels per K chunk
+  int rb;   // bytes per K chunk row (kc * esize): 128 / 64 / 32 == the swizzle mode
   TcParams tc;
   HaloParams halo;
   SimtParams simt;
@@ -809,37 +605,28 @@ static int fill_epi(const occd_conv_desc* d, ConvEpi* e) {
   e->Cout = d->Cout;
   e->Cout_store = round_up(d->Cout, 8);
   e->bias = d->bias;
-  e->out0 = reinterpret_cast<__nv_bfloat16*>(d->out0);
+  e->out0 = d->out0;
   e->out0_cstride = d->out0_cstride; e->out0_coff = d->out0_coff;
   e->act = d->act;
-  e->res1 = reinterpret_cast<const __nv_bfloat16*>(d->res1);
+  e->out0_exact = d->out0_exact;
+  e->res1 = d->res1;
   e->res1_cstride = d->res1_cstride; e->res1_coff = d->res1_coff;
-  e->res2 = reinterpret_cast<const __nv_bfloat16*>(d->res2);
+  e->res2 = d->res2;
   e->res2_cstride = d->res2_cstride; e->res2_coff = d->res2_coff; e->res2_post = d->res2_post;
   e->out1_mode = d->out1_mode; e->out1 = d->out1;
   e->out1_cstride = d->out1_cstride; e->out1_coff = d->out1_coff; e->out1_C = d->out1_C;
-  {
-    // experiment hook OCCD_EPI_WIDE=1: 256-bit epilogue loads/stores where every channels-last window involved is
-    // 32-byte aligned (buffers come from the caching allocator: 512-byte aligned bases)
-    static const int want = [] { const char* v = getenv("OCCD_EPI_WIDE"); return (v && atoi(v) == 1) ? 1 : 0; }();
-    auto ok = [](const void* p, int cstride, int coff) {
-      return !p || (cstride % 16 == 0 && coff % 16 == 0 && (reinterpret_cast<uintptr_t>(p) & 31u) == 0);
-    };
-    e->wide = want && ok(d->out0, d->out0_cstride, d->out0_coff) && ok(d->res1, d->res1_cstride, d->res1_coff) &&
-              ok(d->res2, d->res2_cstride, d->res2_coff) &&
-              (d->out1_mode != OCCD_OUT1_BF16_CL || ok(d->out1, d->out1_cstride, d->out1_coff));
-  }
   return 0;
 }
 
-
-// OCCD_PDL=1: conv launches carry cudaLaunchAttributeProgrammaticStreamSerialization and the kernels wait on
-// griddepcontrol after their prologue (off by default: not yet timed on a B200)
+// Programmatic dependent launch: conv launches carry cudaLaunchAttributeProgrammaticStreamSerialization and the
+// kernels wait on griddepcontrol after their prologue (barrier init, TMEM alloc, tensor-map prefetch overlap the
+// tail of the previous grid).  Measured on B200 (round 2, profiles/r02_ab_experiments.txt): 1.0 % of the config-2
+// forward, results bit-identical.  OCCD_PDL=0 switches it off.
 static int pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("OCCD_PDL");
-    v = (e && atoi(e) == 1) ? 1 : 0;
+    v = (e && atoi(e) == 0) ? 0 : 1;
   }
   return v;
 }
@@ -860,22 +647,21 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, int threads, 
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-static int n_sms_cached() {
-  static int n_sms = 0;
-  if (n_sms == 0) {
-    int dev = 0;
-    cudaDeviceProp prop;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess)
-      n_sms = prop.multiProcessorCount;
-    else
-      n_sms = 148;
+static int n_sms_current() {
+  static int n_sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (n_sms[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n_sms[dev] = v;
+    else n_sms[dev] = 148;
   }
-  return n_sms;
+  return n_sms[dev];
 }
 
 // Halo-tile plan: stride-1 "same" convolution whose taps are {-d,0,d} offsets, one source, one k-chunk, one N tile.
-// halo_geometry is pure host arithmetic (tests/host_emul/ runs it without a GPU); halo_encode builds the tensor maps.
-static int halo_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
+// halo_geometry is pure host arithmetic; halo_encode builds the tensor maps.
+static int halo_geometry(const occd_conv_desc* d, occd_conv_plan* pl) {
 #define HALO_REQUIRE(cond, msg) do { if (!(cond)) { occd_set_last_error("occd_conv_plan_create(halo): " msg); return OCCD_ERR_UNSUPPORTED; } } while (0)
   HALO_REQUIRE(d->n_src == 1, "one source only");
   HALO_REQUIRE(d->stride[0] == 1 && d->stride[1] == 1 && d->stride[2] == 1, "stride must be 1");
@@ -884,7 +670,8 @@ static int halo_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
   HALO_REQUIRE(d->OD + 2 * d->src_d0 == d->ID && d->OH == d->IH && d->OW == d->IW,
                "output grid must equal the input grid (plus symmetric halo margins)");
   HALO_REQUIRE(d->n_taps <= 27, "at most 27 taps");
-  HALO_REQUIRE(d->src_C[0] <= 64 && d->Cout_pad <= 128, "channel counts too large for the resident-weight scheme");
+  HALO_REQUIRE(d->src_C[0] <= 128 / pl->esize && d->Cout_pad <= 128,
+               "channel counts too large for the resident-weight scheme (one K chunk)");
   int dil = 0;
   for (int i = 0; i < d->n_taps; ++i) {
     const int o[3] = {abs(d->taps[i].dz), abs(d->taps[i].dy), abs(d->taps[i].dx)};
@@ -898,55 +685,39 @@ static int halo_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
     if (d->taps[i].dy) hal[1] = 1;
     if (d->taps[i].dx) hal[2] = 1;
   }
-  if (xp) {
-    // x-packed: the taps must come as lexicographic (dz, dy) groups of three W taps -d, 0, +d
-    HALO_REQUIRE(hal[2] == 1 && d->n_taps % 3 == 0, "x-packed: taps along W required");
-    for (int i = 0; i < d->n_taps; i += 3)
-      HALO_REQUIRE(d->taps[i].dx == -dil && d->taps[i + 1].dx == 0 && d->taps[i + 2].dx == dil &&
-                   d->taps[i].dz == d->taps[i + 1].dz && d->taps[i].dz == d->taps[i + 2].dz &&
-                   d->taps[i].dy == d->taps[i + 1].dy && d->taps[i].dy == d->taps[i + 2].dy,
-                   "x-packed: taps must be ordered (dz, dy) groups of dx = -d, 0, +d");
-    HALO_REQUIRE(3 * d->Cout_pad <= 256, "x-packed: 3 * Cout_pad must fit one MMA (N <= 256)");
-  }
   HaloParams& h = pl->halo;
   fill_epi(d, &h.epi);
-  const int C = d->src_C[0];
-  const int KC = C > 32 ? 64 : (C > 16 ? 32 : 16);
+  const int KC = chunk_channels(d->src_C[0], pl->esize);
   HALO_REQUIRE(d->Kpad == KC, "Kpad must equal the k-chunk");
   pl->kc = KC;
-  const int row_bytes = KC * 2;
+  pl->rb = KC * pl->esize;
+  const int row_bytes = pl->rb;
   h.d = dil; h.D = d->OD; h.H = d->IH; h.W = d->IW;
   h.src_d0 = d->src_d0;
   h.hd = hal[0]; h.hh = hal[1]; h.hw = hal[2];
-  h.n_taps = xp ? d->n_taps / 3 : d->n_taps;   // MMA groups per M tile
-  h.CP = d->Cout_pad;
-  h.N_tile = xp ? 3 * d->Cout_pad : d->Cout_pad;
+  h.n_taps = d->n_taps;
+  h.N_tile = d->Cout_pad;
   h.b_stride = round_up(h.N_tile * row_bytes, 1024);
   h.w_bytes = h.n_taps * h.b_stride;
   HALO_REQUIRE(h.w_bytes <= 112 * 1024, "weights do not fit in shared memory");
   const int sD = (d->OD + dil - 1) / dil, sH = (d->IH + dil - 1) / dil, sW = (d->IW + dil - 1) / dil;
   const int smem_total = 224 * 1024 - h.w_bytes - 2048;
   // W extent of the box: the whole sub-sampled line when it fits, else equal splits of at most 62
-  // x-packed: the box is exactly one warp wide (30 outputs + 2 halo columns)
-  const int nW = xp ? (sW + 29) / 30 : (sW + 61) / 62;
-  const int BW = xp ? 30 : (sW + nW - 1) / nW;
+  const int nW = (sW + 61) / 62;
+  const int BW = (sW + nW - 1) / nW;
   long long best_cost = -1;
-  // x-packed tiles finish their MMAs in ~1.5 k cycles per M tile, about one TMA round trip: ask for a ring of at
-  // least 3 stages first (min_stages pass 3), and only if no tile shape allows that accept 2
-  for (int min_stages = xp ? 3 : 2; min_stages >= 2 && best_cost < 0; --min_stages)
   for (int BD = 1; BD <= (hal[0] ? 4 : 1); ++BD)
     for (int BH = 1; BH <= sH && BH <= 96; ++BH) {
       const int PD = BD + 2 * hal[0], PH = BH + 2 * hal[1], PW = BW + 2 * hal[2];
       if ((PW - 1) * dil + 1 > 256 || (PH - 1) * dil + 1 > 256 || (PD - 1) * dil + 1 > 256) continue;
-      // x-packed: M tiles cover whole box rows (columns 0..31), so lanes and box columns coincide
-      const int R0 = (hal[0] * PH + hal[1]) * PW + (xp ? 0 : hal[2]);
-      const int Rend = ((BD - 1 + hal[0]) * PH + (BH - 1 + hal[1])) * PW + (xp ? PW - 1 : BW - 1 + hal[2]);
+      const int R0 = (hal[0] * PH + hal[1]) * PW + hal[2];
+      const int Rend = ((BD - 1 + hal[0]) * PH + (BH - 1 + hal[1])) * PW + BW - 1 + hal[2];
       const int nM = (Rend - R0 + 1 + 127) / 128;
       if (nM * h.N_tile > 256) continue;
       int rows_alloc = PD * PH * PW;
       if (R0 + nM * 128 + R0 > rows_alloc) rows_alloc = R0 + nM * 128 + R0;
       const int stage = round_up(rows_alloc * row_bytes, 1024);
-      if (min_stages * stage > smem_total) continue;
+      if (2 * stage > smem_total) continue;
       if (2 * BD * BH * BW < nM * 128) continue;  // < 50 % useful MMA rows: the per-tap kernel is the better choice
       const long long tiles = (long long)((sD + BD - 1) / BD) * ((sH + BH - 1) / BH) * nW;
       const long long cost = tiles * nM * 1000 + tiles;  // MMA work first, then tile count
@@ -964,55 +735,56 @@ static int halo_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
   h.set_stride = 32;
   while (h.set_stride < h.nM * h.N_tile) h.set_stride *= 2;
   h.tmem_cols = 2 * h.set_stride;
-  if (xp) {
-    for (int g = 0; g < h.n_taps; ++g)   // the group's A rows are NOT shifted along W: the epilogue shifts instead
-      h.tap_off16[g] = (h.R0 + ((d->taps[3 * g].dz / dil) * h.PH + d->taps[3 * g].dy / dil) * h.PW) * row_bytes / 16;
-  } else {
-    for (int i = 0; i < d->n_taps; ++i)
-      h.tap_off16[i] = (h.R0 + ((d->taps[i].dz / dil) * h.PH + d->taps[i].dy / dil) * h.PW + d->taps[i].dx / dil) *
-                       row_bytes / 16;
-  }
-  { const char* e = getenv("OCCD_HALO_BO"); h.bo_mode = e ? atoi(e) : 0; }  // measured on B200: absolute address bits
-  { const char* e = getenv("OCCD_CONV_TRACE_PTR"); h.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
+  for (int i = 0; i < d->n_taps; ++i)
+    h.tap_off16[i] = (h.R0 + ((d->taps[i].dz / dil) * h.PH + d->taps[i].dy / dil) * h.PW + d->taps[i].dx / dil) *
+                     row_bytes / 16;
+  h.trace = g_trace_buf;
   h.pdl = pdl_enabled();
   pl->smem = (size_t)h.w_bytes + (size_t)h.stages * h.a_stage_bytes + 128 + 1024;
   const long long num_tiles = (long long)d->B * dil * dil * dil * h.tilesD * h.tilesH * h.tilesW;
   HALO_REQUIRE(num_tiles < 2147483647LL, "too many tiles");
-  const int n_sms = n_sms_cached();
+  const int n_sms = n_sms_current();
   pl->grid = dim3((unsigned)(num_tiles < n_sms ? num_tiles : n_sms));
 #undef HALO_REQUIRE
   return OCCD_OK;
 }
 
+static CUtensorMapSwizzle swizzle_for(int rb) {
+  return rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+static CUtensorMapDataType tm_dtype(int dtype) {
+  return dtype == OCCD_DTYPE_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
+
 static int halo_encode(const occd_conv_desc* d, occd_conv_plan* pl) {
   const HaloParams& h = pl->halo;
-  const int KC = pl->kc, C = d->src_C[0], dil = h.d;
+  const int KC = pl->kc, C = d->src_C[0], dil = h.d, es = pl->esize;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     occd_set_last_error("occd_conv_plan_create: cuTensorMapEncodeTiled unavailable (no CUDA driver / GPU?)");
     return OCCD_ERR_CUDA;
   }
-  const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                         : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUtensorMapSwizzle sw = swizzle_for(pl->rb);
   {
-    const cuuint64_t cs = (cuuint64_t)d->src_cstride[0] * 2;
+    const cuuint64_t cs = (cuuint64_t)d->src_cstride[0] * es;
     cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)d->IW, (cuuint64_t)d->IH, (cuuint64_t)d->ID, (cuuint64_t)d->B};
     cuuint64_t gstr[4] = {cs, cs * d->IW, cs * d->IW * d->IH, cs * d->IW * d->IH * d->ID};
     cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)((h.PW - 1) * dil + 1), (cuuint32_t)((h.PH - 1) * dil + 1),
                          (cuuint32_t)((h.PD - 1) * dil + 1), 1};
     cuuint32_t estr[5] = {1, (cuuint32_t)dil, (cuuint32_t)dil, (cuuint32_t)dil, 1};
-    void* base = (void*)((const char*)d->src[0] + (size_t)d->src_coff[0] * 2);
-    CUresult r = enc(&pl->tmA[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr,
+    void* base = (void*)((const char*)d->src[0] + (size_t)d->src_coff[0] * es);
+    CUresult r = enc(&pl->tmA[0], tm_dtype(pl->dtype), 5, base, gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { occd_set_last_error("occd_conv_plan_create(halo): cuTensorMapEncodeTiled(source) failed"); return OCCD_ERR_CUDA; }
   }
   {
     cuuint64_t gdim[2] = {(cuuint64_t)d->Kpad, (cuuint64_t)d->n_taps * d->Cout_pad};
-    cuuint64_t gstr[1] = {(cuuint64_t)d->Kpad * 2};
+    cuuint64_t gstr[1] = {(cuuint64_t)d->Kpad * es};
     cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)h.N_tile};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&pl->tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d->weight, gdim, gstr, box, estr,
+    CUresult r = enc(&pl->tmW, tm_dtype(pl->dtype), 2, (void*)d->weight, gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { occd_set_last_error("occd_conv_plan_create(halo): cuTensorMapEncodeTiled(weights) failed"); return OCCD_ERR_CUDA; }
@@ -1020,27 +792,18 @@ static int halo_encode(const occd_conv_desc* d, occd_conv_plan* pl) {
   return OCCD_OK;
 }
 
-static int build_halo_plan(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
-  const int rc = halo_geometry(d, pl, xp);
-  return rc != OCCD_OK ? rc : halo_encode(d, pl);
-}
-
-// Per-tap (TC) plan: host arithmetic only (tests/host_emul/ runs it without a GPU); tc_encode builds the tensor maps.
-// mode: 0 = per-tap kernel, 1 = x-packed (TCX), 2 = two M tiles per weight tile (M2)
-static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, int mode) {
-  const bool xp = mode == 1, m2 = mode == 2;
-  if (m2 && d->weight_per_image) {
-    occd_set_last_error("occd_conv_plan_create(m2): per-image weight sets are not supported (a pair may span two images)");
-    return OCCD_ERR_UNSUPPORTED;
-  }
+// Per-tap (TC) plan: host arithmetic only; tc_encode builds the tensor maps.  xp: x-packed variant (TCX)
+static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
   int maxC = 0;
   for (int s = 0; s < d->n_src; ++s) maxC = d->src_C[s] > maxC ? d->src_C[s] : maxC;
   TcParams& t = pl->tc;
   fill_epi(d, &t.epi);
-  const int KC = maxC > 32 ? 64 : (maxC > 16 ? 32 : 16);
+  const int KC = chunk_channels(maxC, pl->esize);
   pl->kc = KC;
+  pl->rb = KC * pl->esize;
+  const int RB = pl->rb;
   if (d->Kpad % KC != 0) {
-    occd_set_last_error("occd_conv_plan_create: Kpad must be a multiple of the K chunk (64/32/16)");
+    occd_set_last_error("occd_conv_plan_create: Kpad must be a multiple of the K chunk");
     return OCCD_ERR_ARG;
   }
   t.n_taps = xp ? d->n_taps / 3 : d->n_taps;  // x-packed: one pipeline item per (source, dz, dy) group
@@ -1049,8 +812,8 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, int mode) {
   for (int s = 0; s < OCCD_CONV_MAX_SRC; ++s) t.n_kchunks[s] = s < d->n_src ? (d->src_C[s] + KC - 1) / KC : 0;
   for (int i = 0; i < 3; ++i) t.stride[i] = d->stride[i];
   if (xp) {
-    // x-packed (see conv_halo_kernel): groups of three W taps -1, 0, +1 share one MMA with N = 3 * Cout_pad; the
-    // tile is 32 positions wide (30 outputs + one halo column each side) so that lane == column in the epilogue
+    // groups of three W taps -1, 0, +1 share one MMA with N = 3 * Cout_pad; the tile is 32 positions wide (30
+    // outputs + one halo column each side) so that lane == column in the epilogue
     if (d->n_taps % 3 || d->stride[2] != 1 || 3 * d->Cout_pad > 256) {
       occd_set_last_error("occd_conv_plan_create(tcx): needs W-tap triples, W stride 1 and 3 * Cout_pad <= 256");
       return OCCD_ERR_UNSUPPORTED;
@@ -1073,14 +836,12 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, int mode) {
       if (best < 0 || vol < best) { best = vol; t.TH = th; t.TD = tdd; }
     }
   } else {
-  for (int i = 0; i < d->n_taps; ++i) {
-    t.tap_src[i] = (signed char)d->taps[i].src;
-    t.tap_dz[i] = (short)d->taps[i].dz; t.tap_dy[i] = (short)d->taps[i].dy; t.tap_dx[i] = (short)d->taps[i].dx;
-  }
-  // tile box (TD,TH,TW), product 128, minimal padded volume; ties -> widest TW
-  {
-    // minimal padded volume, but a wide innermost extent (long contiguous TMA runs, coalesced stores) wins
-    // whenever it costs < 4% extra positions
+    for (int i = 0; i < d->n_taps; ++i) {
+      t.tap_src[i] = (signed char)d->taps[i].src;
+      t.tap_dz[i] = (short)d->taps[i].dz; t.tap_dy[i] = (short)d->taps[i].dy; t.tap_dx[i] = (short)d->taps[i].dx;
+    }
+    // tile box (TD,TH,TW), product 128: minimal padded volume, but a wide innermost extent (long contiguous TMA
+    // runs, coalesced stores) wins whenever it costs < 4% extra positions
     long long best = -1;
     for (int pass = 0; pass < 2; ++pass)
       for (int tw = 128; tw >= 1; tw >>= 1)
@@ -1096,7 +857,6 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, int mode) {
           }
         }
   }
-  }
   t.TWv = xp ? 30 : t.TW;
   t.tiles_w = (d->OW + t.TWv - 1) / t.TWv; t.tiles_h = (d->OH + t.TH - 1) / t.TH; t.tiles_d = (d->OD + t.TD - 1) / t.TD;
   // N tile: largest divisor of Cout_pad that is a multiple of 16 and <= 256
@@ -1108,38 +868,31 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, int mode) {
     // small-M layers (late encoder stages): a narrower N tile that still keeps >= 64 columns trades some A
     // re-reads for enough tiles to occupy every SM
     const long long m_tiles0 = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w;
-    const int n_sms = n_sms_cached();
+    const int n_sms = n_sms_current();
     int best = t.N_tile;
     for (int n = t.N_tile; n >= 64; n -= 16) {
       if (d->Cout_pad % n) continue;
       best = n;
       if (m_tiles0 * (d->Cout_pad / n) >= n_sms) break;
     }
-    if (!m2 && m_tiles0 * (d->Cout_pad / t.N_tile) < n_sms) t.N_tile = best;
+    if (m_tiles0 * (d->Cout_pad / t.N_tile) < n_sms) t.N_tile = best;
   }
   if (xp) t.N_tile = 3 * d->Cout_pad;  // one N tile: the three taps' weights stacked
   t.tmem_cols = 32;
   while (t.tmem_cols < t.N_tile) t.tmem_cols *= 2;
-  { const char* e = getenv("OCCD_CONV_TRACE_PTR"); t.trace = e ? (long long*)strtoull(e, nullptr, 0) : nullptr; }
+  t.trace = g_trace_buf;
   t.tmem_cols *= 2;  // two accumulators: the epilogue of tile j overlaps the MMAs of tile j+1
-  t.m2_sets = 0;
-  if (m2) {
-    // {D0, D1} per set; a second set (epilogue / MMA overlap across pairs) when it fits the 512 columns
-    t.m2_sets = 4 * t.N_tile <= 512 ? 2 : 1;
-    t.tmem_cols = 32;
-    while (t.tmem_cols < t.m2_sets * 2 * t.N_tile) t.tmem_cols *= 2;
-  }
   t.pdl = pdl_enabled();
-  t.a_bytes = 128 * KC * 2;
-  t.b_bytes = t.N_tile * KC * 2;
+  t.a_bytes = 128 * RB;
+  t.b_bytes = t.N_tile * RB;
   t.b_stride = round_up(t.b_bytes, 1024);
-  const int stage_bytes = (m2 ? 2 : 1) * t.a_bytes + t.b_stride;
+  const int stage_bytes = t.a_bytes + t.b_stride;
   int total_iters = 0;
   for (int i = 0; i < t.n_taps; ++i) total_iters += t.n_kchunks[t.tap_src[i]];
   const int budget = 200 * 1024;  // persistent kernel: one CTA per SM owns the shared memory
   // (tap, k-chunk) items per pipeline stage: the single-thread producer/MMA hand-off costs ~0.25 us, so a stage
   // must carry >= ~512 tensor-pipe cycles of work (or up to 9 items) while leaving >= 3 stages in flight
-  const int mma_cycles_per_item = (m2 ? 2 : 1) * (KC / 16) * (128 * t.N_tile / 256);
+  const int mma_cycles_per_item = (RB / 32) * (128 * t.N_tile / 256);
   int group = (512 + mma_cycles_per_item - 1) / mma_cycles_per_item;
   if (group > 9) group = 9;
   if (group > total_iters) group = total_iters;
@@ -1149,61 +902,48 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, int mode) {
   if (stages > kMaxStages) stages = kMaxStages;
   const int groups_per_tile = (total_iters + group - 1) / group;
   {
-    // Ring depth: two tiles' worth of stage groups, but never fewer than 8 stages when they fit -- a conv with one
-    // item per tile (1x1 layers, 16-channel bottleneck convs) otherwise keeps only two TMA loads in flight and runs
-    // at two tiles per load latency (~0.75 us per tile in the round-1 plan profile).  OCCD_TC_STAGES_LEGACY=1
-    // restores the old "2 x groups per tile" rule for A/B runs.
-    static const bool legacy = [] { const char* e = getenv("OCCD_TC_STAGES_LEGACY"); return e && atoi(e) == 1; }();
+    // ring depth: two tiles' worth of stage groups, but never fewer than 8 stages when they fit (a conv with one
+    // item per tile otherwise keeps only two TMA loads in flight)
     int cap = 2 * groups_per_tile;
-    if (!legacy && cap < 8) cap = 8;
+    if (cap < 8) cap = 8;
     if (stages > cap) stages = cap;
-  }
-  {
-    // experiment hook: OCCD_TC_STAGES_MIN=n keeps at least n stages (when they fit) so that the producer of a
-    // one-item-per-tile conv (1x1 layers) can run more than two tiles ahead
-    static const int min_stages = [] { const char* e = getenv("OCCD_TC_STAGES_MIN"); return e ? atoi(e) : 0; }();
-    const int fit = budget / (group * stage_bytes);
-    if (min_stages > stages) stages = min_stages < fit ? min_stages : fit;
-    if (stages > kMaxStages) stages = kMaxStages;
   }
   if (stages < 1) stages = 1;
   t.stages = stages;
   pl->smem = (size_t)stages * group * stage_bytes + 16 * kMaxStages + 64 + 1024;  // + barriers + alignment slack
   const long long m_tiles = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w;
-  const long long all_tiles = (m2 ? (m_tiles + 1) / 2 : m_tiles) * (xp ? 1 : d->Cout_pad / t.N_tile);
+  const long long all_tiles = m_tiles * (xp ? 1 : d->Cout_pad / t.N_tile);
   if (all_tiles > 2147483647LL) {
     occd_set_last_error("occd_conv_plan_create: too many tiles");
     return OCCD_ERR_UNSUPPORTED;
   }
   t.num_m_tiles = (int)m_tiles;
   {
-    const int n_sms = n_sms_cached();
+    const int n_sms = n_sms_current();
     pl->grid = dim3((unsigned)(all_tiles < n_sms ? all_tiles : n_sms));
   }
-
   return OCCD_OK;
 }
 
 static int tc_encode(const occd_conv_desc* d, occd_conv_plan* pl) {
   const TcParams& t = pl->tc;
-  const int KC = pl->kc;
+  const int KC = pl->kc, es = pl->esize;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     occd_set_last_error("occd_conv_plan_create: cuTensorMapEncodeTiled unavailable (no CUDA driver / GPU?)");
     return OCCD_ERR_CUDA;
   }
-  const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                         : (KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  const CUtensorMapSwizzle sw = swizzle_for(pl->rb);
   for (int s = 0; s < d->n_src; ++s) {
-    const cuuint64_t cs = (cuuint64_t)d->src_cstride[s] * 2;
+    const cuuint64_t cs = (cuuint64_t)d->src_cstride[s] * es;
     cuuint64_t gdim[5] = {(cuuint64_t)d->src_C[s], (cuuint64_t)d->IW, (cuuint64_t)d->IH, (cuuint64_t)d->ID,
                           (cuuint64_t)d->B};
     cuuint64_t gstr[4] = {cs, cs * d->IW, cs * d->IW * d->IH, cs * d->IW * d->IH * d->ID};
     cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)(t.TW * d->stride[2]), (cuuint32_t)(t.TH * d->stride[1]),
                          (cuuint32_t)(t.TD * d->stride[0]), 1};
     cuuint32_t estr[5] = {1, (cuuint32_t)d->stride[2], (cuuint32_t)d->stride[1], (cuuint32_t)d->stride[0], 1};
-    void* base = (void*)((const char*)d->src[s] + (size_t)d->src_coff[s] * 2);
-    CUresult r = enc(&pl->tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr,
+    void* base = (void*)((const char*)d->src[s] + (size_t)d->src_coff[s] * es);
+    CUresult r = enc(&pl->tmA[s], tm_dtype(pl->dtype), 5, base, gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1217,10 +957,10 @@ static int tc_encode(const occd_conv_desc* d, occd_conv_plan* pl) {
   {
     cuuint64_t gdim[2] = {(cuuint64_t)d->Kpad,
                           (cuuint64_t)d->n_taps * d->Cout_pad * (d->weight_per_image ? d->B : 1)};
-    cuuint64_t gstr[1] = {(cuuint64_t)d->Kpad * 2};
+    cuuint64_t gstr[1] = {(cuuint64_t)d->Kpad * es};
     cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)t.N_tile};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&pl->tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d->weight, gdim, gstr, box, estr,
+    CUresult r = enc(&pl->tmW, tm_dtype(pl->dtype), 2, (void*)d->weight, gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1235,6 +975,7 @@ static int tc_encode(const occd_conv_desc* d, occd_conv_plan* pl) {
 
 extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** out) {
   OCCD_CHECK_ARG(d && out, "occd_conv_plan_create: null argument");
+  OCCD_CHECK_ARG(d->dtype == OCCD_DTYPE_F32 || d->dtype == OCCD_DTYPE_BF16, "occd_conv_plan_create: dtype");
   OCCD_CHECK_ARG(d->n_src >= 1 && d->n_src <= OCCD_CONV_MAX_SRC, "occd_conv_plan_create: n_src");
   OCCD_CHECK_ARG(d->n_taps >= 1 && d->n_taps <= OCCD_CONV_MAX_TAPS, "occd_conv_plan_create: n_taps");
   OCCD_CHECK_ARG(d->src_d0 >= 0 && d->src_d0 < d->ID, "occd_conv_plan_create: src_d0");
@@ -1244,16 +985,18 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
   OCCD_CHECK_ARG(d->Kpad > 0 && d->Kpad % 8 == 0, "occd_conv_plan_create: Kpad must be a multiple of 8");
   OCCD_CHECK_ARG(d->weight && d->bias, "occd_conv_plan_create: weight/bias");
   OCCD_CHECK_ARG(d->out0 || d->out1_mode != OCCD_OUT1_NONE, "occd_conv_plan_create: no output");
+  const int es = d->dtype == OCCD_DTYPE_F32 ? 4 : 2;
+  auto aligned = [es](const void* p) { return (reinterpret_cast<uintptr_t>(p) % (8 * es)) == 0; };
   const int cst = round_up(d->Cout, 8);
-  if (d->out0) OCCD_CHECK_ARG(d->out0_coff % 8 == 0 && d->out0_cstride % 8 == 0 && d->out0_coff + cst <= d->out0_cstride,
-                              "occd_conv_plan_create: out0 channel window");
-  if (d->res1) OCCD_CHECK_ARG(d->res1_coff % 8 == 0 && d->res1_cstride % 8 == 0 && d->res1_coff + cst <= d->res1_cstride,
-                              "occd_conv_plan_create: res1 channel window");
-  if (d->res2) OCCD_CHECK_ARG(d->res2_coff % 8 == 0 && d->res2_cstride % 8 == 0 && d->res2_coff + cst <= d->res2_cstride,
-                              "occd_conv_plan_create: res2 channel window");
-  if (d->out1_mode == OCCD_OUT1_BF16_CL)
-    OCCD_CHECK_ARG(d->out1 && d->out1_coff % 8 == 0 && d->out1_cstride % 8 == 0 && d->out1_coff + cst <= d->out1_cstride,
-                   "occd_conv_plan_create: out1 channel window");
+  if (d->out0) OCCD_CHECK_ARG(d->out0_coff % 8 == 0 && d->out0_cstride % 8 == 0 && d->out0_coff + cst <= d->out0_cstride &&
+                              aligned(d->out0), "occd_conv_plan_create: out0 channel window");
+  if (d->res1) OCCD_CHECK_ARG(d->res1_coff % 8 == 0 && d->res1_cstride % 8 == 0 && d->res1_coff + cst <= d->res1_cstride &&
+                              aligned(d->res1), "occd_conv_plan_create: res1 channel window");
+  if (d->res2) OCCD_CHECK_ARG(d->res2_coff % 8 == 0 && d->res2_cstride % 8 == 0 && d->res2_coff + cst <= d->res2_cstride &&
+                              aligned(d->res2), "occd_conv_plan_create: res2 channel window");
+  if (d->out1_mode == OCCD_OUT1_CL)
+    OCCD_CHECK_ARG(d->out1 && d->out1_coff % 8 == 0 && d->out1_cstride % 8 == 0 && d->out1_coff + cst <= d->out1_cstride &&
+                   aligned(d->out1), "occd_conv_plan_create: out1 channel window");
   if (d->out1_mode == OCCD_OUT1_F32_PLANAR)
     OCCD_CHECK_ARG(d->out1 && d->out1_coff + d->Cout <= d->out1_C, "occd_conv_plan_create: out1 planar window");
   for (int i = 0; i < 3; ++i) {
@@ -1262,12 +1005,11 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
   OCCD_CHECK_ARG((long long)(d->OD - 1) * d->omul[0] + d->oadd[0] < d->ODf &&
                  (long long)(d->OH - 1) * d->omul[1] + d->oadd[1] < d->OHf &&
                  (long long)(d->OW - 1) * d->omul[2] + d->oadd[2] < d->OWf, "occd_conv_plan_create: output mapping");
-  int maxC = 0;
   for (int s = 0; s < d->n_src; ++s) {
     OCCD_CHECK_ARG(d->src[s] && d->src_C[s] > 0 && d->src_cstride[s] % 8 == 0 && d->src_coff[s] % 8 == 0 &&
-                   d->src_coff[s] + d->src_C[s] <= d->src_cstride[s], "occd_conv_plan_create: source channel window");
+                   d->src_coff[s] + d->src_C[s] <= d->src_cstride[s] && aligned(d->src[s]),
+                   "occd_conv_plan_create: source channel window");
     OCCD_CHECK_ARG(d->src_C[s] <= d->Kpad, "occd_conv_plan_create: Kpad smaller than a source");
-    maxC = d->src_C[s] > maxC ? d->src_C[s] : maxC;
   }
   for (int i = 0; i < d->n_taps; ++i) {
     OCCD_CHECK_ARG(d->taps[i].src >= 0 && d->taps[i].src < d->n_src, "occd_conv_plan_create: tap source");
@@ -1275,27 +1017,28 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
                    "occd_conv_plan_create: tap offset");
   }
   OCCD_CHECK_ARG(d->impl == OCCD_CONV_IMPL_TC || d->impl == OCCD_CONV_IMPL_SIMT || d->impl == OCCD_CONV_IMPL_HALO ||
-                 d->impl == OCCD_CONV_IMPL_HALOX || d->impl == OCCD_CONV_IMPL_TCX || d->impl == OCCD_CONV_IMPL_TCM2,
-                 "occd_conv_plan_create: impl");
-  OCCD_CHECK_ARG(!d->weight_per_image || (d->impl != OCCD_CONV_IMPL_HALO && d->impl != OCCD_CONV_IMPL_HALOX),
+                 d->impl == OCCD_CONV_IMPL_TCX, "occd_conv_plan_create: impl");
+  OCCD_CHECK_ARG(!d->weight_per_image || d->impl != OCCD_CONV_IMPL_HALO,
                  "occd_conv_plan_create: per-image weights: TC or SIMT impl");
 
   occd_conv_plan* pl = new (std::nothrow) occd_conv_plan;
   OCCD_CHECK_ARG(pl != nullptr, "occd_conv_plan_create: out of memory");
   memset(pl, 0, sizeof(*pl));
   pl->impl = d->impl;
+  pl->dtype = d->dtype;
+  pl->esize = es;
 
   if (d->impl == OCCD_CONV_IMPL_SIMT) {
     SimtParams& s = pl->simt;
     fill_epi(d, &s.epi);
     s.n_src = d->n_src; s.n_taps = d->n_taps;
     for (int i = 0; i < d->n_src; ++i) {
-      s.src[i] = reinterpret_cast<const __nv_bfloat16*>(d->src[i]);
+      s.src[i] = d->src[i];
       s.src_C[i] = d->src_C[i]; s.src_cstride[i] = d->src_cstride[i]; s.src_coff[i] = d->src_coff[i];
     }
     s.ID = d->ID; s.IH = d->IH; s.IW = d->IW; s.src_d0 = d->src_d0;
     for (int i = 0; i < 3; ++i) s.stride[i] = d->stride[i];
-    s.weight = reinterpret_cast<const __nv_bfloat16*>(d->weight);
+    s.weight = d->weight;
     s.Cout_pad = d->Cout_pad; s.Kpad = d->Kpad;
     s.w_batch_rows = d->weight_per_image ? d->n_taps * d->Cout_pad : 0;
     for (int i = 0; i < d->n_taps; ++i) {
@@ -1308,19 +1051,15 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
     return OCCD_OK;
   }
 
-  if (d->impl == OCCD_CONV_IMPL_HALO || d->impl == OCCD_CONV_IMPL_HALOX) {
-    const int rc = build_halo_plan(d, pl, d->impl == OCCD_CONV_IMPL_HALOX);
-    if (rc != OCCD_OK) { delete pl; return rc; }
-    *out = pl;
-    return OCCD_OK;
-  }
-
-  // ---------------- TC plan (per-tap kernel; TCX: three W taps per MMA) ----------------
-  {
-    int rc = tc_geometry(d, pl, d->impl == OCCD_CONV_IMPL_TCX ? 1 : (d->impl == OCCD_CONV_IMPL_TCM2 ? 2 : 0));
+  int rc;
+  if (d->impl == OCCD_CONV_IMPL_HALO) {
+    rc = halo_geometry(d, pl);
+    if (rc == OCCD_OK) rc = halo_encode(d, pl);
+  } else {
+    rc = tc_geometry(d, pl, d->impl == OCCD_CONV_IMPL_TCX);
     if (rc == OCCD_OK) rc = tc_encode(d, pl);
-    if (rc != OCCD_OK) { delete pl; return rc; }
   }
+  if (rc != OCCD_OK) { delete pl; return rc; }
   *out = pl;
   return OCCD_OK;
 }
@@ -1337,7 +1076,7 @@ extern "C" int occd_conv_plan_info(const occd_conv_plan* pl, int* info) {
     info[6] = (int)pl->grid.x;
     return OCCD_OK;
   }
-  if (pl->impl == OCCD_CONV_IMPL_HALO || pl->impl == OCCD_CONV_IMPL_HALOX) {
+  if (pl->impl == OCCD_CONV_IMPL_HALO) {
     const HaloParams& h = pl->halo;
     info[0] = h.BD; info[1] = h.BH; info[2] = h.BW; info[3] = h.N_tile; info[4] = pl->kc;
     info[5] = h.stages * 100 + h.nM; info[6] = (int)pl->grid.x;
@@ -1345,124 +1084,90 @@ extern "C" int occd_conv_plan_info(const occd_conv_plan* pl, int* info) {
     return OCCD_OK;
   }
   info[0] = pl->tc.TD; info[1] = pl->tc.TH; info[2] = pl->tc.TW; info[3] = pl->tc.N_tile;
-  info[4] = pl->kc; info[5] = pl->tc.stages * 100 + pl->tc.group; info[6] = (int)pl->grid.x; info[7] = pl->tc.num_m_tiles * (pl->tc.Cout_pad / pl->tc.N_tile);
+  info[4] = pl->kc; info[5] = pl->tc.stages * 100 + pl->tc.group; info[6] = (int)pl->grid.x;
+  info[7] = pl->tc.num_m_tiles * (pl->impl == OCCD_CONV_IMPL_TCX ? 1 : pl->tc.Cout_pad / pl->tc.N_tile);
   return OCCD_OK;
 }
 
-template <int KC, bool XP, bool WIDE>
+template <typename T, int RB, bool XP>
 static int launch_tc(const occd_conv_plan* pl, cudaStream_t st) {
   static bool attr_set[64] = {false};  // per instantiation, per device (the attribute is per device)
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KC, XP, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<T, RB, XP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
     attr_set[dev] = true;
   }
   if (pl->tc.pdl) {
-    cudaError_t e = launch_pdl(conv_tc_kernel<KC, XP, WIDE>, pl->grid, kTcThreads, pl->smem, st, pl->tc, pl->tmA[0], pl->tmA[1],
-                               pl->tmA[2], pl->tmW);
+    cudaError_t e = launch_pdl(conv_tc_kernel<T, RB, XP>, pl->grid, kTcThreads, pl->smem, st, pl->tc, pl->tmA[0],
+                               pl->tmA[1], pl->tmA[2], pl->tmW);
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
     return OCCD_OK;
   }
-  conv_tc_kernel<KC, XP, WIDE><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->tc, pl->tmA[0], pl->tmA[1], pl->tmA[2], pl->tmW);
+  conv_tc_kernel<T, RB, XP><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->tc, pl->tmA[0], pl->tmA[1], pl->tmA[2], pl->tmW);
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
 
-template <int KC, bool XP>
+template <typename T, int RB>
 static int launch_halo(const occd_conv_plan* pl, cudaStream_t st) {
   static bool attr_set[64] = {false};  // per device
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<KC, XP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<T, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
     attr_set[dev] = true;
   }
   if (pl->halo.pdl) {
-    cudaError_t e = launch_pdl(conv_halo_kernel<KC, XP>, pl->grid, kTcThreads, pl->smem, st, pl->halo, pl->tmA[0],
+    cudaError_t e = launch_pdl(conv_halo_kernel<T, RB>, pl->grid, kTcThreads, pl->smem, st, pl->halo, pl->tmA[0],
                                pl->tmW);
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
     return OCCD_OK;
   }
-  conv_halo_kernel<KC, XP><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->halo, pl->tmA[0], pl->tmW);
+  conv_halo_kernel<T, RB><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->halo, pl->tmA[0], pl->tmW);
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
 
-template <int KC>
-static int launch_tc_m2(const occd_conv_plan* pl, cudaStream_t st) {
-  static bool attr_set[64] = {false};  // per instantiation, per device
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) dev = 0;
-  if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_m2_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
-    attr_set[dev] = true;
-  }
-  if (pl->tc.pdl) {
-    cudaError_t e = launch_pdl(conv_tc_m2_kernel<KC>, pl->grid, kTcThreads, pl->smem, st, pl->tc, pl->tmA[0],
-                               pl->tmA[1], pl->tmA[2], pl->tmW);
-    if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
+template <typename T>
+static int run_typed(const occd_conv_plan* pl, cudaStream_t st) {
+  if (pl->impl == OCCD_CONV_IMPL_SIMT) {
+    conv_simt_kernel<T><<<pl->grid, 128, 0, st>>>(pl->simt);
+    OCCD_CHECK_LAUNCH();
     return OCCD_OK;
   }
-  conv_tc_m2_kernel<KC><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->tc, pl->tmA[0], pl->tmA[1], pl->tmA[2], pl->tmW);
-  OCCD_CHECK_LAUNCH();
-  return OCCD_OK;
+  if (pl->impl == OCCD_CONV_IMPL_HALO) {
+    switch (pl->rb) {
+      case 128: return launch_halo<T, 128>(pl, st);
+      case 64: return launch_halo<T, 64>(pl, st);
+      case 32: return launch_halo<T, 32>(pl, st);
+    }
+  }
+  if (pl->impl == OCCD_CONV_IMPL_TCX) {
+    switch (pl->rb) {
+      case 128: return launch_tc<T, 128, true>(pl, st);
+      case 64: return launch_tc<T, 64, true>(pl, st);
+      case 32: return launch_tc<T, 32, true>(pl, st);
+    }
+  }
+  if (pl->impl == OCCD_CONV_IMPL_TC) {
+    switch (pl->rb) {
+      case 128: return launch_tc<T, 128, false>(pl, st);
+      case 64: return launch_tc<T, 64, false>(pl, st);
+      case 32: return launch_tc<T, 32, false>(pl, st);
+    }
+  }
+  occd_set_last_error("occd_conv_run: bad plan");
+  return OCCD_ERR_ARG;
 }
 
 extern "C" int occd_conv_run(const occd_conv_plan* pl, void* stream) {
   OCCD_CHECK_ARG(pl != nullptr, "occd_conv_run: null plan");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (pl->impl == OCCD_CONV_IMPL_SIMT) {
-    conv_simt_kernel<<<pl->grid, 128, 0, st>>>(pl->simt);
-    OCCD_CHECK_LAUNCH();
-    return OCCD_OK;
-  }
-  if (pl->impl == OCCD_CONV_IMPL_HALO) {
-    switch (pl->kc) {
-      case 64: return launch_halo<64, false>(pl, st);
-      case 32: return launch_halo<32, false>(pl, st);
-      case 16: return launch_halo<16, false>(pl, st);
-    }
-  }
-  if (pl->impl == OCCD_CONV_IMPL_HALOX) {
-    switch (pl->kc) {
-      case 64: return launch_halo<64, true>(pl, st);
-      case 32: return launch_halo<32, true>(pl, st);
-      case 16: return launch_halo<16, true>(pl, st);
-    }
-  }
-  if (pl->impl == OCCD_CONV_IMPL_TCM2) {
-    switch (pl->kc) {
-      case 64: return launch_tc_m2<64>(pl, st);
-      case 32: return launch_tc_m2<32>(pl, st);
-      case 16: return launch_tc_m2<16>(pl, st);
-    }
-  }
-  if (pl->impl == OCCD_CONV_IMPL_TCX) {
-    switch (pl->kc) {
-      case 64: return launch_tc<64, true, false>(pl, st);
-      case 32: return launch_tc<32, true, false>(pl, st);
-      case 16: return launch_tc<16, true, false>(pl, st);
-    }
-  }
-  if (pl->tc.epi.wide) {   // OCCD_EPI_WIDE=1 and every window 32-byte aligned: 256-bit epilogue instance
-    switch (pl->kc) {
-      case 64: return launch_tc<64, false, true>(pl, st);
-      case 32: return launch_tc<32, false, true>(pl, st);
-      case 16: return launch_tc<16, false, true>(pl, st);
-    }
-  }
-  switch (pl->kc) {
-    case 64: return launch_tc<64, false, false>(pl, st);
-    case 32: return launch_tc<32, false, false>(pl, st);
-    case 16: return launch_tc<16, false, false>(pl, st);
-  }
-  occd_set_last_error("occd_conv_run: bad plan");
-  return OCCD_ERR_ARG;
+  if (pl->dtype == OCCD_DTYPE_F32) return run_typed<float>(pl, st);
+  return run_typed<__nv_bfloat16>(pl, st);
 }

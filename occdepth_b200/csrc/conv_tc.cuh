@@ -115,11 +115,15 @@ __device__ __forceinline__ uint64_t make_sdesc_shifted(uint32_t saddr, uint32_t 
   return d;
 }
 
-// instruction descriptor for kind::f16, BF16 x BF16 -> F32, both operands K-major
-//   bits [4,6) D format (1 = F32)  [7,10) A format (1 = BF16)  [10,13) B format  [15] A major  [16] B major
+// instruction descriptor, both operands K-major, F32 accumulate
+//   bits [4,6) D format (1 = F32)  [7,10) A format  [10,13) B format  [15] A major  [16] B major
 //   bits [17,23) N >> 3            [24,29) M >> 4
+//   A/B format: kind::f16 -> 1 = BF16;  kind::tf32 -> 2 = TF32
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -146,6 +150,37 @@ __device__ __forceinline__ void mma_bf16_imm(uint32_t tmem_d, uint64_t desc_a, u
       "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(ACC)
       : "memory");
 }
+
+// kind::tf32: fp32 containers in shared memory, the tensor core reads the TF32 bits (sign, 8-bit exponent, 10-bit
+// mantissa); one instruction consumes K = 8 elements = 32 bytes per row, the same 32 bytes as 16 bf16
+template <int ACC>
+__device__ __forceinline__ void mma_tf32_imm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(ACC)
+      : "memory");
+}
+
+// element-type dispatch: T = __nv_bfloat16 (kind::f16) or float (kind::tf32); a 32-byte K slice per instruction
+template <typename T> struct Mma;
+template <> struct Mma<__nv_bfloat16> {
+  static __host__ __device__ constexpr uint32_t idesc(int M, int N) { return make_idesc_bf16(M, N); }
+  template <int ACC>
+  static __device__ __forceinline__ void issue(uint32_t d, uint64_t a, uint64_t b, uint32_t id) {
+    mma_bf16_imm<ACC>(d, a, b, id);
+  }
+};
+template <> struct Mma<float> {
+  static __host__ __device__ constexpr uint32_t idesc(int M, int N) { return make_idesc_tf32(M, N); }
+  template <int ACC>
+  static __device__ __forceinline__ void issue(uint32_t d, uint64_t a, uint64_t b, uint32_t id) {
+    mma_tf32_imm<ACC>(d, a, b, id);
+  }
+};
 
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {

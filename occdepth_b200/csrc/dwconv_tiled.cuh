@@ -1,4 +1,5 @@
-// Shared-memory-tiled depthwise KxK conv + folded BN + activation + squeeze (channels-last bf16).
+// Shared-memory-tiled depthwise KxK conv + folded BN + activation + squeeze (channels-last, element type T =
+// __nv_bfloat16 or TF32-valued float -- see Elem<T> in common.cuh).
 // Same contract as dwconv_kernel (effnet_ops.cu); replaces geffnet conv_dw + bn + act (+ the SE squeeze) as
 // iterated by Encoder.forward (unet2d.py:188-196).
 //
@@ -25,16 +26,17 @@ constexpr int kPX = 4;   // consecutive outputs (along W) per thread
 #define DWT_HD __host__ __device__ __forceinline__
 
 struct Args {
-  const __nv_bfloat16* in;
+  const void* in;     // T [B][H][W][cs_in]
   const float* w;     // [K*K][C] BN-folded filter taps
   const float* bias;  // [C]
-  __nv_bfloat16* out;
+  void* out;          // T [B][OH][OW][cs_out]
   long long* pool;    // [B][C] fixed-point (2^-24) squeeze sums, or null
   int H, W, OH, OW, C, cs_in, cs_out, pad_top, pad_left, act, tiles_x;
 };
 
-template <int K, int S, int CVB, int TH>
+template <typename T, int K, int S, int CVB, int TH>
 struct Cfg {
+  static constexpr int PIECES = (int)sizeof(T) / 2;  // 16-byte pieces per 8-channel vector
   static constexpr int CT = CVB * 8;              // channels per CTA
   static constexpr int GX = kTW / kPX;            // thread groups along W
   static constexpr int GROUPS = kThreads / CVB;   // (row, x-group) slots per pass
@@ -43,10 +45,10 @@ struct Cfg {
   static_assert(TH % RPP == 0 && PASSES >= 1, "tile height must be a multiple of the rows per pass");
   static constexpr int ITH = (TH - 1) * S + K, ITW = (kTW - 1) * S + K;  // input halo tile
   static constexpr int NIN = (kPX - 1) * S + K;   // input vectors one thread reads per filter row
-  static constexpr int TILE_ELEMS = ITH * ITW * CT;  // bf16
+  static constexpr int TILE_ELEMS = ITH * ITW * CT;  // T
   static constexpr int W_ELEMS = K * K * CT;         // fp32, layout [tap][half][CVB][4]
   static constexpr int RED_ELEMS = GROUPS * CT;      // fp32
-  static constexpr size_t kTileBytes = (size_t)TILE_ELEMS * 2;
+  static constexpr size_t kTileBytes = (size_t)TILE_ELEMS * sizeof(T);
   static constexpr size_t kSmemBytes = kTileBytes + (size_t)W_ELEMS * 4 + (size_t)RED_ELEMS * 4;
   static_assert(kTileBytes % 16 == 0, "weights must start 16-byte aligned");
 };
@@ -86,6 +88,57 @@ DWT_HD void unpack8f2(const uint4& u, float2* f) {
   for (int i = 0; i < 4; ++i) f[i] = make_float2(bits2f(w[i] << 16), bits2f(w[i] & 0xffff0000u));
 }
 
+DWT_HD uint32_t f2bits(float f) {
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(f);
+#else
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+#endif
+}
+
+// fp32 -> nearest TF32 value (10-bit mantissa), ties away from zero: what cvt.rna.tf32.f32 computes
+DWT_HD float tf32_rna(float v) {
+#ifdef __CUDA_ARCH__
+  return round_tf32(v);
+#else
+  return bits2f((f2bits(v) + 0x1000u) & 0xffffe000u);
+#endif
+}
+
+// one 8-channel vector of the staged tile -> 4 float2
+DWT_HD void load8f2(const __nv_bfloat16* p, float2* f) { unpack8f2(*reinterpret_cast<const uint4*>(p), f); }
+DWT_HD void load8f2(const float* p, float2* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = make_float2(a.x, a.y); f[1] = make_float2(a.z, a.w);
+  f[2] = make_float2(b.x, b.y); f[3] = make_float2(b.z, b.w);
+}
+
+// round + store one output vector; v[] is left holding the stored values (what the next layer reads)
+DWT_HD void store8(__nv_bfloat16* p, float* v) {
+  uint4 packed;
+  uint32_t* pw = reinterpret_cast<uint32_t*>(&packed);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    uint32_t bits;
+    memcpy(&bits, &h2, 4);
+    pw[i] = bits;
+  }
+  *reinterpret_cast<uint4*>(p) = packed;
+  float2 r[4];
+  unpack8f2(packed, r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = r[i].x; v[2 * i + 1] = r[i].y; }
+}
+DWT_HD void store8(float* p, float* v) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = tf32_rna(v[i]);
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 DWT_HD float2 fma2(float2 a, float2 b, float2 c) {
 #ifdef __CUDA_ARCH__
   return __ffma2_rn(a, b, c);  // one packed FFMA2 issue slot for two IEEE fp32 FMAs (sm_100)
@@ -116,18 +169,19 @@ struct BlockIdx {
 };
 
 // ---- phase 1: stage the zero-filled input halo tile and this CTA's filter taps in shared memory ----------------
-template <int K, int S, int CVB, int TH>
-DWT_HD void phase_load(const Args& a, BlockIdx blk, int tid, __nv_bfloat16* tile, float* wsm) {
-  using C_ = Cfg<K, S, CVB, TH>;
+template <typename T, int K, int S, int CVB, int TH>
+DWT_HD void phase_load(const Args& a, BlockIdx blk, int tid, T* tile, float* wsm) {
+  using C_ = Cfg<T, K, S, CVB, TH>;
   const int b = blk.z, c0 = blk.y * C_::CT;
   const int gy0 = (blk.x / a.tiles_x) * TH * S - a.pad_top;
   const int gx0 = (blk.x % a.tiles_x) * kTW * S - a.pad_left;
-  const __nv_bfloat16* inb = a.in + (long long)b * a.H * a.W * a.cs_in;
-  for (int i = tid; i < C_::ITH * C_::ITW * CVB; i += kThreads) {
-    const int cv = i % CVB, pix = i / CVB;
+  constexpr int PC = C_::PIECES, EPP = 8 / PC;   // 16-byte pieces per vector, elements per piece
+  const T* inb = reinterpret_cast<const T*>(a.in) + (long long)b * a.H * a.W * a.cs_in;
+  for (int i = tid; i < C_::ITH * C_::ITW * CVB * PC; i += kThreads) {
+    const int piece = i % (CVB * PC), pix = i / (CVB * PC);   // piece = (cv, half): consecutive 16-byte runs
     const int iy = pix / C_::ITW, ix = pix - iy * C_::ITW;
-    const int gy = gy0 + iy, gx = gx0 + ix, c = c0 + cv * 8;
-    __nv_bfloat16* dst = tile + (long long)pix * C_::CT + cv * 8;
+    const int gy = gy0 + iy, gx = gx0 + ix, c = c0 + piece * EPP;
+    T* dst = tile + (long long)pix * C_::CT + piece * EPP;
     if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && c < a.C)
       copy16_async(dst, inb + ((long long)gy * a.W + gx) * a.cs_in + c);
     else
@@ -146,10 +200,10 @@ DWT_HD void phase_load(const Args& a, BlockIdx blk, int tid, __nv_bfloat16* tile
 }
 
 // ---- phase 2: FMA loop out of shared memory, activation, bf16 store, per-thread squeeze partials -> red[] -----
-template <int K, int S, int CVB, int TH>
-DWT_HD void phase_compute(const Args& a, BlockIdx blk, int tid, const __nv_bfloat16* tile, const float* wsm,
+template <typename T, int K, int S, int CVB, int TH>
+DWT_HD void phase_compute(const Args& a, BlockIdx blk, int tid, const T* tile, const float* wsm,
                           float* red) {
-  using C_ = Cfg<K, S, CVB, TH>;
+  using C_ = Cfg<T, K, S, CVB, TH>;
   const int cv = tid % CVB, g = tid / CVB;
   const int gxi = g % C_::GX, r0 = g / C_::GX;
   const int b = blk.z, c = blk.y * C_::CT + cv * 8;
@@ -187,11 +241,11 @@ DWT_HD void phase_compute(const Args& a, BlockIdx blk, int tid, const __nv_bfloa
         wv[kx][2] = make_float2(w1.x, w1.y);
         wv[kx][3] = make_float2(w1.z, w1.w);
       }
-      const __nv_bfloat16* rowp = tile + ((long long)(orow * S + ky) * C_::ITW + gxi * kPX * S) * C_::CT + cv * 8;
+      const T* rowp = tile + ((long long)(orow * S + ky) * C_::ITW + gxi * kPX * S) * C_::CT + cv * 8;
 #pragma unroll
       for (int j = 0; j < C_::NIN; ++j) {
         float2 x[4];
-        unpack8f2(*reinterpret_cast<const uint4*>(rowp + j * C_::CT), x);
+        load8f2(rowp + j * C_::CT, x);
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
           const int d = j - kx;  // input column j feeds output p = d / S through tap kx (compile-time resolved)
@@ -202,7 +256,7 @@ DWT_HD void phase_compute(const Args& a, BlockIdx blk, int tid, const __nv_bfloa
         }
       }
     }
-    __nv_bfloat16* orow_p = a.out + (((long long)b * a.OH + oy) * a.OW + ox0) * a.cs_out + c;
+    T* orow_p = reinterpret_cast<T*>(a.out) + (((long long)b * a.OH + oy) * a.OW + ox0) * a.cs_out + c;
 #pragma unroll
     for (int p = 0; p < kPX; ++p) {
       if (ox0 + p >= a.OW) break;
@@ -213,24 +267,13 @@ DWT_HD void phase_compute(const Args& a, BlockIdx blk, int tid, const __nv_bfloa
         v[2 * i + 1] = acc[p][i].y;
       }
       act8(v, a.act);
-      uint4 packed;
-      uint32_t* pw = reinterpret_cast<uint32_t*>(&packed);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        uint32_t bits;
-        memcpy(&bits, &h2, 4);
-        pw[i] = bits;
-      }
-      *reinterpret_cast<uint4*>(orow_p + (long long)p * a.cs_out) = packed;
+      store8(orow_p + (long long)p * a.cs_out, v);
       if (a.pool) {
-        // squeeze what the next layer will actually read (the bf16-rounded activation)
-        float2 r[4];
-        unpack8f2(packed, r);
+        // squeeze what the next layer will actually read (the rounded activation)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          psum[i].x += r[i].x;
-          psum[i].y += r[i].y;
+          psum[i].x += v[2 * i];
+          psum[i].y += v[2 * i + 1];
         }
       }
     }
@@ -247,9 +290,9 @@ DWT_HD void phase_compute(const Args& a, BlockIdx blk, int tid, const __nv_bfloa
 
 // ---- phase 3: one thread per channel folds the CTA's partials and adds them to pool[b][c] (integer atomics:
 //      order-independent, so the SE gates are bit-reproducible run to run) ---------------------------------------
-template <int K, int S, int CVB, int TH>
+template <typename T, int K, int S, int CVB, int TH>
 DWT_HD void phase_pool(const Args& a, BlockIdx blk, int tid, const float* red) {
-  using C_ = Cfg<K, S, CVB, TH>;
+  using C_ = Cfg<T, K, S, CVB, TH>;
   const int c = blk.y * C_::CT + tid;
   if (tid >= C_::CT || c >= a.C) return;
   float s = 0.f;
@@ -263,37 +306,38 @@ DWT_HD void phase_pool(const Args& a, BlockIdx blk, int tid, const float* red) {
 }
 
 #ifdef __CUDACC__
-template <int K, int S, int CVB, int TH>
+template <typename T, int K, int S, int CVB, int TH>
 __global__ void __launch_bounds__(kThreads, 2) dwconv_tiled_kernel(const Args a) {
-  using C_ = Cfg<K, S, CVB, TH>;
+  using C_ = Cfg<T, K, S, CVB, TH>;
   extern __shared__ __align__(16) unsigned char dwt_smem[];
-  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(dwt_smem);
+  T* tile = reinterpret_cast<T*>(dwt_smem);
   float* wsm = reinterpret_cast<float*>(dwt_smem + C_::kTileBytes);
   float* red = wsm + C_::W_ELEMS;
   const BlockIdx blk{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z};
   const int tid = threadIdx.x;
-  phase_load<K, S, CVB, TH>(a, blk, tid, tile, wsm);
+  phase_load<T, K, S, CVB, TH>(a, blk, tid, tile, wsm);
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  phase_compute<K, S, CVB, TH>(a, blk, tid, tile, wsm, red);
+  phase_compute<T, K, S, CVB, TH>(a, blk, tid, tile, wsm, red);
   if (a.pool) {
     __syncthreads();
-    phase_pool<K, S, CVB, TH>(a, blk, tid, red);
+    phase_pool<T, K, S, CVB, TH>(a, blk, tid, red);
   }
 }
 #endif
 
-// tile-shape choice shared by the launcher and the host emulation: CVB = 4 for layers narrower than 64 channels,
+// tile-shape choice shared by the launcher and the host emulation: CVB = 4 for layers narrower than 64 channels
+// (and always for fp32: 32 channels x 4 bytes = the same 128-byte runs and tile bytes as 64 bf16 channels),
 // tall tiles (TH = 16) when the layer still fills the GPU twice over, TH = 8 otherwise and for stride 2
 struct Choice {
   int cvb, th;
 };
-static inline Choice choose(int B, int OH, int OW, int C, int S, int n_sms) {
+static inline Choice choose(int B, int OH, int OW, int C, int S, int n_sms, int elem_size = 2) {
   Choice ch;
-  ch.cvb = C < 64 ? 4 : 8;
+  ch.cvb = (C < 64 || elem_size == 4) ? 4 : 8;
   if (ch.cvb == 4) {
-    ch.th = 16;
+    ch.th = 16;   // 64 (row, x-group) slots per pass / 4 x-groups = 16 rows per pass
   } else if (S == 2) {
     ch.th = 8;
   } else {

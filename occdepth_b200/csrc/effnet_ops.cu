@@ -9,8 +9,6 @@
 #include <string.h>
 #include "common.cuh"
 #include "dwconv_tiled.cuh"
-#include "se_fold_strip.cuh"
-#include "upsample_rows.cuh"
 #include "../../include/occdepth_b200.h"
 
 namespace {
@@ -27,10 +25,10 @@ constexpr int kDwRows = 4;  // output rows per block (amortises the squeeze atom
 // across threadIdx.y in shared memory and added to pool[b][c] as a 64-bit FIXED-POINT integer (2^-24 units): integer
 // atomics commute exactly, so the SE gates (and everything downstream) are bit-reproducible run to run -- float
 // atomics are not.
-template <int K, int S, int CVB>
+template <typename T, int K, int S, int CVB>
 __global__ void __launch_bounds__(kDwThreads)
-dwconv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-              __nv_bfloat16* __restrict__ out, long long* __restrict__ pool, int H, int W, int OH, int OW, int C,
+dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+              T* __restrict__ out, long long* __restrict__ pool, int H, int W, int OH, int OW, int C,
               int cs_in, int cs_out, int pad_top, int pad_left, int act) {
   constexpr int PY = kDwThreads / CVB;
   constexpr int NIN = (kDwPX - 1) * S + K;
@@ -58,20 +56,20 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[p][i] = bv[i];
     }
-    const __nv_bfloat16* inb = in + (long long)b * H * W * cs_in + c0;
+    const T* inb = in + (long long)b * H * W * cs_in + c0;
     const float* wc = w + c0;
     const int ix0 = ox0 * S - pad_left;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) {
       const int iy = oy * S - pad_top + ky;
       if (iy < 0 || iy >= H) continue;
-      const __nv_bfloat16* row = inb + (long long)iy * W * cs_in;
+      const T* row = inb + (long long)iy * W * cs_in;
       float xin[NIN][8];
 #pragma unroll
       for (int j = 0; j < NIN; ++j) {
         const int ix = ix0 + j;
         if (ix >= 0 && ix < W) {
-          unpack8(__ldg(reinterpret_cast<const uint4*>(row + (long long)ix * cs_in)), xin[j]);
+          Elem<T>::ld8_nc(row + (long long)ix * cs_in, xin[j]);
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) xin[j][i] = 0.f;
@@ -94,14 +92,11 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
       const int ox = ox0 + p;
       if (ox >= OW) break;
       apply_act8(acc[p], act);
-      const uint4 packed = pack8(acc[p]);
-      *reinterpret_cast<uint4*>(out + (((long long)b * OH + oy) * OW + ox) * cs_out + c0) = packed;
+      // store, and pool what the next layer will actually read (the rounded activation)
+      Elem<T>::st8_rb(out + (((long long)b * OH + oy) * OW + ox) * cs_out + c0, acc[p]);
       if (pool) {
-        // pool what the next layer will actually read (the bf16-rounded activation)
-        float r[8];
-        unpack8(packed, r);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) psum[i] += r[i];
+        for (int i = 0; i < 8; ++i) psum[i] += acc[p][i];
       }
     }
   }
@@ -163,9 +158,10 @@ se_fc2_kernel(long long* __restrict__ pool, const float* __restrict__ hidden, co
 
 // fused: gate for a strip of 256 input channels (second FC + sigmoid), then that strip of the projection
 // weights scaled and packed to bf16 for `rows_per_block` output rows.  grid (ceil(Kpad/256), row blocks)
+template <typename T>
 __global__ void __launch_bounds__(256)
 se_fc2_fold_kernel(long long* __restrict__ pool, const float* __restrict__ hidden, const float* __restrict__ w2t,
-                   const float* __restrict__ b2, const float* __restrict__ master, __nv_bfloat16* __restrict__ out,
+                   const float* __restrict__ b2, const float* __restrict__ master, T* __restrict__ out,
                    int C, int R, int rows, int Kpad, int rows_per_block) {
   extern __shared__ float hid[];
   const int img = blockIdx.z;   // one weight set per image
@@ -182,14 +178,15 @@ se_fc2_fold_kernel(long long* __restrict__ pool, const float* __restrict__ hidde
   }
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(rows, r0 + rows_per_block);
-  __nv_bfloat16* o = out + (long long)img * rows * Kpad;
+  T* o = out + (long long)img * rows * Kpad;
   for (int r = r0; r < r1; ++r)
-    o[(long long)r * Kpad + k] = __float2bfloat16_rn(__ldg(master + (long long)r * Kpad + k) * g);
+    o[(long long)r * Kpad + k] = Elem<T>::cvt(__ldg(master + (long long)r * Kpad + k) * g);
 }
 
 // out[row][k] = bf16(master[row][k] * gate[k])  (k < C), rows = Cout_pad, row length Kpad
+template <typename T>
 __global__ void scale_weights_kernel(const float* __restrict__ master, const float* __restrict__ gate,
-                                     __nv_bfloat16* __restrict__ out, int rows, int Kpad, int C) {
+                                     T* __restrict__ out, int rows, int Kpad, int C) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;  // Kpad % 8 == 0
   if (i >= (long long)rows * Kpad) return;
   const int k = (int)(i % Kpad);
@@ -200,11 +197,12 @@ __global__ void scale_weights_kernel(const float* __restrict__ master, const flo
   for (int j = 0; j < 8; ++j) g[j] = (k + j < C) ? gate[k + j] : 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) m[j] *= g[j];
-  *reinterpret_cast<uint4*>(out + i) = pack8(m);
+  Elem<T>::st8(out + i, m);
 }
 
 // bilinear, align_corners=True; in [B][h][w][cs_in] -> out [B][OH][OW][cs_out] (channel windows), C % 8 == 0 padded
-__global__ void upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B,
+template <typename T>
+__global__ void upsample_bilinear_kernel(const T* __restrict__ in, T* __restrict__ out, int B,
                                          int h, int w, int OH, int OW, int CV, int cs_in, int in_off, int cs_out,
                                          int out_off, float sy, float sx) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,22 +219,23 @@ __global__ void upsample_bilinear_kernel(const __nv_bfloat16* __restrict__ in, _
   const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
   const float ly = fy - y0, lx = fx - x0;
   const float hy = 1.f - ly, hx = 1.f - lx;
-  const __nv_bfloat16* base = in + (long long)b * h * w * cs_in + in_off + cv * 8;
+  const T* base = in + (long long)b * h * w * cs_in + in_off + cv * 8;
   float a[8], bb[8], c[8], d[8], o[8];
-  unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * w + x0) * cs_in)), a);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long long)y0 * w + x1) * cs_in)), bb);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * w + x0) * cs_in)), c);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long long)y1 * w + x1) * cs_in)), d);
+  Elem<T>::ld8_nc(base + ((long long)y0 * w + x0) * cs_in, a);
+  Elem<T>::ld8_nc(base + ((long long)y0 * w + x1) * cs_in, bb);
+  Elem<T>::ld8_nc(base + ((long long)y1 * w + x0) * cs_in, c);
+  Elem<T>::ld8_nc(base + ((long long)y1 * w + x1) * cs_in, d);
 #pragma unroll
   for (int k = 0; k < 8; ++k) o[k] = hy * (hx * a[k] + lx * bb[k]) + ly * (hx * c[k] + lx * d[k]);
-  *reinterpret_cast<uint4*>(out + (((long long)b * OH + oy) * OW + ox) * cs_out + out_off + cv * 8) = pack8(o);
+  Elem<T>::st8(out + (((long long)b * OH + oy) * OW + ox) * cs_out + out_off + cv * 8, o);
 }
 
 }  // namespace
 
-extern "C" int occd_dwconv2d_fwd(const void* in, const float* w, const float* bias, void* out, long long* pool, int B,
-                                 int H, int W, int OH, int OW, int C, int cs_in, int cs_out, int K, int stride,
-                                 int pad_top, int pad_left, int act, void* stream) {
+template <typename T>
+static int dwconv2d_direct(const void* in, const float* w, const float* bias, void* out, long long* pool, int B,
+                           int H, int W, int OH, int OW, int C, int cs_in, int cs_out, int K, int stride,
+                           int pad_top, int pad_left, int act, void* stream) {
   OCCD_CHECK_ARG(in && w && bias && out && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "occd_dwconv2d_fwd: args");
   OCCD_CHECK_ARG(C > 0 && C % 8 == 0 && cs_in % 8 == 0 && cs_out % 8 == 0 && cs_in >= C && cs_out >= C,
                  "occd_dwconv2d_fwd: channels must be a multiple of 8");
@@ -253,11 +252,11 @@ extern "C" int occd_dwconv2d_fwd(const void* in, const float* w, const float* bi
   const int py = kDwThreads / cvb;
   dim3 grid((OW + py * kDwPX - 1) / (py * kDwPX), (CV + cvb - 1) / cvb, B * ((OH + kDwRows - 1) / kDwRows)), block(kDwThreads);
   cudaStream_t st = (cudaStream_t)stream;
-  const __nv_bfloat16* i = (const __nv_bfloat16*)in;
-  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  const T* i = (const T*)in;
+  T* o = (T*)out;
 #define OCCD_DW(K_, S_, CVB_)                                                                                   \
-  dwconv_kernel<K_, S_, CVB_><<<grid, block, 0, st>>>(i, w, bias, o, pool, H, W, OH, OW, C, cs_in, cs_out,      \
-                                                       pad_top, pad_left, act)
+  dwconv_kernel<T, K_, S_, CVB_><<<grid, block, 0, st>>>(i, w, bias, o, pool, H, W, OH, OW, C, cs_in, cs_out,   \
+                                                          pad_top, pad_left, act)
 #define OCCD_DW_CVB(K_, S_)                                                                                     \
   { if (cvb == 8) OCCD_DW(K_, S_, 8); else if (cvb == 16) OCCD_DW(K_, S_, 16); else OCCD_DW(K_, S_, 32); }
   if (K == 3 && stride == 1) OCCD_DW_CVB(3, 1)
@@ -270,42 +269,62 @@ extern "C" int occd_dwconv2d_fwd(const void* in, const float* w, const float* bi
   return OCCD_OK;
 }
 
+extern "C" int occd_dwconv2d_fwd(const void* in, const float* w, const float* bias, void* out, long long* pool,
+                                 int dtype, int B, int H, int W, int OH, int OW, int C, int cs_in, int cs_out, int K,
+                                 int stride, int pad_top, int pad_left, int act, void* stream) {
+  OCCD_DISPATCH_DTYPE(dtype, T, return dwconv2d_direct<T>(in, w, bias, out, pool, B, H, W, OH, OW, C, cs_in, cs_out, K,
+                                                         stride, pad_top, pad_left, act, stream));
+}
+
 
 namespace {
 
-template <int K, int S, int CVB, int TH>
+template <typename T, int K, int S, int CVB, int TH>
 int launch_dw_tiled(const dwt::Args& a, int B, cudaStream_t st) {
-  using C_ = dwt::Cfg<K, S, CVB, TH>;
+  using C_ = dwt::Cfg<T, K, S, CVB, TH>;
   static bool attr_set[64] = {false};  // per instantiation, per device
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv_tiled_kernel<K, S, CVB, TH>,
+    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv_tiled_kernel<T, K, S, CVB, TH>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::kSmemBytes);
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
     attr_set[dev] = true;
   }
   const int tiles_y = (a.OH + TH - 1) / TH;
   dim3 grid(a.tiles_x * tiles_y, (a.C + C_::CT - 1) / C_::CT, B);
-  dwt::dwconv_tiled_kernel<K, S, CVB, TH><<<grid, dwt::kThreads, C_::kSmemBytes, st>>>(a);
+  dwt::dwconv_tiled_kernel<T, K, S, CVB, TH><<<grid, dwt::kThreads, C_::kSmemBytes, st>>>(a);
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
 
-template <int K, int S>
+template <typename T, int K, int S>
 int launch_dw_tiled_ks(const dwt::Args& a, int B, dwt::Choice ch, cudaStream_t st) {
-  if (ch.cvb == 4) return launch_dw_tiled<K, S, 4, 16>(a, B, st);
-  if (ch.th == 16) return launch_dw_tiled<K, S, 8, 16>(a, B, st);
-  return launch_dw_tiled<K, S, 8, 8>(a, B, st);
+  if (ch.cvb == 4) return launch_dw_tiled<T, K, S, 4, 16>(a, B, st);   // 16 rows per pass: TH = 16 only
+  if constexpr (sizeof(T) == 2) {
+    if (ch.th == 16) return launch_dw_tiled<T, K, S, 8, 16>(a, B, st);
+    return launch_dw_tiled<T, K, S, 8, 8>(a, B, st);
+  }
+  occd_set_last_error("occd_dwconv2d_tiled_fwd: internal tile choice");
+  return OCCD_ERR_ARG;
+}
+
+template <typename T>
+int dw_tiled_dispatch(const dwt::Args& a, int B, int K, int stride, dwt::Choice ch, cudaStream_t st) {
+  if (K == 3 && stride == 1) return launch_dw_tiled_ks<T, 3, 1>(a, B, ch, st);
+  if (K == 3) return launch_dw_tiled_ks<T, 3, 2>(a, B, ch, st);
+  if (stride == 1) return launch_dw_tiled_ks<T, 5, 1>(a, B, ch, st);
+  return launch_dw_tiled_ks<T, 5, 2>(a, B, ch, st);
 }
 
 }  // namespace
 
 // Shared-memory-tiled variant of occd_dwconv2d_fwd (same arguments, same results up to fp32 summation order).
 extern "C" int occd_dwconv2d_tiled_fwd(const void* in, const float* w, const float* bias, void* out, long long* pool,
-                                       int B, int H, int W, int OH, int OW, int C, int cs_in, int cs_out, int K,
-                                       int stride, int pad_top, int pad_left, int act, void* stream) {
+                                       int dtype, int B, int H, int W, int OH, int OW, int C, int cs_in, int cs_out,
+                                       int K, int stride, int pad_top, int pad_left, int act, void* stream) {
+  OCCD_CHECK_ARG(dtype == OCCD_DTYPE_F32 || dtype == OCCD_DTYPE_BF16, "occd_dwconv2d_tiled_fwd: dtype");
   OCCD_CHECK_ARG(in && w && bias && out && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "occd_dwconv2d_tiled_fwd: args");
   OCCD_CHECK_ARG(C > 0 && C % 8 == 0 && cs_in % 8 == 0 && cs_out % 8 == 0 && cs_in >= C && cs_out >= C,
                  "occd_dwconv2d_tiled_fwd: channels must be a multiple of 8");
@@ -319,15 +338,13 @@ extern "C" int occd_dwconv2d_tiled_fwd(const void* in, const float* w, const flo
     if (cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sms <= 0) n_sms = 148;
   }
   dwt::Args a;
-  a.in = (const __nv_bfloat16*)in; a.w = w; a.bias = bias; a.out = (__nv_bfloat16*)out; a.pool = pool;
+  a.in = in; a.w = w; a.bias = bias; a.out = out; a.pool = pool;
   a.H = H; a.W = W; a.OH = OH; a.OW = OW; a.C = C; a.cs_in = cs_in; a.cs_out = cs_out;
   a.pad_top = pad_top; a.pad_left = pad_left; a.act = act; a.tiles_x = (OW + dwt::kTW - 1) / dwt::kTW;
-  const dwt::Choice ch = dwt::choose(B, OH, OW, C, stride, n_sms);
+  const dwt::Choice ch = dwt::choose(B, OH, OW, C, stride, n_sms, dtype == OCCD_DTYPE_F32 ? 4 : 2);
   cudaStream_t st = (cudaStream_t)stream;
-  if (K == 3 && stride == 1) return launch_dw_tiled_ks<3, 1>(a, B, ch, st);
-  if (K == 3) return launch_dw_tiled_ks<3, 2>(a, B, ch, st);
-  if (stride == 1) return launch_dw_tiled_ks<5, 1>(a, B, ch, st);
-  return launch_dw_tiled_ks<5, 2>(a, B, ch, st);
+  if (dtype == OCCD_DTYPE_F32) return dw_tiled_dispatch<float>(a, B, K, stride, ch, st);
+  return dw_tiled_dispatch<__nv_bfloat16>(a, B, K, stride, ch, st);
 }
 
 extern "C" int occd_se_gate_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
@@ -344,19 +361,20 @@ extern "C" int occd_se_gate_fwd(long long* pool, float inv_hw, const float* w1, 
   return OCCD_OK;
 }
 
-extern "C" int occd_scale_weights(const float* master, const float* gate, void* out, int rows, int Kpad, int C,
-                                  void* stream) {
+extern "C" int occd_scale_weights(const float* master, const float* gate, void* out, int wdtype, int rows, int Kpad,
+                                  int C, void* stream) {
   OCCD_CHECK_ARG(master && gate && out && rows > 0 && Kpad > 0 && C > 0 && C <= Kpad, "occd_scale_weights: args");
   OCCD_CHECK_ARG(Kpad % 8 == 0, "occd_scale_weights: Kpad must be a multiple of 8");
   const long long total = (long long)rows * Kpad / 8;
-  scale_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      master, gate, (__nv_bfloat16*)out, rows, Kpad, C);
+  OCCD_DISPATCH_DTYPE(wdtype, T, (scale_weights_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0,
+                                                             (cudaStream_t)stream>>>(master, gate, (T*)out, rows,
+                                                                                     Kpad, C)));
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
 
-static int upsample_impl(bool rows, const void* in, void* out, int B, int h, int w, int OH, int OW, int C, int cs_in,
-                         int in_off, int cs_out, int out_off, void* stream) {
+extern "C" int occd_upsample_bilinear_ac(const void* in, void* out, int dtype, int B, int h, int w, int OH, int OW,
+                                         int C, int cs_in, int in_off, int cs_out, int out_off, void* stream) {
   OCCD_CHECK_ARG(in && out && B > 0 && h > 0 && w > 0 && OH > 0 && OW > 0 && C > 0, "occd_upsample_bilinear_ac: args");
   OCCD_CHECK_ARG(cs_in % 8 == 0 && cs_out % 8 == 0 && in_off % 8 == 0 && out_off % 8 == 0,
                  "occd_upsample_bilinear_ac: alignment");
@@ -364,76 +382,30 @@ static int upsample_impl(bool rows, const void* in, void* out, int B, int h, int
   OCCD_CHECK_ARG(in_off + CV * 8 <= cs_in && out_off + CV * 8 <= cs_out, "occd_upsample_bilinear_ac: channel window");
   const float sy = OH > 1 ? (float)(h - 1) / (float)(OH - 1) : 0.f;
   const float sx = OW > 1 ? (float)(w - 1) / (float)(OW - 1) : 0.f;
-  if (rows) {
-    OCCD_CHECK_ARG((long long)B * OH <= 65535, "occd_upsample_bilinear_rows: B*OH too large");
-    upr::Args a{(const __nv_bfloat16*)in, (__nv_bfloat16*)out, h, w, OH, OW, CV, cs_in, in_off, cs_out, out_off, sy, sx};
-    const int cvb = upr::choose_cvb(CV);
-    const int pxb = upr::kThreads / cvb;
-    dim3 grid((OW + pxb - 1) / pxb, (CV + cvb - 1) / cvb, B * OH);
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (cvb) {
-      case 1: upr::upsample_rows_kernel<1><<<grid, upr::kThreads, 0, st>>>(a); break;
-      case 2: upr::upsample_rows_kernel<2><<<grid, upr::kThreads, 0, st>>>(a); break;
-      case 4: upr::upsample_rows_kernel<4><<<grid, upr::kThreads, 0, st>>>(a); break;
-      case 8: upr::upsample_rows_kernel<8><<<grid, upr::kThreads, 0, st>>>(a); break;
-      case 16: upr::upsample_rows_kernel<16><<<grid, upr::kThreads, 0, st>>>(a); break;
-      default: upr::upsample_rows_kernel<32><<<grid, upr::kThreads, 0, st>>>(a); break;
-    }
-    OCCD_CHECK_LAUNCH();
-    return OCCD_OK;
-  }
   const long long total = (long long)B * OH * OW * CV;
-  upsample_bilinear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, h, w, OH, OW, CV, cs_in, in_off, cs_out, out_off, sy, sx);
+  OCCD_DISPATCH_DTYPE(dtype, T, (upsample_bilinear_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0,
+                                                                (cudaStream_t)stream>>>(
+                                     (const T*)in, (T*)out, B, h, w, OH, OW, CV, cs_in, in_off, cs_out, out_off, sy,
+                                     sx)));
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
 
-extern "C" int occd_upsample_bilinear_ac(const void* in, void* out, int B, int h, int w, int OH, int OW, int C,
-                                         int cs_in, int in_off, int cs_out, int out_off, void* stream) {
-  return upsample_impl(false, in, out, B, h, w, OH, OW, C, cs_in, in_off, cs_out, out_off, stream);
-}
-
-// same contract, one block row per output row (block-uniform vertical weights, no per-thread div/mod chain)
-extern "C" int occd_upsample_bilinear_rows(const void* in, void* out, int B, int h, int w, int OH, int OW, int C,
-                                           int cs_in, int in_off, int cs_out, int out_off, void* stream) {
-  return upsample_impl(true, in, out, B, h, w, OH, OW, C, cs_in, in_off, cs_out, out_off, stream);
-}
-
-static int se_gate_fold_impl(bool strip, long long* pool, float inv_hw, const float* w1, const float* b1,
-                             const float* w2t, const float* b2, float* hidden, const float* master, void* wout, int B,
-                             int C, int R, int rows, int Kpad, void* stream) {
+extern "C" int occd_se_gate_fold_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
+                                     const float* b2, float* hidden, const float* master, void* wout, int wdtype,
+                                     int B, int C, int R, int rows, int Kpad, void* stream) {
   OCCD_CHECK_ARG(pool && w1 && b1 && w2t && b2 && hidden && master && wout && C > 0 && R > 0 && rows > 0 &&
                  Kpad >= C && R <= 8192, "occd_se_gate_fold_fwd: args");
   cudaStream_t st = (cudaStream_t)stream;
   OCCD_CHECK_ARG(B >= 1 && B <= 65535, "occd_se_gate_fold_fwd: B");
   se_fc1_kernel<<<dim3(R, B), 128, 0, st>>>(pool, inv_hw, w1, b1, hidden, C, R);
   OCCD_CHECK_LAUNCH();
-  if (strip) {
-    sef::Args a{pool, hidden, w2t, b2, master, (__nv_bfloat16*)wout, C, R, rows, Kpad};
-    sef::se_fc2_fold_strip_kernel<<<dim3((Kpad + sef::kStrip - 1) / sef::kStrip, B), sef::kThreads, 0, st>>>(a);
-    OCCD_CHECK_LAUNCH();
-    return OCCD_OK;
-  }
   const int kblocks = (Kpad + 255) / 256;
   int rows_per_block = rows;
   while (rows_per_block > 16 && B * kblocks * ((rows + rows_per_block - 1) / rows_per_block) < 296) rows_per_block /= 2;
   dim3 grid(kblocks, (rows + rows_per_block - 1) / rows_per_block, B);
-  se_fc2_fold_kernel<<<grid, 256, R * sizeof(float), st>>>(pool, hidden, w2t, b2, master,
-                                                           (__nv_bfloat16*)wout, C, R, rows, Kpad, rows_per_block);
+  OCCD_DISPATCH_DTYPE(wdtype, T, (se_fc2_fold_kernel<T><<<grid, 256, R * sizeof(float), st>>>(
+                                      pool, hidden, w2t, b2, master, (T*)wout, C, R, rows, Kpad, rows_per_block)));
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
-}
-
-extern "C" int occd_se_gate_fold_fwd(long long* pool, float inv_hw, const float* w1, const float* b1, const float* w2t,
-                                     const float* b2, float* hidden, const float* master, void* wout, int B, int C,
-                                     int R, int rows, int Kpad, void* stream) {
-  return se_gate_fold_impl(false, pool, inv_hw, w1, b1, w2t, b2, hidden, master, wout, B, C, R, rows, Kpad, stream);
-}
-
-// same contract; the fold runs as one CTA per 32-channel strip so that every gate value is evaluated once
-extern "C" int occd_se_gate_fold_strip_fwd(long long* pool, float inv_hw, const float* w1, const float* b1,
-                                           const float* w2t, const float* b2, float* hidden, const float* master,
-                                           void* wout, int B, int C, int R, int rows, int Kpad, void* stream) {
-  return se_gate_fold_impl(true, pool, inv_hw, w1, b1, w2t, b2, hidden, master, wout, B, C, R, rows, Kpad, stream);
 }

@@ -1,4 +1,5 @@
-// Small bandwidth-bound helpers around the implicit-GEMM convolutions (all channels-last bf16).
+// Small bandwidth-bound helpers around the implicit-GEMM convolutions (channels-last activations, bf16 or
+// TF32-valued fp32: see Elem<T> in common.cuh).
 #include "common.cuh"
 #include "../../include/occdepth_b200.h"
 
@@ -6,7 +7,8 @@ namespace {
 
 // softmax over C (<= 32) planar fp32 channels -> bf16 channels-last window
 // replaces nn.Softmax(dim=1) + torch.cat of modules.py:168-171
-__global__ void softmax_planar_to_cl_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C,
+template <typename T>
+__global__ void softmax_planar_to_cl_kernel(const float* __restrict__ in, T* __restrict__ out, int C,
                                             long long S, long long total, int cstride, int coff) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -17,23 +19,24 @@ __global__ void softmax_planar_to_cl_kernel(const float* __restrict__ in, __nv_b
   float e[32];
   float sum = 0.f;
   for (int c = 0; c < C; ++c) { e[c] = expf(p[(long long)c * S] - m); sum += e[c]; }
-  __nv_bfloat16* o = out + i * cstride + coff;
-  for (int c = 0; c < C; ++c) o[c] = __float2bfloat16_rn(e[c] / sum);
+  T* o = out + i * cstride + coff;
+  for (int c = 0; c < C; ++c) o[c] = Elem<T>::cvt(e[c] / sum);
 }
 
 // out[b][r][c] (row-major [R][ldo]) = in[b][c][r] where in is channels-last [positions P][cstride] window:
 // i.e. weight[f][m] = ctx[m][f]   (CRP3D.py:62-63,81: the mega-context becomes the B operand of the bmm)
-__global__ void cl_transpose_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int P,
+template <typename T>
+__global__ void cl_transpose_kernel(const T* __restrict__ in, T* __restrict__ out, int P,
                                     int C, int cstride, int coff, int ldo, long long in_bstride,
                                     long long out_bstride) {
-  __shared__ __nv_bfloat16 tile[32][33];
+  __shared__ T tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const __nv_bfloat16* inb = in + b * in_bstride;
-  __nv_bfloat16* outb = out + b * out_bstride;
+  const T* inb = in + b * in_bstride;
+  T* outb = out + b * out_bstride;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int pp = p0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (pp < P && c < C) ? inb[(long long)pp * cstride + coff + c] : __float2bfloat16(0.f);
+    tile[i][threadIdx.x] = (pp < P && c < C) ? inb[(long long)pp * cstride + coff + c] : Elem<T>::cvt(0.f);
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -43,15 +46,18 @@ __global__ void cl_transpose_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
 }
 
 // copy a channel window between channels-last buffers (C multiple of 8)
-__global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+// (16-byte pieces: 8 bf16 or 4 fp32 channels)
+template <typename T>
+__global__ void copy_channels_kernel(const T* __restrict__ in, T* __restrict__ out,
                                      long long positions, int C, int in_cs, int in_off, int out_cs, int out_off) {
-  const int vec = C / 8;
+  constexpr int E = 16 / sizeof(T);
+  const int vec = C / E;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= positions * vec) return;
   const long long pos = i / vec;
   const int v = (int)(i % vec);
-  *reinterpret_cast<uint4*>(out + pos * out_cs + out_off + v * 8) =
-      *reinterpret_cast<const uint4*>(in + pos * in_cs + in_off + v * 8);
+  *reinterpret_cast<uint4*>(out + pos * out_cs + out_off + v * E) =
+      *reinterpret_cast<const uint4*>(in + pos * in_cs + in_off + v * E);
 }
 
 // class map of the caller-side post-processing (scripts/generate_output.py:94-95: softmax -> argmax -> uint16):
@@ -95,34 +101,37 @@ extern "C" int occd_argmax_classes(const float* in, void* out, long long B, int 
   return OCCD_OK;
 }
 
-extern "C" int occd_softmax_planar_to_cl(const float* in, void* out, long long B, int C, long long S, int cstride,
-                                         int coff, void* stream) {
+extern "C" int occd_softmax_planar_to_cl(const float* in, void* out, int dtype, long long B, int C, long long S,
+                                         int cstride, int coff, void* stream) {
   OCCD_CHECK_ARG(in && out && B > 0 && C > 0 && C <= 32 && S > 0 && coff + C <= cstride, "occd_softmax_planar_to_cl: args");
   const long long total = B * S;
-  softmax_planar_to_cl_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      in, (__nv_bfloat16*)out, C, S, total, cstride, coff);
+  OCCD_DISPATCH_DTYPE(dtype, T, (softmax_planar_to_cl_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0,
+                                                                   (cudaStream_t)stream>>>(in, (T*)out, C, S, total,
+                                                                                           cstride, coff)));
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
 
-extern "C" int occd_cl_transpose(const void* in, void* out, int B, int P, int C, int cstride, int coff, int ldo,
-                                 long long out_bstride, void* stream) {
+extern "C" int occd_cl_transpose(const void* in, void* out, int dtype, int B, int P, int C, int cstride, int coff,
+                                 int ldo, long long out_bstride, void* stream) {
   OCCD_CHECK_ARG(in && out && B > 0 && P > 0 && C > 0 && coff + C <= cstride && ldo >= P, "occd_cl_transpose: args");
   dim3 grid((P + 31) / 32, (C + 31) / 32, B), block(32, 8);
-  cl_transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, P, C,
-                                                               cstride, coff, ldo, (long long)P * cstride,
-                                                               out_bstride);
+  OCCD_DISPATCH_DTYPE(dtype, T, (cl_transpose_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>(
+                                     (const T*)in, (T*)out, P, C, cstride, coff, ldo, (long long)P * cstride,
+                                     out_bstride)));
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
 
-extern "C" int occd_copy_channels(const void* in, void* out, long long positions, int C, int in_cstride, int in_coff,
-                                  int out_cstride, int out_coff, void* stream) {
+extern "C" int occd_copy_channels(const void* in, void* out, int dtype, long long positions, int C, int in_cstride,
+                                  int in_coff, int out_cstride, int out_coff, void* stream) {
   OCCD_CHECK_ARG(in && out && positions > 0 && C > 0 && C % 8 == 0 && in_coff % 8 == 0 && out_coff % 8 == 0 &&
                  in_cstride % 8 == 0 && out_cstride % 8 == 0, "occd_copy_channels: args");
-  const long long total = positions * (C / 8);
-  copy_channels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)in, (__nv_bfloat16*)out, positions, C, in_cstride, in_coff, out_cstride, out_coff);
+  const long long total = positions * (C / (dtype == OCCD_DTYPE_F32 ? 4 : 8));
+  OCCD_DISPATCH_DTYPE(dtype, T, (copy_channels_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0,
+                                                            (cudaStream_t)stream>>>(
+                                     (const T*)in, (T*)out, positions, C, in_cstride, in_coff, out_cstride,
+                                     out_coff)));
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }

@@ -116,21 +116,22 @@ __global__ void fc_kernel(const float* __restrict__ in, const float* __restrict_
   if (lane == 0) out[(long long)b * n_out + o] = apply_act(s + bias[o], act);
 }
 
-// x[b][pos][c] *= gate[b][c]  (channels-last bf16, C % 8 == 0)
-__global__ void channel_scale_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ gate, long long S, int C,
+// x[b][pos][c] *= gate[b][c]  (channels-last, C % 8 == 0)
+template <typename T>
+__global__ void channel_scale_kernel(T* __restrict__ x, const float* __restrict__ gate, long long S, int C,
                                      int cstride, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int cv = (int)(i % (C / 8));
   const long long pos = i / (C / 8);
   const long long b = pos / S;
-  __nv_bfloat16* p = x + pos * cstride + cv * 8;
+  T* p = x + pos * cstride + cv * 8;
   float v[8];
-  unpack8(*reinterpret_cast<const uint4*>(p), v);
+  Elem<T>::ld8(p, v);
   const float* g = gate + b * C + cv * 8;
 #pragma unroll
   for (int k = 0; k < 8; ++k) v[k] *= g[k];
-  *reinterpret_cast<uint4*>(p) = pack8(v);
+  Elem<T>::st8(p, v);
 }
 
 }  // namespace
@@ -165,13 +166,14 @@ extern "C" int occd_fc_fwd(const float* in, const float* w, const float* bias, f
   return OCCD_OK;
 }
 
-extern "C" int occd_channel_scale(void* x, const float* gate, long long B, long long S, int C, int cstride,
+extern "C" int occd_channel_scale(void* x, const float* gate, int dtype, long long B, long long S, int C, int cstride,
                                   void* stream) {
   OCCD_CHECK_ARG(x && gate && B > 0 && S > 0 && C > 0 && C % 8 == 0 && cstride % 8 == 0 && cstride >= C,
                  "occd_channel_scale: args");
   const long long total = B * S * (C / 8);
-  channel_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (__nv_bfloat16*)x, gate, S, C, cstride, total);
+  OCCD_DISPATCH_DTYPE(dtype, T, (channel_scale_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0,
+                                                            (cudaStream_t)stream>>>((T*)x, gate, S, C, cstride,
+                                                                                    total)));
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }
@@ -182,7 +184,8 @@ namespace {
 // align_corners=False) -> disparity bf/scale / depth (inf -> 0) -> base grid arange(-1,1,2/h) (pixel-CORNER
 // coordinates) shifted by disparity*2/w -> F.grid_sample(bilinear, border, align_corners=False).
 // The reference uses batch item 0's disparity for every item (:257); kept.
-__global__ void virtual_view_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+template <typename T>
+__global__ void virtual_view_kernel(const T* __restrict__ in, T* __restrict__ out,
                                     const float* __restrict__ depth, int B, int h, int w, int CV, int cs_in,
                                     int cs_out, int dh, int dw, float bf_scale) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -213,28 +216,29 @@ __global__ void virtual_view_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
   const int ix0 = (int)floorf(fx), iy0 = (int)floorf(fy);
   const int ix1 = min(ix0 + 1, w - 1), iy1 = min(iy0 + 1, h - 1);
   const float tx = fx - ix0, ty = fy - iy0;
-  const __nv_bfloat16* base = in + (long long)b * h * w * cs_in + cv * 8;
+  const T* base = in + (long long)b * h * w * cs_in + cv * 8;
   float a[8], bb[8], c[8], dd[8], o[8];
-  unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long long)iy0 * w + ix0) * cs_in)), a);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long long)iy0 * w + ix1) * cs_in)), bb);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long long)iy1 * w + ix0) * cs_in)), c);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(base + ((long long)iy1 * w + ix1) * cs_in)), dd);
+  Elem<T>::ld8_nc(base + ((long long)iy0 * w + ix0) * cs_in, a);
+  Elem<T>::ld8_nc(base + ((long long)iy0 * w + ix1) * cs_in, bb);
+  Elem<T>::ld8_nc(base + ((long long)iy1 * w + ix0) * cs_in, c);
+  Elem<T>::ld8_nc(base + ((long long)iy1 * w + ix1) * cs_in, dd);
 #pragma unroll
   for (int k = 0; k < 8; ++k)
     o[k] = (1.f - ty) * ((1.f - tx) * a[k] + tx * bb[k]) + ty * ((1.f - tx) * c[k] + tx * dd[k]);
-  *reinterpret_cast<uint4*>(out + (((long long)b * h + y) * w + x) * cs_out + cv * 8) = pack8(o);
+  Elem<T>::st8(out + (((long long)b * h + y) * w + x) * cs_out + cv * 8, o);
 }
 }  // namespace
 
-extern "C" int occd_virtual_view_fwd(const void* in, void* out, const float* depth, int B, int h, int w, int C,
-                                     int cs_in, int cs_out, int dh, int dw, float bf_scale, void* stream) {
+extern "C" int occd_virtual_view_fwd(const void* in, void* out, const float* depth, int dtype, int B, int h, int w,
+                                     int C, int cs_in, int cs_out, int dh, int dw, float bf_scale, void* stream) {
   OCCD_CHECK_ARG(in && out && depth && B > 0 && h > 0 && w > 0 && C > 0 && dh > 0 && dw > 0 && cs_in % 8 == 0 &&
                  cs_out % 8 == 0, "occd_virtual_view_fwd: args");
   const int CV = (C + 7) / 8;
   OCCD_CHECK_ARG(CV * 8 <= cs_in && CV * 8 <= cs_out, "occd_virtual_view_fwd: channel window");
   const long long total = (long long)B * h * w * CV;
-  virtual_view_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)in, (__nv_bfloat16*)out, depth, B, h, w, CV, cs_in, cs_out, dh, dw, bf_scale);
+  OCCD_DISPATCH_DTYPE(dtype, T, (virtual_view_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0,
+                                                           (cudaStream_t)stream>>>(
+                                     (const T*)in, (T*)out, depth, B, h, w, CV, cs_in, cs_out, dh, dw, bf_scale)));
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }

@@ -217,8 +217,12 @@ sfa_lift_kernel(const SfaKParams p) {
           u.y = *reinterpret_cast<unsigned*>(&hi);
           *reinterpret_cast<uint2*>(o) = u;
         }
-      } else if (p.out_mode == OCCD_SFA_OUT_F32_CL) {
+      } else if (p.out_mode == OCCD_SFA_OUT_F32_CL || p.out_mode == OCCD_SFA_OUT_TF32_CL) {
         float* o = reinterpret_cast<float*>(p.out) + no * p.out_cstride + c0;
+        if (p.out_mode == OCCD_SFA_OUT_TF32_CL) {   // operand of the 3-D net's kind::tf32 convolutions
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[j * VEC + e] = round_tf32(acc[j * VEC + e]);
+        }
 #pragma unroll
         for (int e = 0; e < VEC; e += 4)
           *reinterpret_cast<float4*>(o + e) =
@@ -382,8 +386,12 @@ sfa_lift_p1_kernel(const SfaKParams p) {
           u.y = *reinterpret_cast<unsigned*>(&hi);
           *reinterpret_cast<uint2*>(o) = u;
         }
-      } else if (p.out_mode == OCCD_SFA_OUT_F32_CL) {
+      } else if (p.out_mode == OCCD_SFA_OUT_F32_CL || p.out_mode == OCCD_SFA_OUT_TF32_CL) {
         float* o = reinterpret_cast<float*>(p.out) + no * p.out_cstride + c0;
+        if (p.out_mode == OCCD_SFA_OUT_TF32_CL) {   // operand of the 3-D net's kind::tf32 convolutions
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[j * VEC + e] = round_tf32(acc[j * VEC + e]);
+        }
 #pragma unroll
         for (int e = 0; e < VEC; e += 4)
           *reinterpret_cast<float4*>(o + e) =
@@ -462,7 +470,7 @@ extern "C" int occd_sfa_lift_fwd(const occd_sfa_params* a, void* stream) {
   OCCD_CHECK_ARG(a->feat_dtype == OCCD_DTYPE_F32 || a->feat_dtype == OCCD_DTYPE_BF16, "occd_sfa_lift_fwd: feat dtype");
   const int vec = a->feat_dtype == OCCD_DTYPE_F32 ? 4 : 8;
   OCCD_CHECK_ARG(a->C > 0 && a->C % vec == 0, "occd_sfa_lift_fwd: C must be a multiple of the 16-byte vector width");
-  OCCD_CHECK_ARG(a->out_mode >= 0 && a->out_mode <= 2, "occd_sfa_lift_fwd: out_mode");
+  OCCD_CHECK_ARG(a->out_mode >= 0 && a->out_mode <= 3, "occd_sfa_lift_fwd: out_mode");
   if (a->out_mode != OCCD_SFA_OUT_F32_PLANAR)
     OCCD_CHECK_ARG(a->out_cstride >= a->C && a->out_cstride % vec == 0, "occd_sfa_lift_fwd: out_cstride");
   if (a->N == 0) return OCCD_OK;

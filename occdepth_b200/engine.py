@@ -20,48 +20,59 @@ def _round_up(a, b):
     return (a + b - 1) // b * b
 
 
+PRECISIONS = ("tf32", "bf16")
+TORCH_DTYPE = {"tf32": torch.float32, "bf16": torch.bfloat16}
+LIB_DTYPE = {"tf32": _lib.DTYPE_F32, "bf16": _lib.DTYPE_BF16}
+
+
+def default_precision():
+    """Arithmetic mode of the planned forward (OCCDEPTH_PRECISION, default 'tf32'):
+
+    'tf32': activations are fp32 tensors holding TF32 values, convolutions run as tcgen05 kind::tf32 with fp32
+            accumulation -- the reference's precision (fp32 nn.Conv*d, which PyTorch itself executes on TF32 tensor
+            cores on CUDA); this is the mode the parity tests and the bench headline use.
+    'bf16': bf16 activations and operands (kind::f16), fp32 accumulation -- the throughput mode, own tolerance."""
+    v = os.environ.get("OCCDEPTH_PRECISION", "tf32").lower()
+    if v not in PRECISIONS:
+        raise ValueError("OCCDEPTH_PRECISION must be 'tf32' or 'bf16'")
+    return v
+
+
+def precision_of(torch_dtype):
+    return "tf32" if torch_dtype == torch.float32 else "bf16"
+
+
+def round_tf32_(t):
+    """fp32 tensor -> nearest TF32 value (10-bit mantissa, ties away from zero == cvt.rna.tf32.f32), in place"""
+    i = t.view(torch.int32)
+    i.add_(0x1000).bitwise_and_(-0x2000)
+    return t
+
+
+def chunk_channels(C_, esize):
+    """channels per K chunk (one swizzled smem row of 32 / 64 / 128 bytes), mirrors csrc/conv.cu"""
+    for rb in (32, 64, 128):
+        if C_ <= rb // esize:
+            return rb // esize
+    return 128 // esize
+
+
 def default_impl():
-    """'auto' (default): halo-tile tcgen05 kernel where the shape qualifies, else the per-tap tcgen05 kernel;
-    'tc' / 'halo' / 'simt' force one implementation (simt = CUDA-core cross-check)."""
+    """'auto' (default): halo-tile tcgen05 kernel where the shape qualifies, the x-packed per-tap kernel for
+    narrow-output convs with W taps, else the per-tap tcgen05 kernel; 'tc' / 'tcx' / 'halo' / 'simt' force one
+    implementation (simt = CUDA-core cross-check)."""
     v = os.environ.get("OCCDEPTH_CONV_IMPL", "auto").lower()
-    if v not in ("auto", "tc", "simt", "halo", "halox", "tcx", "tcm2"):
-        raise ValueError("OCCDEPTH_CONV_IMPL must be 'auto', 'tc', 'tcx', 'tcm2', 'halo', 'halox' or 'simt'")
+    if v not in ("auto", "tc", "simt", "halo", "tcx"):
+        raise ValueError("OCCDEPTH_CONV_IMPL must be 'auto', 'tc', 'tcx', 'halo' or 'simt'")
     return {"auto": None, "tc": _lib.CONV_IMPL_TC, "simt": _lib.CONV_IMPL_SIMT, "halo": _lib.CONV_IMPL_HALO,
-            "halox": _lib.CONV_IMPL_HALOX, "tcx": _lib.CONV_IMPL_TCX, "tcm2": _lib.CONV_IMPL_TCM2}[v]
-
-
-def prefer_tcm2():
-    """OCCDEPTH_TCM2=1: in 'auto' mode run wide, large convs on the M2 kernel (two M tiles per weight tile).  Off by
-    default, same status as OCCDEPTH_HALOX / OCCDEPTH_TCX."""
-    return os.environ.get("OCCDEPTH_TCM2", "0") == "1"
-
-
-def tcm2_eligible(B, out_dims, Cout_pad, n_items, weight_per_image, n_sms=148):
-    """wide layers (N tile >= 128) with enough work that the halved tile count still fills the GPU"""
-    if weight_per_image or Cout_pad < 128 or n_items < 9:
-        return False
-    n_tile = max(n for n in range(16, min(256, Cout_pad) + 1, 16) if Cout_pad % n == 0)
-    if n_tile < 128:
-        return False
-    m_tiles = -(-(B * out_dims[0] * out_dims[1] * out_dims[2]) // 128)
-    return (m_tiles + 1) // 2 * (Cout_pad // n_tile) >= 2 * n_sms
-
-
-def prefer_halox():
-    """OCCDEPTH_HALOX=1: in 'auto' mode try the x-packed halo kernel (three W taps per MMA) first where the tap
-    list qualifies.  Off by default: its plan geometry and lane-shift epilogue are checked on the CPU model
-    (tests/test_halo_model_host.py); the kernel itself has not run on a B200 yet."""
-    return os.environ.get("OCCDEPTH_HALOX", "0") == "1"
-
-
-def prefer_tcx():
-    """OCCDEPTH_TCX=1: in 'auto' mode use the x-packed per-tap kernel where the tap list qualifies (W taps -1,0,+1,
-    W stride 1, 3*Cout_pad <= 256).  Off by default, same status as OCCDEPTH_HALOX (tests/test_tc_model_host.py)."""
-    return os.environ.get("OCCDEPTH_TCX", "0") == "1"
+            "tcx": _lib.CONV_IMPL_TCX}[v]
 
 
 def tcx_eligible(taps, stride, Cout_pad):
-    if len(taps) % 3 or 3 * Cout_pad > 256 or stride[2] != 1:
+    """(src, dz, dy) groups of three W taps -1, 0, +1 (what conv_taps emits for a dense 3-wide kernel), W stride 1,
+    N = 3*Cout_pad <= 256, and enough output channels that the packed MMA beats three narrow ones (measured on
+    B200, profiles/r02_convbench_tcx.txt: Cout 80 0.154 -> 0.102 ms; Cout 32 loses to the halo kernel)"""
+    if len(taps) % 3 or 3 * Cout_pad > 256 or Cout_pad < 48 or stride[2] != 1:
         return False
     for i in range(0, len(taps), 3):
         a, b, c = taps[i], taps[i + 1], taps[i + 2]
@@ -70,24 +81,13 @@ def tcx_eligible(taps, stride, Cout_pad):
     return True
 
 
-def halox_eligible(taps, Cout_pad):
-    """(dz, dy) groups of three W taps -d, 0, +d in lexicographic order (what conv_taps emits), N = 3*Cout_pad <= 256"""
-    if len(taps) % 3 or 3 * Cout_pad > 256:
-        return False
-    for i in range(0, len(taps), 3):
-        a, b, c = taps[i], taps[i + 1], taps[i + 2]
-        if not (a[:3] == b[:3] == c[:3] and b[3] == 0 and c[3] > 0 and a[3] == -c[3]):
-            return False
-    return True
-
-
 def halo_eligible(srcs, taps, stride, omul, out_dims, Cout_pad, weight_buf):
-    """shape test mirroring build_halo_plan (csrc/conv.cu): stride-1 'same' conv, {-d,0,d} taps, few channels"""
+    """shape test mirroring halo_geometry (csrc/conv.cu): stride-1 'same' conv, {-d,0,d} taps, one K chunk"""
     if len(srcs) != 1 or weight_buf is not None or len(taps) < 3 or len(taps) > 27:
         return False
     if tuple(stride) != (1, 1, 1) or tuple(omul) != (1, 1, 1) or tuple(out_dims) != tuple(srcs[0].dims[1:]):
         return False
-    if srcs[0].C > 64 or Cout_pad > 64:
+    if srcs[0].C > 128 // srcs[0].esize or Cout_pad > 64:
         return False
     offs = {abs(o) for t in taps for o in t[1:] if o}
     return len(offs) == 1
@@ -99,14 +99,15 @@ def require_cuda(t, what):
 
 
 class CL:
-    """channels-last bf16 activation: a channel window [coff, coff+C) of a [B,D,H,W,cstride] buffer.
+    """channels-last activation (bf16, or fp32 holding TF32 values): a channel window [coff, coff+C) of a
+    [B,D,H,W,cstride] buffer.
 
     X-slab multi-GPU partition: a buffer may carry `halo` margin planes on both sides of D; the CL then denotes the
     INTERIOR planes [d0, d0+dlen) (what this rank owns and writes) while convolutions read the margins
     (neighbour data put there by HaloExchangeOp, zeros at the global boundary).  Requires B == 1."""
 
     def __init__(self, buf, C_, coff=0, d0=0, dlen=None):
-        assert buf.dtype == torch.bfloat16 and buf.dim() == 5 and buf.is_contiguous()
+        assert buf.dtype in (torch.bfloat16, torch.float32) and buf.dim() == 5 and buf.is_contiguous()
         self.buf, self.C, self.coff = buf, int(C_), int(coff)
         self.d0 = int(d0)
         self.dlen = int(buf.shape[1] - 2 * d0 if dlen is None else dlen)
@@ -114,13 +115,26 @@ class CL:
         assert self.d0 == 0 or buf.shape[0] == 1
 
     @staticmethod
-    def alloc(B, D, H, W, C_, device, halo=0):
-        buf = torch.zeros(B, D + 2 * halo, H, W, _round_up(C_, 8), dtype=torch.bfloat16, device=device)
+    def alloc(B, D, H, W, C_, device, halo=0, precision=None):
+        dt = TORCH_DTYPE[precision or default_precision()]
+        buf = torch.zeros(B, D + 2 * halo, H, W, _round_up(C_, 8), dtype=dt, device=device)
         return CL(buf, C_, 0, halo, D)
 
     @property
     def halo(self):
         return self.d0
+
+    @property
+    def precision(self):
+        return precision_of(self.buf.dtype)
+
+    @property
+    def lib_dtype(self):
+        return LIB_DTYPE[self.precision]
+
+    @property
+    def esize(self):
+        return self.buf.element_size()
 
     @property
     def dims(self):
@@ -137,7 +151,7 @@ class CL:
     @property
     def ptr(self):
         """pointer to the first INTERIOR plane"""
-        return self.buf.data_ptr() + 2 * self.d0 * self.plane_elems
+        return self.buf.data_ptr() + self.esize * self.d0 * self.plane_elems
 
     @property
     def full_ptr(self):
@@ -155,8 +169,8 @@ class CL:
 
     # ---- module-boundary conversions (reference tensors are NCHW / NCDHW fp32) ----
     @staticmethod
-    def from_planar(x, out=None):
-        """x: fp32 [B,C,H,W] or [B,C,D,H,W] (CUDA) -> CL (bf16)."""
+    def from_planar(x, out=None, precision=None):
+        """x: fp32 [B,C,H,W] or [B,C,D,H,W] (CUDA) -> CL."""
         require_cuda(x, "CL.from_planar")
         x = x.contiguous().float()
         if x.dim() == 4:
@@ -165,10 +179,10 @@ class CL:
         else:
             B, C_, D, H, W = x.shape
         if out is None:
-            out = CL.alloc(B, D, H, W, C_, x.device)
+            out = CL.alloc(B, D, H, W, C_, x.device, precision=precision)
         assert out.coff == 0 and out.C == C_
         S = D * H * W
-        rc = _lib.lib().occd_planar_to_cl(x.data_ptr(), out.ptr, _lib.DTYPE_BF16, B, C_, S, out.cstride,
+        rc = _lib.lib().occd_planar_to_cl(x.data_ptr(), out.ptr, out.lib_dtype, B, C_, S, out.cstride,
                                           _lib.stream_ptr())
         _lib.check(rc, "occd_planar_to_cl")
         return out
@@ -178,8 +192,8 @@ class CL:
         B, D, H, W = self.dims
         out = torch.empty(B, self.C, D, H, W, dtype=torch.float32, device=self.buf.device)
         S = D * H * W
-        rc = _lib.lib().occd_cl_to_planar(self.ptr + 2 * self.coff, _lib.DTYPE_BF16, out.data_ptr(), B, self.C, S,
-                                          self.cstride, _lib.stream_ptr())
+        rc = _lib.lib().occd_cl_to_planar(self.ptr + self.esize * self.coff, self.lib_dtype, out.data_ptr(), B,
+                                          self.C, S, self.cstride, _lib.stream_ptr())
         _lib.check(rc, "occd_cl_to_planar")
         return out[:, :, 0] if squeeze_d else out
 
@@ -202,7 +216,8 @@ class ConvOp:
 
     def __init__(self, srcs, taps, tap_weights, bias, out_dims, out0=None, act="none", res1=None, res2=None,
                  stride=(1, 1, 1), omul=(1, 1, 1), oadd=(0, 0, 0), full_dims=None, out1=None, out1_mode="none",
-                 out1_coff=0, impl=None, name="", res2_post=False, weight_buf=None, weight_per_image=False):
+                 out1_coff=0, impl=None, name="", res2_post=False, weight_buf=None, weight_per_image=False,
+                 out0_exact=False):
         """srcs: list[CL] (same B,D,H,W);  taps: [(src_idx, dz, dy, dx)];  tap_weights: list of fp32 [Cout, C_src]
         bias: fp32 [Cout];  out0/res1/res2: CL on the full output grid;  out1: CL (pre-activation bf16 copy) or
         fp32 planar tensor [B, C1, D, H, W] (mode "planar", written at channel out1_coff)."""
@@ -214,19 +229,23 @@ class ConvOp:
         Cout = int(bias.numel())
         Cout_pad = _round_up(Cout, 16)
         maxC = max(s.C for s in srcs)
-        KC = 64 if maxC > 32 else (32 if maxC > 16 else 16)
+        adt = srcs[0].buf.dtype
+        for s in srcs:
+            assert s.buf.dtype == adt
+        esize = srcs[0].esize
+        KC = chunk_channels(maxC, esize)
         Kpad = _round_up(maxC, KC)
         if weight_buf is not None:
-            # weights produced at run time by another launch (CRP bmm): bf16 [n_taps, Cout_pad, Kpad]
+            # weights produced at run time by another launch (CRP bmm): [n_taps, Cout_pad, Kpad] in the plan's dtype
             nset = B if weight_per_image else 1
-            assert weight_buf.dtype == torch.bfloat16 and tuple(weight_buf.shape) == (nset * len(taps), Cout_pad, Kpad)
+            assert weight_buf.dtype == adt and tuple(weight_buf.shape) == (nset * len(taps), Cout_pad, Kpad)
             self.weight = weight_buf
         else:
             wp = torch.zeros(len(taps), Cout_pad, Kpad, dtype=torch.float32, device=dev)
             for i, (tp, w) in enumerate(zip(taps, tap_weights)):
                 assert w.shape == (Cout, srcs[tp[0]].C), (w.shape, Cout, srcs[tp[0]].C)
                 wp[i, :Cout, : w.shape[1]] = w
-            self.weight = wp.to(torch.bfloat16).contiguous()
+            self.weight = (round_tf32_(wp) if adt == torch.float32 else wp.to(torch.bfloat16)).contiguous()
         self.bias = torch.zeros(Cout_pad, dtype=torch.float32, device=dev)
         self.bias[:Cout] = bias.float()
         OD, OH, OW = out_dims
@@ -238,15 +257,10 @@ class ConvOp:
         if auto:
             impl = (_lib.CONV_IMPL_HALO if halo_eligible(srcs, taps, stride, omul, out_dims, Cout_pad, weight_buf)
                     else _lib.CONV_IMPL_TC)
-            if impl == _lib.CONV_IMPL_HALO and prefer_halox() and halox_eligible(taps, Cout_pad):
-                impl = _lib.CONV_IMPL_HALOX
-            if impl == _lib.CONV_IMPL_TC and prefer_tcx() and tcx_eligible(taps, stride, Cout_pad):
+            if impl == _lib.CONV_IMPL_TC and tcx_eligible(taps, stride, Cout_pad):
                 impl = _lib.CONV_IMPL_TCX
-            n_items = sum(-(-srcs[t[0]].C // KC) for t in taps)
-            if impl == _lib.CONV_IMPL_TC and prefer_tcm2() and tcm2_eligible(B, out_dims, Cout_pad, n_items,
-                                                                              weight_per_image):
-                impl = _lib.CONV_IMPL_TCM2
         d.impl = impl
+        d.dtype = LIB_DTYPE[precision_of(adt)]
         d.n_src = len(srcs)
         for i, s in enumerate(srcs):
             assert s.d0 == srcs[0].d0 and s.buf.shape[1] == srcs[0].buf.shape[1]
@@ -266,19 +280,20 @@ class ConvOp:
         d.ODf, d.OHf, d.OWf = fd
         d.act = ACT[act]
         d.res2_post = 1 if res2_post else 0
+        d.out0_exact = 1 if out0_exact else 0
         self._keep = [srcs, out0, res1, res2, out1]
         if out0 is not None:
-            assert out0.dims == (B,) + fd and out0.C >= Cout, (out0.dims, fd, out0.C, Cout)
+            assert out0.dims == (B,) + fd and out0.C >= Cout and out0.buf.dtype == adt, (out0.dims, fd, out0.C, Cout)
             d.out0, d.out0_cstride, d.out0_coff = out0.ptr, out0.cstride, out0.coff
         for nm, r in (("res1", res1), ("res2", res2)):
             if r is not None:
-                assert r.dims == (B,) + fd and r.C >= Cout
+                assert r.dims == (B,) + fd and r.C >= Cout and r.buf.dtype == adt
                 setattr(d, nm, r.ptr)
                 setattr(d, nm + "_cstride", r.cstride)
                 setattr(d, nm + "_coff", r.coff)
         if out1_mode == "cl":
-            assert out1.dims == (B,) + fd
-            d.out1_mode, d.out1 = _lib.OUT1_BF16_CL, out1.ptr
+            assert out1.dims == (B,) + fd and out1.buf.dtype == adt
+            d.out1_mode, d.out1 = _lib.OUT1_CL, out1.ptr
             d.out1_cstride, d.out1_coff = out1.cstride, out1.coff
         elif out1_mode == "planar":
             assert out1.dtype == torch.float32 and out1.is_contiguous() and tuple(out1.shape[2:]) == fd
@@ -288,11 +303,8 @@ class ConvOp:
         self.flops = 2 * B * OD * OH * OW * Cout * sum(srcs[t[0]].C for t in taps)
         h = C.c_void_p()
         rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
-        if rc != 0 and auto and d.impl in (_lib.CONV_IMPL_TCX, _lib.CONV_IMPL_TCM2):
+        if rc != 0 and auto and d.impl == _lib.CONV_IMPL_TCX:
             d.impl = _lib.CONV_IMPL_TC
-            rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
-        if rc != 0 and auto and d.impl == _lib.CONV_IMPL_HALOX:
-            d.impl = _lib.CONV_IMPL_HALO    # x-packed geometry did not fit: 27-tap halo kernel
             rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
         if rc != 0 and auto and d.impl == _lib.CONV_IMPL_HALO:
             d.impl = _lib.CONV_IMPL_TC      # shape did not fit the halo scheme: per-tap tcgen05 kernel
@@ -341,8 +353,13 @@ def out_size(i, k, s, p, d):
 class Plan:
     """Ordered list of prepared launches (anything with .run(stream)) + named buffers."""
 
-    def __init__(self, device, slab=None):
+    def __init__(self, device, slab=None, precision=None):
         self.device = device
+        self.precision = precision or default_precision()
+        assert self.precision in PRECISIONS
+        self.dtype = TORCH_DTYPE[self.precision]        # element type of every activation / GEMM weight buffer
+        self.lib_dtype = LIB_DTYPE[self.precision]
+        self.esize = 4 if self.precision == "tf32" else 2
         self.ops = []
         self.flops = 0
         self.graph, self.graph_ops = None, 0
@@ -352,7 +369,15 @@ class Plan:
     def alloc(self, B, D, H, W, C_):
         """3-D activations (D > 1) of a slab-partitioned plan get halo margins; everything else is dense."""
         halo = self.slab.halo if (self.slab is not None and D > 1) else 0
-        return CL.alloc(B, D, H, W, C_, self.device, halo=halo)
+        return CL.alloc(B, D, H, W, C_, self.device, halo=halo, precision=self.precision)
+
+    def kpad_for(self, C_):
+        return _round_up(C_, chunk_channels(C_, self.esize))
+
+    def pack_weights(self, w):
+        """fp32 GEMM weights -> this plan's operand type (TF32-rounded fp32 or bf16)"""
+        w = w.detach().float().contiguous()
+        return round_tf32_(w.clone()) if self.precision == "tf32" else w.to(torch.bfloat16)
 
     def need_halo(self, src, taps, stride0, out_d):
         """Insert the neighbour exchange for `src` before a conv whose taps reach across the slab boundary."""
@@ -379,7 +404,8 @@ class Plan:
 
     # ---- dense convolution (2-D maps have D == 1) ----
     def conv(self, x, weight, bias, stride=1, padding=0, dilation=1, act="none", out=None, res1=None, res2=None,
-             out1=None, out1_mode="none", out1_coff=0, name="conv", impl=None, res2_post=False, no_out0=False):
+             out1=None, out1_mode="none", out1_coff=0, name="conv", impl=None, res2_post=False, no_out0=False,
+             out0_exact=False):
         """x: CL; weight fp32 [Cout,Cin,kd,kh,kw] (BN already folded); returns the output CL."""
         s, p, d = _t3(stride), _t3(padding), _t3(dilation)
         B, ID, IH, IW = x.dims
@@ -392,7 +418,8 @@ class Plan:
         taps, ws = conv_taps(weight, d, p)
         self.need_halo(x, taps, s[0], od[0])
         self.add(ConvOp([x], taps, ws, bias, od, out0=out, act=act, res1=res1, res2=res2, stride=s, out1=out1,
-                        out1_mode=out1_mode, out1_coff=out1_coff, name=name, impl=impl, res2_post=res2_post))
+                        out1_mode=out1_mode, out1_coff=out1_coff, name=name, impl=impl, res2_post=res2_post,
+                        out0_exact=out0_exact))
         return out
 
     def conv_multi(self, srcs, weights, bias, paddings, dilations, act="none", out=None, res1=None, res2=None,
@@ -499,6 +526,5 @@ class FnOp:
         _lib.check(self.fn(stream), self.name)
 
 
-def kpad_for(C_):
-    KC = 64 if C_ > 32 else (32 if C_ > 16 else 16)
-    return _round_up(C_, KC)
+def kpad_for(C_, esize=2):
+    return _round_up(C_, chunk_channels(C_, esize))

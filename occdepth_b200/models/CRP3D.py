@@ -54,21 +54,23 @@ class CPMegaVoxels(B200Module):
         if slab is not None:
             from ..engine import CL
             _, cd, ch, cw = ctx.dims
-            full = CL.alloc(1, cd * slab.world, ch, cw, F2, plan.device)
+            full = CL.alloc(1, cd * slab.world, ch, cw, F2, plan.device, precision=plan.precision)
             plan.add(slab.all_gather_op(ctx.interior(), full.buf))
             ctx = full
         assert ctx.spatial() == M
         # mega-context as the K-major B operand of the bmm: wbuf[b][f][m] = ctx[b][m][f]
-        Kp = kpad_for(M)
+        Kp = plan.kpad_for(M)
         F2p = _round_up(F2, 16)
-        wbuf = torch.zeros(B, 1, F2p, Kp, dtype=torch.bfloat16, device=plan.device)
-        plan.add(FnOp(lambda st: L.occd_cl_transpose(ctx.ptr, wbuf.data_ptr(), B, M, F2, ctx.cstride, ctx.coff, Kp,
-                                                     F2p * Kp, st), "occd_cl_transpose", keep=(ctx, wbuf)))
+        wbuf = torch.zeros(B, 1, F2p, Kp, dtype=plan.dtype, device=plan.device)
+        plan.add(FnOp(lambda st: L.occd_cl_transpose(ctx.ptr, wbuf.data_ptr(), plan.lib_dtype, B, M, F2, ctx.cstride,
+                                                     ctx.coff, Kp, F2p * Kp, st), "occd_cl_transpose",
+                      keep=(ctx, wbuf)))
         P_logits = torch.empty(B, R, M, N, dtype=torch.float32, device=plan.device)
         p_view = P_logits.view(B, R * M, D, H, W)
         cat = plan.alloc(B, D, H, W, F1 + R * F2)
-        plan.add(FnOp(lambda st: L.occd_copy_channels(x.ptr, cat.ptr, B * N, F1, x.cstride, x.coff, cat.cstride,
-                                                      cat.coff, st), "occd_copy_channels", keep=(x, cat)))
+        plan.add(FnOp(lambda st: L.occd_copy_channels(x.ptr, cat.ptr, plan.lib_dtype, B * N, F1, x.cstride, x.coff,
+                                                      cat.cstride, cat.coff, st), "occd_copy_channels",
+                      keep=(x, cat)))
         zero_bias = torch.zeros(F2, device=plan.device)
         for r in range(R):
             c = self.context_prior_logits[r][0]

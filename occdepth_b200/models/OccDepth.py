@@ -121,7 +121,7 @@ class OccDepth(_Base, B200Module):
     # ------------------------------------------------------------------------------------------
     def _build(self, B, V, H, W, N, P, dev, batch):
         slab = self.__dict__.get("slab_ctx")
-        plan = Plan(dev, slab=slab)
+        plan = Plan(dev, slab=slab, precision=self.precision)
         ps = self.project_scale
         S = [int(s) // ps for s in self.full_scene_size]
         n_lo = 0
@@ -146,7 +146,7 @@ class OccDepth(_Base, B200Module):
             # view-major buffers [2, B, h, w, C]: the 2D net writes view 0, the virtual-view kernel view 1
             for s in scales:
                 h_s, w_s = feature_hw(H, W, s)
-                vb = torch.zeros(2, B, h_s, w_s, Cf, dtype=torch.bfloat16, device=dev)
+                vb = torch.zeros(2, B, h_s, w_s, Cf, dtype=plan.dtype, device=dev)
                 views[s] = vb
                 outs["1_%d" % s] = CL(vb[0].unsqueeze(1), Cf)
         x_rgb = self.net_rgb.emit(plan, img, outs)                          # {"1_s": CL [B*V,1,h,w,Cf]}
@@ -160,7 +160,7 @@ class OccDepth(_Base, B200Module):
                 vb = views[s]
                 _, _, h_s, w_s, _ = vb.shape
                 plan.add(FnOp(lambda st, vb=vb, h_s=h_s, w_s=w_s, s=s: L.occd_virtual_view_fwd(
-                    vb[0].data_ptr(), vb[1].data_ptr(), depth0.data_ptr(), B, h_s, w_s, Cf, Cf, Cf,
+                    vb[0].data_ptr(), vb[1].data_ptr(), depth0.data_ptr(), plan.lib_dtype, B, h_s, w_s, Cf, Cf, Cf,
                     depth0.shape[0], depth0.shape[1], bf / s, st), "virtual_view_1_%d" % s, keep=(vb, depth0)))
         pix = torch.zeros(B, VL, N, P, 2, dtype=torch.int64, device=dev)
         fov = torch.zeros(B, VL, N, P, dtype=torch.bool, device=dev)
@@ -214,9 +214,14 @@ class OccDepth(_Base, B200Module):
         virtual = V == 1 and "gt_depth" in batch
         slab = self.__dict__.get("slab_ctx")
         key = (B, V, H, W, N, P, str(dev), virtual, float(batch["virtual_bf"][0]) if virtual else 0.0,
-               None if slab is None else (slab.rank, slab.world))
+               None if slab is None else (slab.rank, slab.world), self.precision, self.param_stamp())
+        with torch.cuda.device(dev):           # launches, tensor maps and function attributes follow the tensors
+            return self._forward_on(batch, key, img, pp, fm, B, V, H, W, N, P, dev)
+
+    def _forward_on(self, batch, key, img, pp, fm, B, V, H, W, N, P, dev):
         ent = self._plans().get(key)
         if ent is None:
+            self._plans().clear()              # weights changed / new shape: drop the stale snapshot
             with torch.no_grad():
                 ent = self._build(B, V, H, W, N, P, dev, batch)
             self._plans()[key] = ent

@@ -78,14 +78,17 @@ def lift_multiscale(feats, divs, projected_pix, fov_mask, out, dataset, scene_si
     V = feats[0].shape[0]
     Cch = feats[0].shape[3]
     for i, (f, dv) in enumerate(zip(feats, divs)):
-        assert f.dtype == torch.bfloat16 and f.shape[0] == V and f.shape[3] == Cch
+        assert f.dtype == feats[0].dtype and f.shape[0] == V and f.shape[3] == Cch
         assert f[0].is_contiguous() and f.stride(3) == 1
         p.feat[i], p.h[i], p.w[i], p.div[i] = f.data_ptr(), f.shape[1], f.shape[2], int(dv)
         p.vstride[i] = f.stride(0) if V > 1 else 0
-    p.n_scales, p.feat_dtype = len(feats), _lib.DTYPE_BF16
+    tf32 = feats[0].dtype == torch.float32
+    assert tf32 or feats[0].dtype == torch.bfloat16
+    assert out.buf.dtype == feats[0].dtype
+    p.n_scales, p.feat_dtype = len(feats), (_lib.DTYPE_F32 if tf32 else _lib.DTYPE_BF16)
     _fill_common(p, projected_pix, fov_mask, V, Cch)
     assert out.coff == 0 and out.C == Cch and out.spatial() == p.N
-    p.out, p.out_mode, p.out_cstride = out.ptr, _lib.SFA_OUT_BF16_CL, out.cstride
+    p.out, p.out_mode, p.out_cstride = out.ptr, (_lib.SFA_OUT_TF32_CL if tf32 else _lib.SFA_OUT_BF16_CL), out.cstride
     _nyu_perm(p, dataset, scene_size, project_scale)
     if prior is not None:
         assert prior.dtype == torch.float32 and prior.numel() == p.N

@@ -67,15 +67,6 @@ def _dw_entry(L):
     return L.occd_dwconv2d_tiled_fwd if impl == "tiled" else L.occd_dwconv2d_fwd
 
 
-def _se_entry(L):
-    """SE MLP + gate fold entry point.  OCCDEPTH_SE_IMPL=strip selects the one-CTA-per-32-channel-strip fold
-    (each gate evaluated once; CPU-emulation tested, not yet timed on a B200), default is the 256-wide fold."""
-    impl = os.environ.get("OCCDEPTH_SE_IMPL", "wide")
-    if impl not in ("wide", "strip"):
-        raise ValueError(f"OCCDEPTH_SE_IMPL must be 'wide' or 'strip', got {impl!r}")
-    return L.occd_se_gate_fold_strip_fwd if impl == "strip" else L.occd_se_gate_fold_fwd
-
-
 def _emit_dw_se_project(plan, x, conv_dw, bn_dw, se, conv_proj, bn_proj, k, stride, residual, out=None, name=""):
     """dw conv + BN + SiLU (+ squeeze) -> SE gate -> gate folded into the 1x1 projection's weights ->
     projection + BN (+ residual).  x: CL [B,1,H,W,C]."""
@@ -91,8 +82,8 @@ def _emit_dw_se_project(plan, x, conv_dw, bn_dw, se, conv_proj, bn_proj, k, stri
     y = plan.alloc(B, 1, OH, OW, Cm)
     pool = torch.zeros(B, Cm, dtype=torch.int64, device=dev)      # squeeze sums, fixed point 2^-24 (deterministic)
     dw_fwd = _dw_entry(L)
-    plan.add(FnOp(lambda st: dw_fwd(x.ptr, wdw.data_ptr(), b.data_ptr(), y.ptr, pool.data_ptr(), B, H,
-                                    W, OH, OW, Cm, x.cstride, y.cstride, k, stride, pt, pl,
+    plan.add(FnOp(lambda st: dw_fwd(x.ptr, wdw.data_ptr(), b.data_ptr(), y.ptr, pool.data_ptr(), plan.lib_dtype, B,
+                                    H, W, OH, OW, Cm, x.cstride, y.cstride, k, stride, pt, pl,
                                     _lib.ACT_SILU, st), name + ".dw", keep=(x, wdw, b, y, pool)))
     R = se.conv_reduce.out_channels
     w1 = se.conv_reduce.weight.detach().float().reshape(R, Cm).contiguous()
@@ -101,18 +92,18 @@ def _emit_dw_se_project(plan, x, conv_dw, bn_dw, se, conv_proj, bn_proj, k, stri
     b2 = se.conv_expand.bias.detach().float().contiguous()
     wp, bp = fold_bn(conv_proj.weight, None, bn_proj)
     Cout = wp.shape[0]
-    Cout_pad, Kp = _round_up(Cout, 16), kpad_for(Cm)
+    Cout_pad, Kp = _round_up(Cout, 16), plan.kpad_for(Cm)
     master = torch.zeros(Cout_pad, Kp, dtype=torch.float32, device=dev)
     master[:Cout, :Cm] = wp.reshape(Cout, Cm)
     if out is None:
         out = plan.alloc(B, 1, OH, OW, Cout)
     hidden = torch.empty(B, R, dtype=torch.float32, device=dev)
     # the gate is per image -> one projection-weight set per image, all images in ONE SE launch pair + ONE GEMM
-    wbuf = torch.zeros(B, Cout_pad, Kp, dtype=torch.bfloat16, device=dev)
-    se_fwd = _se_entry(L)
+    wbuf = torch.zeros(B, Cout_pad, Kp, dtype=plan.dtype, device=dev)
+    se_fwd = L.occd_se_gate_fold_fwd
     plan.add(FnOp(lambda st: se_fwd(
         pool.data_ptr(), 1.0 / (OH * OW), w1.data_ptr(), b1.data_ptr(), w2t.data_ptr(), b2.data_ptr(),
-        hidden.data_ptr(), master.data_ptr(), wbuf.data_ptr(), B, Cm, R, Cout_pad, Kp, st),
+        hidden.data_ptr(), master.data_ptr(), wbuf.data_ptr(), plan.lib_dtype, B, Cm, R, Cout_pad, Kp, st),
         name + ".se", keep=(pool, w1, b1, w2t, b2, hidden, master, wbuf)))
     plan.add(ConvOp([y], [(0, 0, 0, 0)], None, bp, (1, OH, OW), out0=out, res1=residual, weight_buf=wbuf,
                     weight_per_image=True, name=name + ".proj"))

@@ -170,7 +170,8 @@ class FlospDepth(B200Module):
         h2 = fc(h1, dn.mlp.fc2.weight, dn.mlp.fc2.bias, mid, mid, _lib.ACT_NONE, "depthnet.mlp.fc2")
         g1 = fc(h2, dn.se.conv_reduce.weight, dn.se.conv_reduce.bias, mid, mid, _lib.ACT_RELU, "depthnet.se.reduce")
         gate = fc(g1, dn.se.conv_expand.weight, dn.se.conv_expand.bias, mid, mid, _lib.ACT_SIGMOID, "depthnet.se.gate")
-        plan.add(FnOp(lambda st, xg=x: L.occd_channel_scale(xg.ptr, gate.data_ptr(), BV, h * w, mid, xg.cstride, st),
+        plan.add(FnOp(lambda st, xg=x: L.occd_channel_scale(xg.ptr, gate.data_ptr(), plan.lib_dtype, BV, h * w, mid,
+                                                            xg.cstride, st),
                       "depthnet.se.scale", keep=(x, gate)))      # xg bound now: `x` is rebound by the blocks below
         for i, blk in enumerate(dn.depth_conv):
             w1, b1 = fold_bn(blk.conv1.weight, None, blk.bn1)
@@ -220,13 +221,14 @@ class FlospDepth(B200Module):
         if self.training:
             raise RuntimeError("FlospDepth: forward/inference only; call .eval()")
         B, V, C_, h, w = img_feat.shape
-        key = (tuple(img_feat.shape), str(img_feat.device), vox_origin is not None)
+        key = (tuple(img_feat.shape), str(img_feat.device), vox_origin is not None, self.precision, self.param_stamp())
         ent = self._plans().get(key)
         batch = {"cam_k": cam_k, "T_velo_2_cam": T_velo_2_cam, "ida_mats": ida_mats}
         if vox_origin is not None:
             batch["vox_origin"] = vox_origin
         if ent is None:
-            plan = Plan(img_feat.device)
+            self._plans().clear()
+            plan = Plan(img_feat.device, precision=self.precision)
             xin = plan.alloc(B * V, 1, h, w, C_)
             with torch.no_grad():
                 prior = self.emit(plan, {"1_%d" % self.downsample_factor: xin}, batch, B, V)

@@ -112,10 +112,12 @@ class SegmentationHeadCascadeCLS(B200Module):
         L = _lib.lib()
         S = D * H * W
         sm = plan.alloc(B, D, H, W, 2)
-        plan.add(FnOp(lambda st: L.occd_softmax_planar_to_cl(x_occ.data_ptr(), sm.ptr, B, 2, S, sm.cstride, sm.coff,
-                                                            st), "occd_softmax_planar_to_cl", keep=(x_occ, sm)))
+        plan.add(FnOp(lambda st: L.occd_softmax_planar_to_cl(x_occ.data_ptr(), sm.ptr, plan.lib_dtype, B, 2, S,
+                                                            sm.cstride, sm.coff, st), "occd_softmax_planar_to_cl",
+                      keep=(x_occ, sm)))
         w, b = fold_bn(self.conv_classes.weight, self.conv_classes.bias, None)
-        part = plan.conv(x1, w[:, :planes].contiguous(), b, padding=1, name="head.conv_classes.a")
+        # `part` only feeds the second launch's epilogue add (never an MMA operand): stored unrounded in tf32 mode
+        part = plan.conv(x1, w[:, :planes].contiguous(), b, padding=1, name="head.conv_classes.a", out0_exact=True)
         logits = _planar_out(plan, x1, w.shape[0])
         plan.conv(sm, w[:, planes:].contiguous(), torch.zeros_like(b), padding=1, res1=part, out1=logits,
                   out1_mode="planar", no_out0=True, name="head.conv_classes.b")

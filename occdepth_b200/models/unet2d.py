@@ -45,12 +45,8 @@ class UpSampleBN(B200Module):
         B, _, h, w = x.dims
         _, _, OH, OW = concat_with.dims
         up = plan.alloc(B, 1, OH, OW, x.C)
-        # OCCDEPTH_UPSAMPLE_IMPL=rows: one block row per output row (CPU-emulation tested, not yet timed on a B200)
-        impl = os.environ.get("OCCDEPTH_UPSAMPLE_IMPL", "flat")
-        if impl not in ("flat", "rows"):
-            raise ValueError(f"OCCDEPTH_UPSAMPLE_IMPL must be 'flat' or 'rows', got {impl!r}")
-        up_fwd = L.occd_upsample_bilinear_rows if impl == "rows" else L.occd_upsample_bilinear_ac
-        plan.add(FnOp(lambda st: up_fwd(x.ptr, up.ptr, B, h, w, OH, OW, x.C, x.cstride, x.coff,
+        up_fwd = L.occd_upsample_bilinear_ac
+        plan.add(FnOp(lambda st: up_fwd(x.ptr, up.ptr, plan.lib_dtype, B, h, w, OH, OW, x.C, x.cstride, x.coff,
                                         up.cstride, up.coff, st),
                       name + ".bilinear", keep=(x, up)))
         w1, b1 = fold_bn(self._net[0].weight, self._net[0].bias, self._net[1])

@@ -48,7 +48,7 @@ def sfa(x2d, projected_pix, fov_mask, scene_size, dataset, project_scale):
         feats.append(f)
         masks.append((cnt > 0).to(src.dtype))                                  # SFA.py:33,39-41
     if V > 1:
-        out = torch.zeros(C, N, dtype=x2d.dtype)
+        out = torch.zeros(C, N, dtype=x2d.dtype, device=x2d.device)
         for i in range(V):
             for j in range(i + 1, V):
                 wij = masks[i] * masks[j]                                      # SFA.py:53-55
@@ -344,7 +344,8 @@ def virtual_view(x, depth, scale_2d, bf):
     dm = F.interpolate(depth, size=(h, w), mode="bilinear", align_corners=False)        # :240-244
     dx = (bf / int(scale_2d)) / dm                                                      # :246-247
     dx = torch.where(torch.isinf(dx), torch.zeros_like(dx), dx).to(x.dtype)
-    hd, wd = torch.arange(-1, 1, 2 / h), torch.arange(-1, 1, 2 / w)                     # :249-250 (corner coords)
+    hd = torch.arange(-1, 1, 2 / h, device=x.device)                                    # :249-250 (corner coords)
+    wd = torch.arange(-1, 1, 2 / w, device=x.device)
     my, mx = torch.meshgrid(hd, wd, indexing="ij")
     grid = torch.stack((mx, my), 2).unsqueeze(0).repeat(n, 1, 1, 1).to(x.dtype)
     grid[..., 0] = grid[..., 0] + (dx * 2 / w)[0]                                       # item 0's disparity, :255-257

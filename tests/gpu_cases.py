@@ -1,4 +1,4 @@
-"""Shared GPU parity cases (used by tests/test_gpu_*.py and tools/gpu_diag.py)."""
+"""Shared GPU parity cases (used by tests/test_gpu_*.py)."""
 import torch
 import torch.nn.functional as F
 
@@ -10,13 +10,40 @@ def bf16r(t):
     return t.to(torch.bfloat16).float()
 
 
+def tf32r(t):
+    """nearest TF32 value, ties away from zero (cvt.rna.tf32.f32)"""
+    return ((t.contiguous().view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+
+
+PRECISIONS = ("tf32", "bf16")
+# single-launch tolerance relative to max |reference|: operands are exactly representable, accumulation is fp32, the
+# only rounding is the store (bf16: 2^-9, TF32: 2^-11 relative); the bound is 2x that
+TOL = {"tf32": 2.0 ** -10, "bf16": 2.0 ** -8}
+
+
+def rnd(precision):
+    return tf32r if precision == "tf32" else bf16r
+
+
+def record(test, precision, **values):
+    """append measured parity figures to gpurun_out/parity_measured.jsonl (the tolerances in the tests are set to
+    <= 2x what this log shows; profiles/ keeps the log of the round)"""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "parity_measured.jsonl"), "a") as f:
+        f.write(json.dumps(dict(test=test, precision=precision, **values)) + "\n")
+
+
 def rel_err(got, want):
     return float((got - want).abs().max() / want.abs().max().clamp_min(1e-6))
 
 
 def conv_case(impl, B=1, Cin=32, Cout=32, dims=(6, 10, 12), k=(3, 3, 3), stride=(1, 1, 1), dil=(1, 1, 1),
-              pad=None, act="relu", res=False, res_post=False, planar=False, pre=False, seed=0):
-    """one dense conv through the C ABI vs torch (CPU fp32 on bf16-rounded operands). returns rel err."""
+              pad=None, act="relu", res=False, res_post=False, planar=False, pre=False, seed=0, precision="tf32"):
+    """one dense conv through the C ABI vs torch (CPU fp32 on operands rounded to the mode's type). returns rel err."""
+    bf16r = rnd(precision)
     g = torch.Generator().manual_seed(seed)
     if pad is None:
         pad = tuple(d * (kk - 1) // 2 for d, kk in zip(dil, k))
@@ -32,9 +59,9 @@ def conv_case(impl, B=1, Cin=32, Cout=32, dims=(6, 10, 12), k=(3, 3, 3), stride=
             "leaky": lambda t: F.leaky_relu(t, 0.01)}[act]
     out_ref = actf(pre_ref) + (r if (res and res_post) else 0)
     dev = torch.device("cuda")
-    plan = Plan(dev)
-    xin = CL.from_planar(x.to(dev))
-    rcl = CL.from_planar(r.to(dev)) if res else None
+    plan = Plan(dev, precision=precision)
+    xin = CL.from_planar(x.to(dev), precision=precision)
+    rcl = CL.from_planar(r.to(dev), precision=precision) if res else None
     out1, mode = None, "none"
     od = tuple(ref.shape[2:])
     if planar:
@@ -56,7 +83,8 @@ def conv_case(impl, B=1, Cin=32, Cout=32, dims=(6, 10, 12), k=(3, 3, 3), stride=
     return max(errs), plan.ops[0].info()
 
 
-def convT_case(impl, Cin=32, Cout=16, dims=(4, 6, 5), seed=0, skip=True):
+def convT_case(impl, Cin=32, Cout=16, dims=(4, 6, 5), seed=0, skip=True, precision="tf32"):
+    bf16r = rnd(precision)
     g = torch.Generator().manual_seed(seed)
     x = bf16r(torch.randn(1, Cin, *dims, generator=g))
     w = bf16r(torch.randn(Cin, Cout, 3, 3, 3, generator=g) / (Cin * 8) ** 0.5)
@@ -66,16 +94,18 @@ def convT_case(impl, Cin=32, Cout=16, dims=(4, 6, 5), seed=0, skip=True):
     if skip:
         ref = ref + sk
     dev = torch.device("cuda")
-    plan = Plan(dev)
-    y = plan.conv_transpose_k3s2(CL.from_planar(x.to(dev)), w.to(dev), b.to(dev), act="relu",
-                                 res_post=CL.from_planar(sk.to(dev)) if skip else None, impl=impl)
+    plan = Plan(dev, precision=precision)
+    y = plan.conv_transpose_k3s2(CL.from_planar(x.to(dev), precision=precision), w.to(dev), b.to(dev), act="relu",
+                                 res_post=CL.from_planar(sk.to(dev), precision=precision) if skip else None,
+                                 impl=impl)
     plan.run()
     torch.cuda.synchronize()
     return rel_err(y.to_planar().cpu(), ref), plan.ops[0].info()
 
 
-def multi_case(impl, C=32, dims=(6, 8, 8), seed=0):
+def multi_case(impl, C=32, dims=(6, 8, 8), seed=0, precision="tf32"):
     """the fused ASPP conv2 stage: three sources, dilations 1/2/3, one accumulator, residual + relu."""
+    bf16r = rnd(precision)
     g = torch.Generator().manual_seed(seed)
     xs = [bf16r(torch.randn(1, C, *dims, generator=g)) for _ in range(3)]
     ws = [bf16r(torch.randn(C, C, 3, 3, 3, generator=g) / (C * 27) ** 0.5) for _ in range(3)]
@@ -84,9 +114,10 @@ def multi_case(impl, C=32, dims=(6, 8, 8), seed=0):
     ref = sum(F.conv3d(x, w, None, 1, d, d) for x, w, d in zip(xs, ws, (1, 2, 3)))
     ref = F.relu(ref + b.view(1, -1, 1, 1, 1) + r)
     dev = torch.device("cuda")
-    plan = Plan(dev)
-    y = plan.conv_multi([CL.from_planar(x.to(dev)) for x in xs], [w.to(dev) for w in ws], b.to(dev), [1, 2, 3],
-                        [1, 2, 3], act="relu", res1=CL.from_planar(r.to(dev)), impl=impl)
+    plan = Plan(dev, precision=precision)
+    y = plan.conv_multi([CL.from_planar(x.to(dev), precision=precision) for x in xs], [w.to(dev) for w in ws],
+                        b.to(dev), [1, 2, 3], [1, 2, 3], act="relu",
+                        res1=CL.from_planar(r.to(dev), precision=precision), impl=impl)
     plan.run()
     torch.cuda.synchronize()
     return rel_err(y.to_planar().cpu(), ref), plan.ops[0].info()

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
         assert n in _lib.SYMBOLS, "ctypes binding missing for " + n
-    assert L.occd_abi_version() == 1
+    assert L.occd_abi_version() == 2
 
 
 def test_argument_validation_without_gpu():

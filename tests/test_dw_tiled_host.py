@@ -28,7 +28,7 @@ def emul(tmp_path_factory):
     assert r.returncode == 0, r.stderr[-2000:]
     lib = C.CDLL(str(out))
     lib.dw_tiled_emulate.restype = C.c_int
-    lib.dw_tiled_emulate.argtypes = [C.c_void_p] * 5 + [C.c_int] * 14 + [C.POINTER(C.c_int)] * 2
+    lib.dw_tiled_emulate.argtypes = [C.c_void_p] * 5 + [C.c_int] * 15 + [C.POINTER(C.c_int)] * 2
     return lib
 
 
@@ -50,24 +50,32 @@ CASES = [
 ]
 
 
+def round_tf32(t):
+    return ((t.contiguous().view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("B,Cn,H,W,K,S,cs_extra,th", CASES)
-def test_tiled_dw_matches_torch(emul, B, Cn, H, W, K, S, cs_extra, th):
+def test_tiled_dw_matches_torch(emul, B, Cn, H, W, K, S, cs_extra, th, dtype):
     g = torch.Generator().manual_seed(1000 * K + 10 * S + Cn + H)
     cs_in, cs_out = Cn + cs_extra, Cn + cs_extra
-    x = torch.randn(B, H, W, cs_in, generator=g).to(torch.bfloat16)
+    bf16 = dtype == torch.bfloat16
+    x = torch.randn(B, H, W, cs_in, generator=g)
+    x = x.to(torch.bfloat16) if bf16 else round_tf32(x)
     w = torch.randn(Cn, K, K, generator=g) * 0.3
     bias = torch.randn(Cn, generator=g) * 0.2
     OH, OW = math.ceil(H / S), math.ceil(W / S)
     ph, pw = same_pad(H, K, S), same_pad(W, K, S)
     pt, pl = ph // 2, pw // 2
     wt = w.reshape(Cn, K * K).t().contiguous()                       # [K*K][C], the layout the kernel reads
-    out = torch.full((B, OH, OW, cs_out), float("nan")).to(torch.bfloat16)
+    out = torch.full((B, OH, OW, cs_out), float("nan")).to(dtype)
     pool = torch.zeros(B, Cn, dtype=torch.int64)
     cvb, tho = C.c_int(), C.c_int()
-    rc = emul.dw_tiled_emulate(x.data_ptr(), wt.data_ptr(), bias.data_ptr(), out.data_ptr(), pool.data_ptr(), B, H, W,
-                               OH, OW, Cn, cs_in, cs_out, K, S, pt, pl, 3, th, C.byref(cvb), C.byref(tho))
+    rc = emul.dw_tiled_emulate(x.data_ptr(), wt.data_ptr(), bias.data_ptr(), out.data_ptr(), pool.data_ptr(),
+                               2 if bf16 else 4, B, H, W, OH, OW, Cn, cs_in, cs_out, K, S, pt, pl, 3, th,
+                               C.byref(cvb), C.byref(tho))
     assert rc == 0
-    assert cvb.value == (4 if Cn < 64 else 8)
+    assert cvb.value == (4 if (Cn < 64 or not bf16) else 8)
     if th and cvb.value == 8 and S == 1:
         assert tho.value == th
     xin = x[..., :Cn].float().permute(0, 3, 1, 2)
@@ -75,8 +83,11 @@ def test_tiled_dw_matches_torch(emul, B, Cn, H, W, K, S, cs_extra, th):
     ref = F.silu(F.conv2d(xin, w[:, None], bias, stride=S, groups=Cn)).permute(0, 2, 3, 1)
     got = out[..., :Cn].float()
     assert torch.isfinite(got).all()
-    assert torch.allclose(got, ref, rtol=1e-2, atol=1e-2), (got - ref).abs().max()
-    # the squeeze sums the bf16-rounded outputs in 2^-24 fixed point
+    tol = 1e-2 if bf16 else 1e-3        # one bf16 / TF32 store rounding
+    assert torch.allclose(got, ref, rtol=tol, atol=tol), (got - ref).abs().max()
+    if not bf16:                        # every stored value is TF32-representable
+        assert torch.equal(got, round_tf32(got))
+    # the squeeze sums the rounded outputs in 2^-24 fixed point
     want = got.double().sum(dim=(1, 2))
     assert torch.allclose(pool.double() / 2 ** 24, want, rtol=1e-5, atol=1e-3)
     if cs_extra:                                                     # padding lanes of the output are untouched

@@ -1,16 +1,25 @@
 """Full-size parity at the benchmark configuration (BASELINE.json configs[1]): CUDA forward vs the CPU fp32 oracle
-on the same seeded stereo pair / weights / KITTI-like projection indices.  The metric the north star names:
-voxel-logit max-abs-diff (also reported relative to max |logit|) plus arg-max agreement."""
+on the same seeded stereo pair / weights / KITTI-like projection indices, in both precision modes.  The metric the north
+star names: voxel-logit max-abs-diff (also reported relative to max |logit|) plus arg-max agreement."""
 import json
 import os
 
 import pytest
 import torch
 
+import gpu_cases as G
+
 pytestmark = pytest.mark.gpu
 
+# stated tolerances (<= 2x the values measured on B200, profiles/r02_config2_parity.json): relative = max-abs-diff /
+# max |oracle logit|.  tf32 = the reference-precision mode (TF32 operands, fp32 accumulation, TF32-valued fp32
+# activations); bf16 = the throughput mode.  A CPU simulation of the tf32 mode (TF32-rounded conv operands inside the
+# fp32 oracle) gives rel 6.3e-4 / arg-max 99.93 %, so these bounds are what the arithmetic allows, not slack for bugs.
+TOL = {"tf32": dict(rel=1.5e-3, argmax=0.998), "bf16": dict(rel=1.4e-2, argmax=0.985)}
 
-def test_config2_logits_vs_oracle():
+
+@pytest.fixture(scope="module")
+def case():
     import bench
     from oracle import functional as OF
     m = bench.build_model()
@@ -20,8 +29,15 @@ def test_config2_logits_vs_oracle():
     batch = {"img": img, "projected_pix_2": [pix], "fov_mask_2": [fov]}
     with torch.no_grad():
         want = OF.occdepth_forward({k: v.clone() for k, v in m.state_dict().items()}, batch, cfg)
-        got = m.cuda()({"img": img.cuda(), "projected_pix_2": [pix], "fov_mask_2": [fov]})
-    rep = {}
+    return m.cuda(), {"img": img.cuda(), "projected_pix_2": [pix], "fov_mask_2": [fov]}, want
+
+
+@pytest.mark.parametrize("precision", G.PRECISIONS)
+def test_config2_logits_vs_oracle(case, precision):
+    m, batch, want = case
+    with torch.no_grad():
+        got = m.set_precision(precision)(batch)
+    rep = {"precision": precision}
     for k in ("ssc_logit", "occ_logit"):
         g, w = got[k].float().cpu(), want[k]
         assert g.shape == w.shape
@@ -30,9 +46,9 @@ def test_config2_logits_vs_oracle():
     agree = float((got["ssc_logit"].argmax(1).cpu() == want["ssc_logit"].argmax(1)).float().mean())
     rep["argmax_agreement"] = agree
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/config2_parity.json", "w") as f:
+    with open("gpurun_out/config2_parity_%s.json" % precision, "w") as f:
         json.dump(rep, f)
     print("config-2 parity:", rep)
-    # stated tolerance of the bf16-operand / fp32-accumulate pipeline
-    assert rep["ssc_logit"]["rel"] <= 6e-2 and rep["occ_logit"]["rel"] <= 6e-2, rep
-    assert agree >= 0.9, rep
+    t = TOL[precision]
+    assert rep["ssc_logit"]["rel"] <= t["rel"] and rep["occ_logit"]["rel"] <= t["rel"], rep
+    assert agree >= t["argmax"], rep

@@ -9,10 +9,15 @@ import os
 import pytest
 import torch
 
+import gpu_cases as G
+
 pytestmark = pytest.mark.gpu
+# <= 2x the values measured on B200 (profiles/r02_config4_parity_*.json); see tests/test_gpu_config2.py
+TOL = {"tf32": dict(rel=1.5e-3, argmax=0.998), "bf16": dict(rel=1.4e-2, argmax=0.99)}
 
 
-def test_config4_logits_vs_oracle():
+@pytest.fixture(scope="module")
+def case():
     import synthetic as synth
     from oracle import functional as OF
     from occdepth_b200.models.OccDepth import OccDepth
@@ -37,9 +42,17 @@ def test_config4_logits_vs_oracle():
     ocfg["project_res"] = ["1", "2", "4", "8"]
     with torch.no_grad():
         want = OF.occdepth_forward({k: v.clone() for k, v in m.state_dict().items()}, batch, ocfg)
-        b2 = dict(batch)
-        b2["img"] = img.cuda()
-        got = m.cuda()(b2)
+    b2 = dict(batch)
+    b2["img"] = img.cuda()
+    return m.cuda(), b2, want, N
+
+
+@pytest.mark.parametrize("precision", G.PRECISIONS)
+def test_config4_logits_vs_oracle(case, precision):
+    m, b2, want, N = case
+    m.set_precision(precision)
+    with torch.no_grad():
+        got = m(b2)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -49,14 +62,15 @@ def test_config4_logits_vs_oracle():
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     g_, w_ = got["ssc_logit"].float().cpu(), want["ssc_logit"]
-    rep = {"max_abs_diff": float((g_ - w_).abs().max()), "max_abs_ref": float(w_.abs().max()),
+    rep = {"precision": precision, "max_abs_diff": float((g_ - w_).abs().max()), "max_abs_ref": float(w_.abs().max()),
            "rel": float((g_ - w_).abs().max() / w_.abs().max()),
            "argmax_agreement": float((g_.argmax(1) == w_.argmax(1)).float().mean()),
            "P_logits_rel": float((got["P_logits"].cpu() - want["P_logits"]).abs().max() / want["P_logits"].abs().max()),
            "ms_per_frame": ms, "voxels_per_s": N / ms * 1e3}
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/config4_parity.json", "w") as f:
+    with open("gpurun_out/config4_parity_%s.json" % precision, "w") as f:
         json.dump(rep, f)
     print("config-4 parity:", rep)
-    assert rep["rel"] <= 6e-2 and rep["P_logits_rel"] <= 6e-2, rep
-    assert rep["argmax_agreement"] >= 0.9, rep
+    t = TOL[precision]
+    assert rep["rel"] <= t["rel"] and rep["P_logits_rel"] <= t["rel"], rep
+    assert rep["argmax_agreement"] >= t["argmax"], rep

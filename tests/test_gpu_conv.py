@@ -1,74 +1,70 @@
-"""Implicit-GEMM convolution through the C ABI: tcgen05 path and SIMT path vs torch fp32 on bf16-rounded operands."""
+"""Implicit-GEMM convolution through the C ABI: tcgen05 paths and the SIMT path vs torch fp32 on operands rounded
+to the mode's element type (TF32 values in fp32 containers / bf16), both precision modes."""
 import pytest
 
 import gpu_cases as G
 
 pytestmark = pytest.mark.gpu
-# operands are exactly representable in bf16, accumulation is fp32; the only rounding is the bf16 store
-TOL = 2 ** -7
+PREC = pytest.mark.parametrize("precision", G.PRECISIONS)
 
 
+@PREC
 @pytest.mark.parametrize("impl", ["tc", "simt"])
 @pytest.mark.parametrize("case", sorted(G.CONV_CASES))
-def test_conv(impl, case):
+def test_conv(impl, case, precision):
     from occdepth_b200 import _lib
-    e, info = G.conv_case(_lib.CONV_IMPL_TC if impl == "tc" else _lib.CONV_IMPL_SIMT, **G.CONV_CASES[case])
-    assert e <= TOL, (e, info)
+    e, info = G.conv_case(_lib.CONV_IMPL_TC if impl == "tc" else _lib.CONV_IMPL_SIMT, precision=precision,
+                          **G.CONV_CASES[case])
+    assert e <= G.TOL[precision], (e, info)
 
 
+@PREC
 @pytest.mark.parametrize("impl", ["tc", "simt"])
-def test_conv_transpose_and_multi(impl):
+def test_conv_transpose_and_multi(impl, precision):
     from occdepth_b200 import _lib
     i = _lib.CONV_IMPL_TC if impl == "tc" else _lib.CONV_IMPL_SIMT
-    e, info = G.convT_case(i)
-    assert e <= TOL, (e, info)
-    e, info = G.multi_case(i)
-    assert e <= TOL, (e, info)
+    e, info = G.convT_case(i, precision=precision)
+    assert e <= G.TOL[precision], (e, info)
+    e, info = G.multi_case(i, precision=precision)
+    assert e <= G.TOL[precision], (e, info)
 
 
-def test_conv_large_vs_simt():
-    """full-size head conv shape (Cin=Cout=32, dil 3) on a 64x64x32 slab: TC vs SIMT on the same buffers."""
+@PREC
+def test_conv_large_vs_simt(precision):
+    """full-size head conv shape (Cin=Cout=32, dil 3) on a 64x64x32 slab: auto (halo) / TC vs SIMT on the same
+    buffers."""
     import torch
     from occdepth_b200 import _lib
     from occdepth_b200.engine import CL, Plan
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(1)
-    x = CL.from_planar(torch.randn(1, 32, 64, 64, 32, generator=g).cuda())
+    x = CL.from_planar(torch.randn(1, 32, 64, 64, 32, generator=g).cuda(), precision=precision)
     w = (torch.randn(32, 32, 3, 3, 3, generator=g) / 30).cuda()
     b = torch.randn(32, generator=g).cuda()
     outs = []
-    for impl in (_lib.CONV_IMPL_TC, _lib.CONV_IMPL_SIMT):
-        plan = Plan(dev)
+    for impl in (None, _lib.CONV_IMPL_TC, _lib.CONV_IMPL_SIMT):
+        plan = Plan(dev, precision=precision)
         outs.append(plan.conv(x, w, b, padding=3, dilation=3, act="relu", impl=impl))
         plan.run()
     torch.cuda.synchronize()
-    a, c = outs[0].buf.float(), outs[1].buf.float()
-    assert float((a - c).abs().max()) <= TOL * float(c.abs().max())
+    c = outs[2].buf.float()
+    for o in outs[:2]:
+        assert float((o.buf.float() - c).abs().max()) <= G.TOL[precision] * float(c.abs().max())
 
 
+@PREC
 @pytest.mark.parametrize("case", sorted(G.HALO_CASES))
-def test_conv_halo(case):
+def test_conv_halo(case, precision):
     """halo-tile tcgen05 kernel (row-shifted swizzled smem views, sub-sampled TMA for dilation)"""
     from occdepth_b200 import _lib
-    e, info = G.conv_case(_lib.CONV_IMPL_HALO, **G.HALO_CASES[case])
-    assert e <= TOL, (e, info)
-
-
-@pytest.mark.parametrize("case", sorted(G.HALO_CASES))
-def test_conv_halo_xpacked(case):
-    """x-packed halo kernel (three W taps per MMA, lane-shifted epilogue).  Plan geometry and epilogue mapping are
-    covered on the CPU (tests/test_halo_model_host.py); the first GPU run is opt-in until it has been seen green."""
-    import os
-    from occdepth_b200 import _lib
-    if os.environ.get("OCCD_EXPERIMENTAL") != "1":
-        pytest.skip("x-packed halo kernel: set OCCD_EXPERIMENTAL=1 to run")
-    try:
-        e, info = G.conv_case(_lib.CONV_IMPL_HALOX, **G.HALO_CASES[case])
-    except RuntimeError as err:
-        if "(halo)" in str(err):        # geometry declined (e.g. weights + stage do not fit): auto mode falls back
-            pytest.skip(str(err))
-        raise
-    assert e <= TOL, (e, info)
+    kw = G.HALO_CASES[case]
+    one_chunk = 32 if precision == "tf32" else 64           # the resident-weight scheme holds ONE K chunk
+    if kw.get("Cin", 32) > one_chunk:
+        with pytest.raises(RuntimeError, match="halo"):
+            G.conv_case(_lib.CONV_IMPL_HALO, precision=precision, **kw)
+        return
+    e, info = G.conv_case(_lib.CONV_IMPL_HALO, precision=precision, **kw)
+    assert e <= G.TOL[precision], (e, info)
 
 
 TCX_CASES = {
@@ -80,34 +76,24 @@ TCX_CASES = {
 }
 
 
+@PREC
 @pytest.mark.parametrize("case", sorted(TCX_CASES))
-def test_conv_tc_xpacked(case):
-    """x-packed per-tap kernel (TCX); opt-in until it has been seen green on a B200 (CPU model:
-    tests/test_tc_model_host.py)"""
-    import os
+def test_conv_tc_xpacked(case, precision):
+    """x-packed per-tap kernel (TCX: three W taps per MMA, lane-shifted epilogue sum)"""
     from occdepth_b200 import _lib
-    if os.environ.get("OCCD_EXPERIMENTAL") != "1":
-        pytest.skip("x-packed per-tap kernel: set OCCD_EXPERIMENTAL=1 to run")
-    e, info = G.conv_case(_lib.CONV_IMPL_TCX, **TCX_CASES[case])
-    assert e <= TOL, (e, info)
+    e, info = G.conv_case(_lib.CONV_IMPL_TCX, precision=precision, **TCX_CASES[case])
+    assert e <= G.TOL[precision], (e, info)
 
 
-M2_CASES = {
-    "m_2d_c160": dict(k=(1, 3, 3), Cin=160, Cout=160, dims=(1, 40, 90), res=True),       # N 160: one TMEM set
-    "m_2d_c64_n128": dict(k=(1, 3, 3), Cin=64, Cout=128, dims=(1, 33, 70), B=2),        # N 128: two sets
-    "m_3d_odd_tiles": dict(Cin=32, Cout=64, dims=(3, 9, 15)),                            # odd tile count: phantom tile
-    "m_1x1_n256": dict(k=(1, 1, 1), Cin=96, Cout=256, dims=(1, 30, 50), act="silu"),
-    "m_ntiles2": dict(k=(1, 3, 3), Cin=48, Cout=320, dims=(1, 20, 37)),                  # two N tiles of 160
-}
-
-
-@pytest.mark.parametrize("case", sorted(M2_CASES))
-def test_conv_tc_m2(case):
-    """M2 per-tap kernel (two M tiles per weight tile); opt-in until it has been seen green on a B200 (CPU model:
-    tests/test_tc_model_host.py)"""
-    import os
+def test_auto_picks_tcx_and_halo():
+    """the default ('auto') selection: decoder-width 3x3 convs run x-packed, head-width convs on the halo kernel"""
+    import torch
     from occdepth_b200 import _lib
-    if os.environ.get("OCCD_EXPERIMENTAL") != "1":
-        pytest.skip("M2 per-tap kernel: set OCCD_EXPERIMENTAL=1 to run")
-    e, info = G.conv_case(_lib.CONV_IMPL_TCM2, **M2_CASES[case])
-    assert e <= TOL, (e, info)
+    from occdepth_b200.engine import Plan
+    dev = torch.device("cuda")
+    plan = Plan(dev)
+    x = plan.alloc(1, 1, 40, 64, 80)
+    plan.conv(x, torch.randn(80, 80, 1, 3, 3, device=dev), torch.zeros(80, device=dev), padding=(0, 1, 1))
+    y = plan.alloc(1, 8, 16, 32, 32)
+    plan.conv(y, torch.randn(32, 32, 3, 3, 3, device=dev), torch.zeros(32, device=dev), padding=1)
+    assert plan.ops[0].impl == _lib.CONV_IMPL_TCX and plan.ops[1].impl == _lib.CONV_IMPL_HALO

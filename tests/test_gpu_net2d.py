@@ -5,19 +5,26 @@ import torch
 from oracle import functional as OF
 from oracle import ref_import, synth
 
-pytestmark = pytest.mark.gpu
+import gpu_cases as G
 
-# stated tolerance for the bf16-operand / fp32-accumulate pipeline, relative to max-abs of the oracle tensor
-TOL_2D = 5e-2
-TOL_E2E = 6e-2
+pytestmark = pytest.mark.gpu
+PREC = pytest.mark.parametrize("precision", G.PRECISIONS)
+
+# stated tolerances relative to max-abs of the CPU fp32 oracle tensor, per precision mode (<= 2x the values measured on
+# B200, profiles/r02_parity_measured.jsonl): "tf32" = TF32 operands / fp32 accumulate / TF32-valued fp32 activations
+# (the reference-precision mode), "bf16" = bf16 operands and activations
+TOL_2D = {"tf32": 2e-3, "bf16": 2e-2}
+TOL_E2E = {"tf32": 2e-3, "bf16": 2e-2}
+TOL_ARGMAX = {"tf32": 0.995, "bf16": 0.97}
 
 
 def _rel(g, w):
     return float((g.float().cpu() - w).abs().max() / w.abs().max().clamp_min(1e-6))
 
 
+@PREC
 @pytest.mark.parametrize("backbone,hw", [("tf_efficientnet_b3_ns", (38, 45)), ("tf_efficientnet_b7_ns", (33, 49))])
-def test_unet2d(backbone, hw):
+def test_unet2d(backbone, hw, precision):
     from occdepth_b200.models.unet2d import UNet2D
     torch.manual_seed(0)
     with ref_import.quiet():
@@ -27,15 +34,17 @@ def test_unet2d(backbone, hw):
     x = torch.randn(1, 3, *hw)
     with torch.no_grad():
         want = OF.unet2d(sd, "net_rgb", x, backbone, 1)
-        got = m.cuda()(x.cuda())
+        got = m.cuda().set_precision(precision)(x.cuda())
     assert set(got.keys()) == set(want.keys())
+    G.record("unet2d[%s]" % backbone, precision, **{k: _rel(got[k], want[k]) for k in want})
     for k in want:
         assert got[k].shape == want[k].shape, k
-        assert _rel(got[k], want[k]) <= TOL_2D, (k, _rel(got[k], want[k]))
+        assert _rel(got[k], want[k]) <= TOL_2D[precision], (k, _rel(got[k], want[k]))
 
 
+@PREC
 @pytest.mark.parametrize("dataset", ["kitti", "NYU"])
-def test_occdepth_forward_small(dataset):
+def test_occdepth_forward_small(dataset, precision):
     """config-1-like plumbing case: tiny stereo pair, both decoders, CRP on; max-abs-diff of the voxel logits."""
     from occdepth_b200.models.OccDepth import OccDepth
     torch.manual_seed(0)
@@ -59,13 +68,16 @@ def test_occdepth_forward_small(dataset):
     ocfg["project_res"] = ["1", "2", "4", "8"]
     with torch.no_grad():
         want = OF.occdepth_forward({k: v.clone() for k, v in m.state_dict().items()}, batch, ocfg)
-        got = m.cuda()({"img": img.cuda(), "projected_pix_%d" % ps: [pix], "fov_mask_%d" % ps: [fov]})
+        got = m.cuda().set_precision(precision)({"img": img.cuda(), "projected_pix_%d" % ps: [pix],
+                                                 "fov_mask_%d" % ps: [fov]})
     assert set(got.keys()) == set(want.keys())
+    agree = float((got["ssc_logit"].argmax(1).cpu() == want["ssc_logit"].argmax(1)).float().mean())
+    G.record("occdepth_forward_small[%s]" % dataset, precision, argmax=agree,
+             **{k: _rel(got[k], want[k]) for k in want})
     for k in want:
         assert got[k].shape == want[k].shape, k
-        assert _rel(got[k], want[k]) <= TOL_E2E, (k, _rel(got[k], want[k]))
-    agree = (got["ssc_logit"].argmax(1).cpu() == want["ssc_logit"].argmax(1)).float().mean()
-    assert agree > 0.9, float(agree)
+        assert _rel(got[k], want[k]) <= TOL_E2E[precision], (k, _rel(got[k], want[k]))
+    assert agree >= TOL_ARGMAX[precision], agree
 
 
 def _flosp_conf(H, W):
@@ -78,7 +90,8 @@ def _flosp_conf(H, W):
     return conf
 
 
-def test_flosp_depth_module():
+@PREC
+def test_flosp_depth_module(precision):
     """FlospDepth drop-in (DepthNet on tcgen05 + fused frustum sampling kernel) vs the CPU oracle"""
     from occdepth_b200.models.flosp_depth import FlospDepth
     torch.manual_seed(0)
@@ -93,13 +106,15 @@ def test_flosp_depth_module():
     with torch.no_grad():
         want, want_d = OF.flosp_depth({"f." + k: v.clone() for k, v in m.state_dict().items()}, "f", feat, cam_k, T, ida,
                                       conf)
-        got, got_d = m.cuda()(feat.cuda(), cam_k, T, ida, None)
+        got, got_d = m.cuda().set_precision(precision)(feat.cuda(), cam_k, T, ida, None)
     assert float((want > 0).float().mean()) > 0.2
-    assert _rel(got_d, want_d) <= 3e-2, _rel(got_d, want_d)
-    assert _rel(got, want) <= 3e-2, _rel(got, want)
+    G.record("flosp_depth_module", precision, depth=_rel(got_d, want_d), prior=_rel(got, want))
+    assert _rel(got_d, want_d) <= TOL_E2E[precision], _rel(got_d, want_d)
+    assert _rel(got, want) <= TOL_E2E[precision], _rel(got, want)
 
 
-def test_occdepth_forward_flosp_depth():
+@PREC
+def test_occdepth_forward_flosp_depth(precision):
     """OccDepth.forward with trans_2d_to_3d="flosp_depth" (the README-default configs): lift x depth prior x 100"""
     from occdepth_b200.models.OccDepth import OccDepth
     import occdepth_b200.models.flosp_depth.flosp_depth as fd
@@ -136,13 +151,16 @@ def test_occdepth_forward_flosp_depth():
         want = OF.occdepth_forward({k: v.clone() for k, v in m.state_dict().items()}, batch, ocfg)
         b2 = dict(batch)
         b2["img"] = img.cuda()
-        got = m.cuda()(b2)
+        got = m.cuda().set_precision(precision)(b2)
     assert set(got.keys()) == set(want.keys())
+    G.record("occdepth_forward_flosp_depth", precision,
+             **{k: _rel(got[k], want[k]) for k in ("ssc_logit", "occ_logit", "depth_pred")})
     for k in ("ssc_logit", "occ_logit", "depth_pred"):
-        assert _rel(got[k], want[k]) <= TOL_E2E, (k, _rel(got[k], want[k]))
+        assert _rel(got[k], want[k]) <= TOL_E2E[precision], (k, _rel(got[k], want[k]))
 
 
-def test_occdepth_forward_nyu_virtual_view():
+@PREC
+def test_occdepth_forward_nyu_virtual_view(precision):
     """config-4-type path: single RGB view + gt_depth -> virtual right view kernel -> lift -> NYU 3D net"""
     from occdepth_b200.models.OccDepth import OccDepth
     from test_oracle_vs_reference import _nyu_virtual_batch
@@ -161,7 +179,8 @@ def test_occdepth_forward_nyu_virtual_view():
         want = OF.occdepth_forward({k: v.clone() for k, v in m.state_dict().items()}, batch, ocfg)
         b2 = dict(batch)
         b2["img"] = batch["img"].cuda()
-        got = m.cuda()(b2)
+        got = m.cuda().set_precision(precision)(b2)
     assert set(got.keys()) == set(want.keys())
+    G.record("occdepth_forward_nyu_virtual_view", precision, **{k: _rel(got[k], want[k]) for k in want})
     for k in want:
-        assert _rel(got[k], want[k]) <= TOL_E2E, (k, _rel(got[k], want[k]))
+        assert _rel(got[k], want[k]) <= TOL_E2E[precision], (k, _rel(got[k], want[k]))

@@ -37,9 +37,11 @@ def test_sfa_empty_and_all_masked():
     assert float(got.abs().max()) == 0.0
 
 
-def test_lift_multiscale_bf16_kitti_calibration():
-    """fused 4-scale / 2-view bf16 fast path against the oracle run on the bf16-rounded feature maps,
-    with the KITTI-like vox2pix indices (realistic locality, FOV fraction ~0.7)."""
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_lift_multiscale_kitti_calibration(precision):
+    """fused 4-scale / 2-view production path (features and output in the plan's element type) against the oracle
+    run on the same rounded feature maps, with the KITTI-like vox2pix indices (realistic locality, FOV fraction ~0.7)."""
+    import gpu_cases as G
     from occdepth_b200.engine import CL
     from occdepth_b200.models.SFA import lift_multiscale
     H, W, C = 94, 343, 64
@@ -49,15 +51,15 @@ def test_lift_multiscale_bf16_kitti_calibration():
     feats, x_rgb = [], [{}, {}]
     for s in (1, 2, 4, 8):
         h, w = synth.feature_hw(H, W, s)
-        f = torch.randn(2, C, h, w, generator=g).to(torch.bfloat16)
-        feats.append(f.permute(0, 2, 3, 1).contiguous().cuda())
+        f = G.rnd(precision)(torch.randn(2, C, h, w, generator=g))
+        feats.append(f.permute(0, 2, 3, 1).contiguous().to(torch.float32 if precision == "tf32" else torch.bfloat16).cuda())
         for v in range(2):
             x_rgb[v]["1_%d" % s] = f[v].float()
     want = OF.lift_flosp(x_rgb, pix, fov, ["1", "2", "4", "8"], full, "kitti", ps)
     X, Y, Z = [s // ps for s in full]
-    out = CL.alloc(1, X, Y, Z, C, torch.device("cuda"))
+    out = CL.alloc(1, X, Y, Z, C, torch.device("cuda"), precision=precision)
     lift_multiscale(feats, [1, 2, 4, 8], pix.cuda(), fov.cuda(), out, "kitti", full, ps)
     got = out.to_planar()[0].cpu()
     assert fov.float().mean() > 0.3
-    # output is rounded to bf16 once: 2^-8 relative
-    assert float((got - want).abs().max()) <= 2 ** -7 * float(want.abs().max())
+    # the output is rounded once to the plan's element type
+    assert float((got - want).abs().max()) <= G.TOL[precision] * float(want.abs().max())

@@ -6,22 +6,31 @@ import torch.nn as nn
 from oracle import functional as OF
 from oracle import synth
 
+import gpu_cases as G
+
 pytestmark = pytest.mark.gpu
+PREC = pytest.mark.parametrize("precision", G.PRECISIONS)
 
-# bf16 operands / bf16 activations between ~25 fused layers, fp32 accumulation: stated tolerance on
-# max-abs-diff relative to max-abs of the oracle tensor
-TOL = 4e-2
+# stated tolerance on max-abs-diff relative to max-abs of the oracle tensor, per precision mode (<= 2x the values
+# measured on B200, profiles/r02_parity_measured.jsonl); ~25 fused layers between input and logits
+TOL = {"tf32": 1.5e-3, "bf16": 1.5e-2}
+TOL_BLOCK = {"tf32": 1e-3, "bf16": 1e-2}
+TOL_ARGMAX = {"tf32": 0.995, "bf16": 0.97}
 
 
-def _check(got, want, tol=TOL):
+def _check(name, precision, got, want, tol):
+    errs = {}
     for k in want:
         g, w = got[k].float().cpu(), want[k]
         assert g.shape == w.shape, (k, g.shape, w.shape)
-        err = float((g - w).abs().max() / w.abs().max().clamp_min(1e-6))
+        errs[k] = float((g - w).abs().max() / w.abs().max().clamp_min(1e-6))
+    G.record(name, precision, **errs)
+    for k, err in errs.items():
         assert err <= tol, (k, err)
 
 
-def test_process_downsample_upsample():
+@PREC
+def test_process_downsample_upsample(precision):
     from occdepth_b200.models.modules import Downsample, Process, Upsample
     torch.manual_seed(0)
     proc = Process(32, nn.BatchNorm3d, 0.1).eval()
@@ -34,13 +43,15 @@ def test_process_downsample_upsample():
         want_p = OF.process({"p." + k: v for k, v in proc.state_dict().items()}, "p", x)
         want_d = OF.downsample({"p." + k: v for k, v in down.state_dict().items()}, "p", x)
         want_u = OF.upsample({"p." + k: v for k, v in up.state_dict().items()}, "p", want_d)
-        _check({"p": proc.cuda()(x.cuda())}, {"p": want_p}, 2e-2)
-        _check({"d": down.cuda()(x.cuda())}, {"d": want_d}, 2e-2)
-        _check({"u": up.cuda()(want_d.cuda())}, {"u": want_u}, 2e-2)
+        t = TOL_BLOCK[precision]
+        _check("process", precision, {"p": proc.cuda().set_precision(precision)(x.cuda())}, {"p": want_p}, t)
+        _check("downsample", precision, {"d": down.cuda().set_precision(precision)(x.cuda())}, {"d": want_d}, t)
+        _check("upsample", precision, {"u": up.cuda().set_precision(precision)(want_d.cuda())}, {"u": want_u}, t)
 
 
+@PREC
 @pytest.mark.parametrize("which", ["kitti", "nyu"])
-def test_unet3d(which):
+def test_unet3d(which, precision):
     torch.manual_seed(0)
     if which == "kitti":
         from occdepth_b200.models.unet3d_kitti import UNet3D
@@ -59,8 +70,9 @@ def test_unet3d(which):
             want = OF.unet3d_kitti(sd, "n", x, full, ps, True, True, True)
         else:
             want = OF.unet3d_nyu(sd, "n", x, full, 4, True, False)
-        got = m.cuda()({"x3d": x.cuda()})
+        got = m.cuda().set_precision(precision)({"x3d": x.cuda()})
     assert set(got.keys()) == set(want.keys())
-    _check(got, want)
-    agree = (got["ssc_logit"].argmax(1).cpu() == want["ssc_logit"].argmax(1)).float().mean()
-    assert agree > 0.9, float(agree)
+    agree = float((got["ssc_logit"].argmax(1).cpu() == want["ssc_logit"].argmax(1)).float().mean())
+    G.record("unet3d[%s].argmax" % which, precision, argmax=agree)
+    _check("unet3d[%s]" % which, precision, got, want, TOL[precision])
+    assert agree >= TOL_ARGMAX[precision], agree

@@ -87,39 +87,36 @@ def test_occdepth_config2_plan(simt, monkeypatch):
 
 
 def test_variant_eligibility_rules():
-    """host-side selection rules of the opt-in conv variants (engine.py) on the shapes they were written for"""
+    """host-side kernel selection rules (engine.py) on the shapes they were written for"""
     from occdepth_b200 import engine as E
     t333 = [(0, a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)]
     t333_d2 = [(0, 2 * a, 2 * b, 2 * c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)]
-    t311 = [(0, a, 0, 0) for a in (-1, 0, 1)]
     two_src = [(s, 0, b, c) for s in (0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)]
-    assert E.halox_eligible(t333, 32) and E.halox_eligible(t333_d2, 32)
-    assert not E.halox_eligible(t333, 96)                    # 3 * 96 > 256
-    assert not E.halox_eligible(t311, 32)                    # no W taps
     assert E.tcx_eligible(t333, (1, 1, 1), 80) and E.tcx_eligible(two_src, (1, 1, 1), 80)
-    assert not E.tcx_eligible(t333_d2, (1, 1, 1), 32)        # W dilation 2: per-tap kernel has no sub-grids
-    assert not E.tcx_eligible(t333, (1, 1, 2), 32) and not E.tcx_eligible(t333, (1, 1, 1), 96)
-    # M2: wide layers with enough pairs to fill the GPU twice (up2 / up4 of the 1370x376 decoder), not the 24x86 stage
-    assert E.tcm2_eligible(2, (1, 188, 685), 160, 27, False)
-    assert E.tcm2_eligible(2, (1, 94, 343), 320, 45, False)
-    assert not E.tcm2_eligible(2, (1, 24, 86), 1280, 396, False)
-    assert not E.tcm2_eligible(2, (1, 188, 685), 160, 27, True)    # per-image weight sets
-    assert not E.tcm2_eligible(2, (1, 376, 1370), 80, 9, False)    # narrow: that is TCX territory
+    assert not E.tcx_eligible(t333_d2, (1, 1, 1), 64)        # W dilation 2: per-tap kernel has no sub-grids
+    assert not E.tcx_eligible(t333, (1, 1, 2), 64) and not E.tcx_eligible(t333, (1, 1, 1), 96)
+    assert not E.tcx_eligible(t333, (1, 1, 1), 32)           # narrow outputs: the halo kernel's shapes
+    # K chunk = one swizzled smem row of 32 / 64 / 128 bytes
+    assert [E.chunk_channels(c, 2) for c in (3, 16, 17, 32, 33, 64, 65, 2784)] == [16, 16, 32, 32, 64, 64, 64, 64]
+    assert [E.chunk_channels(c, 4) for c in (3, 8, 9, 16, 17, 32, 33, 2784)] == [8, 8, 16, 16, 32, 32, 32, 32]
+    # TF32 rounding: ties away from zero on the 13 dropped mantissa bits == cvt.rna.tf32.f32
+    t = torch.tensor([1.0, 1.0 + 2.0 ** -11, 1.0 + 2.0 ** -11 + 2.0 ** -20, -(1.0 + 2.0 ** -11), 3.0e-39, 65504.0])
+    r = E.round_tf32_(t.clone())
+    assert r.tolist()[:4] == [1.0, 1.0 + 2.0 ** -10, 1.0 + 2.0 ** -10, -(1.0 + 2.0 ** -10)]
+    assert torch.equal(r.view(torch.int32) & 0x1FFF, torch.zeros(6, dtype=torch.int32))
 
 
-@pytest.mark.parametrize("flags", [{}, {"OCCDEPTH_HALOX": "1", "OCCDEPTH_TCX": "1", "OCCDEPTH_TCM2": "1"}])
-def test_auto_impl_selection_reaches_tensor_map_encode(monkeypatch, flags):
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_auto_impl_selection_reaches_tensor_map_encode(monkeypatch, precision):
     """'auto' mode (the GPU default) on the CPU: selection rules + plan geometry run; the first thing that needs a
     driver is cuTensorMapEncodeTiled, and the product must say so instead of falling back to anything"""
     from occdepth_b200.engine import CL, Plan
     monkeypatch.delenv("OCCDEPTH_CONV_IMPL", raising=False)
-    for k, v in flags.items():
-        monkeypatch.setenv(k, v)
     shapes = [((4, 8, 40), 32, 32, (3, 3, 3)), ((1, 40, 90), 160, 160, (1, 3, 3)), ((1, 20, 30), 48, 288, (1, 1, 1)),
               ((1, 188, 685), 80, 80, (1, 3, 3))]
     for dims, ci, co, k in shapes:
-        plan = Plan(torch.device("cpu"))
-        x = CL(torch.zeros(2, dims[0], dims[1], dims[2], (ci + 7) // 8 * 8, dtype=torch.bfloat16), ci)
+        plan = Plan(torch.device("cpu"), precision=precision)
+        x = plan.alloc(2, dims[0], dims[1], dims[2], ci)
         with pytest.raises(RuntimeError, match="cuTensorMapEncodeTiled unavailable"):
             plan.conv(x, torch.randn(co, ci, *k), torch.randn(co), padding=tuple(kk // 2 for kk in k))
 

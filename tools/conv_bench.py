@@ -41,12 +41,13 @@ def main():
     dev = torch.device("cuda")
     for n in names:
         dims, ci, co, k, dl, act = SHAPES[n]
-        plan = Plan(dev)
-        x = CL(torch.randn(1, dims[0], dims[1], dims[2], (ci + 7) // 8 * 8, device=dev).to(torch.bfloat16), ci)
+        plan = Plan(dev, precision=os.environ.get("OCCDEPTH_PRECISION", "tf32"))
+        x = plan.alloc(1, dims[0], dims[1], dims[2], ci)
+        x.buf.normal_()
         w = torch.randn(co, ci, *k, device=dev) / (ci * k[0] * k[1] * k[2]) ** 0.5
         b = torch.randn(co, device=dev)
         pad = tuple(dl * (kk - 1) // 2 for kk in k)
-        impl = {"tc": 0, "simt": 1, "halo": 2, "halox": 3, "tcx": 4, "tcm2": 5}.get(os.environ.get("BENCH_IMPL", ""), None)
+        impl = {"tc": 0, "simt": 1, "halo": 2, "tcx": 4}.get(os.environ.get("BENCH_IMPL", ""), None)
         plan.conv(x, w, b, padding=pad, dilation=dl, act=act, name=n, impl=impl)
         for _ in range(3):
             plan.run()
@@ -60,7 +61,7 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         fl = plan.ops[0].flops
-        byts = (x.buf.numel() + dims[0] * dims[1] * dims[2] * co) * 2
+        byts = (x.buf.numel() + dims[0] * dims[1] * dims[2] * co) * x.esize
         print("%-14s %8.3f ms  %7.1f TF/s  %7.1f GB/s(min traffic)  %s" % (n, ms, fl / ms / 1e9, byts / ms / 1e6,
                                                                           plan.ops[0].info()), flush=True)
 

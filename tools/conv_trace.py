@@ -9,14 +9,18 @@ import torch  # noqa: E402
 
 dev = torch.device("cuda")
 buf = torch.zeros(64 * 8, dtype=torch.int64, device=dev)
-os.environ["OCCD_CONV_TRACE_PTR"] = str(buf.data_ptr())
 import conv_bench  # noqa: E402
+from occdepth_b200 import _lib  # noqa: E402
 from occdepth_b200.engine import CL, Plan  # noqa: E402
+
+_lib.check(_lib.lib().occd_conv_debug_trace(buf.data_ptr()), "occd_conv_debug_trace")
+PREC = os.environ.get("OCCDEPTH_PRECISION", "tf32")
 
 n = sys.argv[1]
 dims, ci, co, k, dl, act = conv_bench.SHAPES[n]
-plan = Plan(dev)
-x = CL(torch.randn(1, dims[0], dims[1], dims[2], (ci + 7) // 8 * 8, device=dev).to(torch.bfloat16), ci)
+plan = Plan(dev, precision=PREC)
+x = plan.alloc(1, dims[0], dims[1], dims[2], ci)
+x.buf.normal_()
 w = torch.randn(co, ci, *k, device=dev) / (ci * k[0] * k[1] * k[2]) ** 0.5
 plan.conv(x, w, torch.randn(co, device=dev), padding=tuple(dl * (kk - 1) // 2 for kk in k), dilation=dl, act=act)
 for _ in range(3):
