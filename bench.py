@@ -32,7 +32,7 @@ WORKLOAD = ("configs[1]: 1370x376 stereo, tf_efficientnet_b7_ns, flosp lift to 1
             "UNet3D+CRP+cascade head -> 256x256x32x20 logits, B=1 per GPU")
 # stated parity of the two arithmetic modes vs the CPU fp32 oracle at this configuration (tests/test_gpu_config2.py,
 # profiles/r02_config2_parity_*.json): max-abs logit diff relative to max |logit|, arg-max agreement
-TOLERANCE = {"tf32": {"rel": 1.5e-3, "argmax": 0.998}, "bf16": {"rel": 1.4e-2, "argmax": 0.985}}
+TOLERANCE = {"tf32": {"rel": 1.5e-3, "argmax": 0.9984}, "bf16": {"rel": 1.4e-2, "argmax": 0.984}}
 
 
 def make_cfg():
@@ -64,25 +64,59 @@ def build_model():
 
 
 class ClockSampler(threading.Thread):
-    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    """samples SM clocks / throttle reasons while the timed regions run: NVML in-process (nvidia_ml_py) when it is
+    importable -- no fork, microseconds per sample -- else `nvidia-smi` (whose first, cold invocation on a fresh box
+    can stall driver calls for ~100 ms: the sampler is therefore started BEFORE the warm-up, never next to a timed
+    region)"""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index)))
+        except Exception:  # noqa: BLE001
+            self.nvml = None
 
-    def run(self):
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except Exception:  # noqa: BLE001
+                return index
+        return index
+
+    def _sample_nvml(self):
+        nv, h = self.nvml
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:  # noqa: BLE001
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        return [str(sm), str(mx)] + ["Active" if (r & b) else "Not Active" for _, b in bits]
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                            "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        return [x.strip() for x in o.strip().split(",")]
+
+    def run(self):
         while not self.stop_flag:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in o.strip().split(",")]
+                f = self._sample_nvml() if self.nvml else self._sample_smi()
                 if len(f) >= 6:
                     self.samples.append(f)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05 if self.nvml else 0.25)
 
     def summary(self):
         if not self.samples:
@@ -91,7 +125,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def oracle_inputs(device=None):
@@ -106,12 +140,25 @@ def oracle_inputs(device=None):
     return sd, {"img": img, "projected_pix_2": [pix], "fov_mask_2": [fov]}, cfg
 
 
+def host_cores():
+    """physical cores of the host (one oneDNN thread per hyper-thread pair: 128 threads on the 64-core B200 hosts run
+    the forward 15x SLOWER than 64, measured); torchrun's OMP_NUM_THREADS=1 is overridden on purpose"""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, (os.cpu_count() or 2) // 2)
+
+
 def cpu_forward_seconds(steps=1, warmup=0):
     """the reference algorithm (oracle/functional.py, pinned against /root/reference) on ALL host cores.
     torchrun exports OMP_NUM_THREADS=1: the thread count is set explicitly."""
     import torch
     from oracle import functional as OF      # bench.py executes oracle/ code only in the baseline legs
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_cores())
     sd, batch, cfg = oracle_inputs()
     times = []
     with torch.no_grad():
@@ -244,6 +291,9 @@ def run_b200(args):
     if slab_only:
         m.enable_slab_parallel(parallel.SlabContext(halo=3))
     warm = max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # before the warm-up: its first sample is taken long before any timed region
     # ---- device-resident arm ----
     batch_dev = {"img": img.to(dev), "projected_pix_2": [pix.to(dev)], "fov_mask_2": [fov.to(dev)]}
     with torch.no_grad():
@@ -255,9 +305,6 @@ def run_b200(args):
         parallel.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ms_total, out = time_forwards(m, batch_dev, args.steps, barrier, dev)
 
     # ---- end-to-end arm: host buffers, H2D of the inputs and D2H of the logits inside the timed region ----

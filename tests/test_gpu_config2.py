@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 # max |oracle logit|.  tf32 = the reference-precision mode (TF32 operands, fp32 accumulation, TF32-valued fp32
 # activations); bf16 = the throughput mode.  A CPU simulation of the tf32 mode (TF32-rounded conv operands inside the
 # fp32 oracle) gives rel 6.3e-4 / arg-max 99.93 %, so these bounds are what the arithmetic allows, not slack for bugs.
-TOL = {"tf32": dict(rel=1.5e-3, argmax=0.998), "bf16": dict(rel=1.4e-2, argmax=0.985)}
+# measured on B200: tf32 rel 7.4e-4 (ssc) / 8.7e-4 (occ), arg-max 99.918 %; bf16 rel 6.5e-3 / 7.2e-3, arg-max 99.195 %
+TOL = {"tf32": dict(rel=1.5e-3, argmax=0.9984), "bf16": dict(rel=1.4e-2, argmax=0.984)}
 
 
 @pytest.fixture(scope="module")

@@ -13,7 +13,8 @@ import gpu_cases as G
 
 pytestmark = pytest.mark.gpu
 # <= 2x the values measured on B200 (profiles/r02_config4_parity_*.json); see tests/test_gpu_config2.py
-TOL = {"tf32": dict(rel=1.5e-3, argmax=0.998), "bf16": dict(rel=1.4e-2, argmax=0.99)}
+# measured on B200: tf32 rel 8.2e-4, P_logits 5.3e-4, arg-max 99.954 %; bf16 rel 6.2e-3, P_logits 4.3e-3, arg-max 99.673 %
+TOL = {"tf32": dict(rel=1.6e-3, argmax=0.9991), "bf16": dict(rel=1.25e-2, argmax=0.9935)}
 
 
 @pytest.fixture(scope="module")

@@ -13,8 +13,9 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PREC = pytest.mark.parametrize("precision", GC.PRECISIONS)
 # relative to max-abs of the reference's tensor, per precision mode (<= 2x measured, profiles/r02_parity_measured.jsonl)
-TOL_3D = {"tf32": 1.5e-3, "bf16": 1.5e-2}
-TOL_E2E = {"tf32": 2e-3, "bf16": 2e-2}
+# measured: 3-D nets tf32 <= 2.2e-3 (P_logits, |max| 9) / bf16 <= 1.05e-2; full forward tf32 7.0e-4 / bf16 6.8e-3
+TOL_3D = {"tf32": 4e-3, "bf16": 2e-2}
+TOL_E2E = {"tf32": 1.4e-3, "bf16": 1.4e-2}
 
 
 def _rel(g, w):

@@ -13,9 +13,11 @@ PREC = pytest.mark.parametrize("precision", G.PRECISIONS)
 # stated tolerances relative to max-abs of the CPU fp32 oracle tensor, per precision mode (<= 2x the values measured on
 # B200, profiles/r02_parity_measured.jsonl): "tf32" = TF32 operands / fp32 accumulate / TF32-valued fp32 activations
 # (the reference-precision mode), "bf16" = bf16 operands and activations
-TOL_2D = {"tf32": 2e-3, "bf16": 2e-2}
-TOL_E2E = {"tf32": 2e-3, "bf16": 2e-2}
-TOL_ARGMAX = {"tf32": 0.995, "bf16": 0.97}
+# measured: 2D net tf32 <= 6.9e-4 / bf16 <= 6.4e-3; small full forwards tf32 <= 1.3e-3 / bf16 <= 8.5e-3, arg-max
+# agreement tf32 >= 0.99958, bf16 >= 0.9985
+TOL_2D = {"tf32": 1.4e-3, "bf16": 1.3e-2}
+TOL_E2E = {"tf32": 2.5e-3, "bf16": 1.7e-2}
+TOL_ARGMAX = {"tf32": 0.999, "bf16": 0.997}
 
 
 def _rel(g, w):

@@ -13,9 +13,11 @@ PREC = pytest.mark.parametrize("precision", G.PRECISIONS)
 
 # stated tolerance on max-abs-diff relative to max-abs of the oracle tensor, per precision mode (<= 2x the values
 # measured on B200, profiles/r02_parity_measured.jsonl); ~25 fused layers between input and logits
-TOL = {"tf32": 1.5e-3, "bf16": 1.5e-2}
-TOL_BLOCK = {"tf32": 1e-3, "bf16": 1e-2}
-TOL_ARGMAX = {"tf32": 0.995, "bf16": 0.97}
+# measured (profiles/r02_parity_measured.jsonl): nets tf32 <= 8.5e-4 / bf16 <= 7.1e-3, blocks 8.1e-4 / 7.9e-3,
+# arg-max agreement tf32 >= 0.99994, bf16 >= 0.9948
+TOL = {"tf32": 1.5e-3, "bf16": 1.4e-2}
+TOL_BLOCK = {"tf32": 1.5e-3, "bf16": 1.5e-2}
+TOL_ARGMAX = {"tf32": 0.9995, "bf16": 0.99}
 
 
 def _check(name, precision, got, want, tol):
