@@ -104,6 +104,10 @@ int occd_cl_to_planar(const void* in, int in_dtype, float* out, long long B, int
 #define OCCD_CONV_IMPL_HALO 2 /* tcgen05, halo tile loaded once + row-shifted smem views per tap:    */
                               /* stride-1 {-d,0,d}-tap convs, Cin <= 64, resident weights; returns  */
                               /* OCCD_ERR_UNSUPPORTED from plan_create when the shape does not fit   */
+#define OCCD_CONV_IMPL_HALOX 3 /* halo tile for grids whose innermost extent W is 8 / 16 / 32 (one warp row): the   */
+                              /* three W taps of each (dz,dy) pair packed into ONE MMA (N = 3*Cout_pad <= 256),  */
+                              /* epilogue sums the lane-shifted partials (masked lanes == zero padding); taps in  */
+                              /* lexicographic (dz,dy,dx) order, one K chunk, stride 1                           */
 #define OCCD_CONV_IMPL_TCX 4  /* per-tap kernel, the three W taps of each (src,dz,dy) group packed into    */
                               /* ONE MMA (N = 3*Cout_pad <= 256): taps ordered as groups of dx = -1,0,+1,   */
                               /* W stride 1, tiles 32 wide (30 outputs), epilogue sums lane-shifted partials */

@@ -43,7 +43,7 @@ class SfaParams(C.Structure):
 
 
 CONV_MAX_TAPS, CONV_MAX_SRC = 81, 3
-CONV_IMPL_TC, CONV_IMPL_SIMT, CONV_IMPL_HALO, CONV_IMPL_TCX = 0, 1, 2, 4
+CONV_IMPL_TC, CONV_IMPL_SIMT, CONV_IMPL_HALO, CONV_IMPL_HALOX, CONV_IMPL_TCX = 0, 1, 2, 3, 4
 OUT1_NONE, OUT1_CL, OUT1_F32_PLANAR = 0, 1, 2
 
 

@@ -191,13 +191,18 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       }
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
-    const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int grp = ((warp - 2) >> 2) & 1;   // accumulator index (tile parity)
-    const int half = (warp - 2) >> 3;        // which half of the accumulator's 16-column chunks
-    const int n_chunks = p.N_tile >> 4;
-    const int c_begin = half == 0 ? 0 : ((n_chunks + 1) >> 1) * 16;
-    const int c_end = half == 0 ? ((n_chunks + 1) >> 1) * 16 : p.N_tile;
+    // ===== epilogue: TMEM -> registers -> (bias, residuals, activation) -> global =====
+    // (a shared-memory-staged TMA-store epilogue was measured on B200, round 2: same 4-5 B/cycle/SM as these direct
+    // stores -- the write path, not the store instruction mix, is the limit -- and the 64 KB of staging cost the
+    // large-K convs a third of their smem ring: 4.0 -> 5.4 ms for the decoder 3x3 convs.  Removed.)
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int egrp = (warp - 2) >> 2;        // epilogue group 0..3 (128 threads == 128 tile rows)
+    const int grp = egrp & 1;                // accumulator index (tile parity)
+    const int half = egrp >> 1;              // this group takes the first / second half of the 16-column chunks
+    const int ncols = XP ? p.Cout_pad : p.N_tile;        // output channels of one tile
+    const int n_chunks = ncols >> 4;
+    const int c_begin = half == 0 ? 0 : ((n_chunks + 1) >> 1) * 16;   // contiguous per thread: whole lines fill up
+    const int c_end = half == 0 ? ((n_chunks + 1) >> 1) * 16 : ncols;
     const int row = q * 32 + lane;
     const int rw = row % p.TW;
     const int rh = (row / p.TW) % p.TH;
@@ -222,29 +227,24 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       if (tracer && j < 64) p.trace[j * 8 + 5] = clock64();
       const uint32_t taddr = tmem_base + acc * acc_stride + ((uint32_t)(q * 32) << 16);
       if constexpr (XP) {
-        // TW == 32: lane == tile column, so the W neighbours are the neighbouring lanes; the two column halves of
-        // the epilogue groups split the Cout_pad output channels, each needing its three tap slices
-        const int CP = p.Cout_pad;
-        const int xch = CP >> 4;
-        const int xb = half == 0 ? 0 : ((xch + 1) >> 1) * 16;
-        const int xe = half == 0 ? ((xch + 1) >> 1) * 16 : CP;
-        for (int c0 = xb; c0 < xe; c0 += 16) {
+        // TW == 32: lane == tile column, so the W neighbours' partial sums sit in the neighbouring lanes
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
           float lo[16], v[16], hi[16];
           tc::tmem_ld16(taddr + (uint32_t)c0, lo);
-          tc::tmem_ld16(taddr + (uint32_t)(CP + c0), v);
-          tc::tmem_ld16(taddr + (uint32_t)(2 * CP + c0), hi);
+          tc::tmem_ld16(taddr + (uint32_t)(p.Cout_pad + c0), v);
+          tc::tmem_ld16(taddr + (uint32_t)(2 * p.Cout_pad + c0), hi);
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             v[i] += __shfl_up_sync(0xffffffffu, lo[i], 1) + __shfl_down_sync(0xffffffffu, hi[i], 1);
           if (valid) conv_epilogue_row<T, 16>(p.epi, b, od, oh, ow, c0, v);
         }
       } else {
-      // software-pipelined: the tcgen05.ld of the next 16 columns is in flight while these 16 are stored
-      if (c_begin < c_end) {
+        // software-pipelined: the tcgen05.ld of this group's next 16 columns is in flight while these are stored
         uint32_t ra[16], rb[16];
-        tc::tmem_ld16_issue(taddr + (uint32_t)c_begin, ra);
-        tc::tmem_ld_wait16(ra);
-        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        int c0 = c_begin;
+        if (c0 < c_end) tc::tmem_ld16_issue(taddr + (uint32_t)c0, ra);
+        for (; c0 < c_end; c0 += 32) {
+          tc::tmem_ld_wait16(ra);
           const bool has_b = c0 + 16 < c_end;
           if (has_b) tc::tmem_ld16_issue(taddr + (uint32_t)(c0 + 16), rb);
           if (valid) {
@@ -262,10 +262,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
               for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rb[i]);
               conv_epilogue_row<T, 16>(p.epi, b, od, oh, ow, n0 + c0 + 16, v);
             }
-            if (c0 + 32 < c_end) tc::tmem_ld_wait16(ra);
           }
         }
-      }
       }
       tc::fence_before_sync();
       tc::mbar_arrive(tmem_empty_bar + 8u * acc);  // this thread's TMEM reads of the buffer are done
@@ -483,6 +481,216 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// x-packed halo kernel for grids whose innermost extent W is one warp wide or narrower (W in {8, 16, 32}: every
+// 3-D activation of this network -- Z = 32 / 16 / 8).  Measured on B200 (tools/micro/mma_issue_bench.cu,
+// profiles/r02_mma_issue_bench.txt): one tcgen05.mma costs max(59, N/2) cycles for M = 128 whatever the operand
+// type, so a 32-output-channel conv issued tap by tap runs the tensor pipe at N/2 / 59 = 27 % (bf16) and, with
+// K = 8 per instruction, 14 % (TF32).  Here the three W taps (dx = -d, 0, +d) of each (dz, dy) pair share ONE
+// instruction: its B operand stacks the three taps' weights along N (N = 3 * Cout_pad: three consecutive tap slices
+// of the ordinary weight tensor), its A operand is the un-shifted rows, and the accumulator holds
+//     Q_c[r] = sum_{a,b} W[a][b][c] . in[r + (a*PH + b)*PW]      c = 0, 1, 2
+// from which the epilogue forms out[r] = Q_0[r - d] + Q_1[r] + Q_2[r + d].  Smem rows are linearised with W
+// fastest and PW == W divides 32, so r +- d stays inside the warp: two shuffles per channel, masked where the
+// neighbour would fall outside [0, W) -- which is exactly the convolution's zero padding, so the W axis needs no
+// halo columns and no sub-sampling.  D and H keep the halo-tile scheme (one zero-filled halo position per side on
+// the d-sub-sampled grids, TMA traversal stride d).  27 taps become 9 instructions per 32 bytes of K.
+struct HaloxParams {
+  ConvEpi epi;
+  int d;                      // dilation (== padding) of the taps
+  int D, H;                   // output grid (W == PW)
+  int BD, BH, PD, PH, PW;     // valid box / halo box in sub-sampled (D, H) coordinates; PW == W
+  int hd, hh;                 // 1 where the taps reach into D / H
+  int src_d0;
+  int tilesD, tilesH;
+  int nM;                     // M tiles (128 smem rows = 128 / PW h-rows of one plane) per CTA tile, <= 2
+  int mt_row[2], mt_pd[2], mt_ph0[2];
+  int box_bytes, a_stage_bytes, stages;
+  int n_groups;               // (dz, dy) groups = n_taps / 3
+  int CP, N_tile;             // padded output channels, N_tile = 3 * CP
+  int tmem_cols, set_stride;
+  int b_stride, w_bytes;
+  int grp_off[9];             // (a*PH + b)*PW: smem row offset of a group's A operand relative to the M tile
+  int pdl;
+  long long* trace;
+};
+
+template <typename T, int RB>
+__global__ void __launch_bounds__(kTcThreads)
+conv_halox_kernel(const __grid_constant__ HaloxParams p, const __grid_constant__ CUtensorMap tmA,
+                  const __grid_constant__ CUtensorMap tmW) {
+  constexpr int NMMA = RB / 32;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_w = smem_base;                                   // [n_groups][b_stride] resident weights
+  const uint32_t smem_a = smem_w + (uint32_t)p.w_bytes;                 // [stages][a_stage_bytes]
+  const uint32_t bar_base = smem_a + (uint32_t)p.stages * p.a_stage_bytes;
+  const uint32_t full_bar = bar_base;            // [4]
+  const uint32_t empty_bar = bar_base + 32u;     // [4]
+  const uint32_t tfull_bar = bar_base + 64u;     // [2]
+  const uint32_t tempty_bar = bar_base + 80u;    // [2]
+  const uint32_t w_bar = bar_base + 96u;
+  const uint32_t tmem_slot = bar_base + 104u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int d = p.d;
+  const int num_tiles = p.epi.B * d * d * p.tilesD * p.tilesH;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmW);
+    for (int s = 0; s < p.stages; ++s) {
+      tc::mbar_init(full_bar + 8u * s, 1);
+      tc::mbar_init(empty_bar + 8u * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(tfull_bar + 8u * a, 1);
+      tc::mbar_init(tempty_bar + 8u * a, 256);
+    }
+    tc::mbar_init(w_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (p.pdl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+
+  // tile -> (batch, (D, H) residue class, sub-grid tile origin)
+  auto decode = [&](int tile, int& b, int& ra, int& rb, int& td, int& th) {
+    int t = tile;
+    th = t % p.tilesH; t /= p.tilesH;
+    td = t % p.tilesD; t /= p.tilesD;
+    rb = t % d; t /= d;
+    ra = t % d; t /= d;
+    b = t;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: resident weights once, then one halo box per tile =====
+      tc::mbar_expect_tx(w_bar, (uint32_t)(p.n_groups * p.N_tile * RB));
+      for (int g = 0; g < p.n_groups; ++g)
+        tc::tma_load_2d(smem_w + (uint32_t)g * p.b_stride, &tmW, w_bar, 0, g * p.N_tile);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int b, ra, rb, td, th;
+        decode(tile, b, ra, rb, td, th);
+        tc::mbar_wait(empty_bar + 8u * s, ph ^ 1u);
+        tc::mbar_expect_tx(full_bar + 8u * s, (uint32_t)p.box_bytes);
+        tc::tma_load_5d(smem_a + (uint32_t)s * p.a_stage_bytes, &tmA, full_bar + 8u * s, 0, 0,
+                        (th * p.BH - p.hh) * d + rb, (td * p.BD - p.hd) * d + ra + p.src_d0, b);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = tc::Mma<T>::idesc(128, p.N_tile);
+      const uint64_t db_w = tc::make_sdesc(smem_w, RB);
+      const int w_step16 = p.b_stride / 16;
+      tc::mbar_wait(w_bar, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int j = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+        const uint32_t set = (uint32_t)j & 1u;
+        const uint32_t use = (uint32_t)j >> 1;
+        tc::mbar_wait(tempty_bar + 8u * set, (use & 1u) ^ 1u);
+        tc::mbar_wait(full_bar + 8u * s, ph);
+        tc::fence_after_sync();
+        if (p.trace && blockIdx.x == 0 && j < 64) p.trace[j * 8 + 2] = clock64();
+        const uint64_t da_stage = tc::make_sdesc(smem_a + (uint32_t)s * p.a_stage_bytes, RB);
+        for (int m = 0; m < p.nM; ++m) {
+          const uint32_t d_tmem = tmem_base + set * (uint32_t)p.set_stride + (uint32_t)(m * p.N_tile);
+          {
+            const uint64_t da = da_stage + (uint64_t)((p.mt_row[m] + p.grp_off[0]) * (RB / 16));
+            tc::Mma<T>::template issue<0>(d_tmem, da, db_w, idesc);
+#pragma unroll
+            for (int k = 1; k < NMMA; ++k) tc::Mma<T>::template issue<1>(d_tmem, da + 2 * k, db_w + 2 * k, idesc);
+          }
+#pragma unroll 2
+          for (int g = 1; g < p.n_groups; ++g) {
+            const uint64_t da = da_stage + (uint64_t)((p.mt_row[m] + p.grp_off[g]) * (RB / 16));
+            const uint64_t db = db_w + (uint64_t)(g * w_step16);
+#pragma unroll
+            for (int k = 0; k < NMMA; ++k) tc::Mma<T>::template issue<1>(d_tmem, da + 2 * k, db + 2 * k, idesc);
+          }
+        }
+        tc::mma_commit(empty_bar + 8u * s);
+        tc::mma_commit(tfull_bar + 8u * set);
+        if (p.trace && blockIdx.x == 0 && j < 64) p.trace[j * 8 + 3] = clock64();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue: 16 warps; group (egrp & 1) drains accumulator set (tile parity), (egrp >> 1) picks the work
+    // items (M tile, 16-channel chunk) it takes =====
+    const int q = warp & 3;
+    const int egrp = (warp - 2) >> 2;
+    const int grp = egrp & 1;
+    const int half = egrp >> 1;
+    const int rr = q * 32 + lane;            // row inside an M tile
+    const int hr = rr / p.PW;                // h-row inside the M tile
+    const int pw = rr - hr * p.PW;           // == output w
+    const bool lo_ok = pw >= d, hi_ok = pw + d < p.PW;
+    const int chunks = p.CP >> 4;
+    const int n_items = p.nM * chunks;
+    const bool tracer = p.trace && blockIdx.x == 0 && threadIdx.x == 64;
+    int j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      const uint32_t set = (uint32_t)j & 1u;
+      const uint32_t use = (uint32_t)j >> 1;
+      if ((int)set != grp) continue;
+      int b, ra, rb, td, th;
+      decode(tile, b, ra, rb, td, th);
+      if (tracer && j < 64) p.trace[j * 8 + 4] = clock64();
+      tc::mbar_wait(tfull_bar + 8u * set, use & 1u);
+      tc::fence_after_sync();
+      if (tracer && j < 64) p.trace[j * 8 + 5] = clock64();
+      for (int it = half; it < n_items; it += 2) {
+        const int m = it / chunks, c0 = (it - m * chunks) * 16;
+        const int od = (td * p.BD + p.mt_pd[m] - p.hd) * d + ra;
+        const int oh = (th * p.BH + p.mt_ph0[m] + hr - p.hh) * d + rb;
+        const bool valid = od < p.D && oh < p.H;
+        const uint32_t taddr = tmem_base + set * (uint32_t)p.set_stride + (uint32_t)(m * p.N_tile) +
+                               ((uint32_t)(q * 32) << 16);
+        float lo[16], v[16], hi[16];
+        tc::tmem_ld16(taddr + (uint32_t)c0, lo);
+        tc::tmem_ld16(taddr + (uint32_t)(p.CP + c0), v);
+        tc::tmem_ld16(taddr + (uint32_t)(2 * p.CP + c0), hi);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float l = __shfl_up_sync(0xffffffffu, lo[i], (unsigned)d);
+          const float h = __shfl_down_sync(0xffffffffu, hi[i], (unsigned)d);
+          v[i] += (lo_ok ? l : 0.f) + (hi_ok ? h : 0.f);
+        }
+        if (valid) conv_epilogue_row<T, 16>(p.epi, b, od, oh, pw, c0, v);
+      }
+      tc::fence_before_sync();
+      tc::mbar_arrive(tempty_bar + 8u * set);
+      if (tracer && j < 64) p.trace[j * 8 + 6] = clock64();
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // SIMT direct convolution: one thread = one output position x 8 output channels
 struct SimtParams {
@@ -591,6 +799,7 @@ struct occd_conv_plan {
   int rb;   // bytes per K chunk row (kc * esize): 128 / 64 / 32 == the swizzle mode
   TcParams tc;
   HaloParams halo;
+  HaloxParams halox;
   SimtParams simt;
   CUtensorMap tmA[OCCD_CONV_MAX_SRC];
   CUtensorMap tmW;
@@ -749,6 +958,106 @@ static int halo_geometry(const occd_conv_desc* d, occd_conv_plan* pl) {
   return OCCD_OK;
 }
 
+
+// x-packed halo plan (conv_halox_kernel): host arithmetic
+static int halox_geometry(const occd_conv_desc* d, occd_conv_plan* pl) {
+#define HX_REQUIRE(cond, msg) do { if (!(cond)) { occd_set_last_error("occd_conv_plan_create(halox): " msg); return OCCD_ERR_UNSUPPORTED; } } while (0)
+  HX_REQUIRE(d->n_src == 1 && !d->weight_per_image, "one source, shared weights");
+  HX_REQUIRE(d->stride[0] == 1 && d->stride[1] == 1 && d->stride[2] == 1, "stride must be 1");
+  HX_REQUIRE(d->omul[0] == 1 && d->omul[1] == 1 && d->omul[2] == 1 && d->oadd[0] == 0 && d->oadd[1] == 0 &&
+             d->oadd[2] == 0, "identity output mapping only");
+  HX_REQUIRE(d->OD + 2 * d->src_d0 == d->ID && d->OH == d->IH && d->OW == d->IW,
+             "output grid must equal the input grid (plus symmetric halo margins)");
+  HX_REQUIRE(d->IW == 8 || d->IW == 16 || d->IW == 32, "innermost extent W must be 8, 16 or 32 (one warp row)");
+  HX_REQUIRE(d->n_taps % 3 == 0 && d->n_taps <= 27, "taps must come as W triples");
+  HX_REQUIRE(d->src_C[0] <= 128 / pl->esize && 3 * d->Cout_pad <= 256, "one K chunk, 3 * Cout_pad <= 256");
+  const int dil = d->taps[2].dx;
+  HX_REQUIRE(dil >= 1 && dil <= 8 && dil < d->IW, "W dilation");
+  int hal[2] = {0, 0};
+  for (int i = 0; i < d->n_taps; i += 3) {
+    const occd_conv_tap &a = d->taps[i], &b = d->taps[i + 1], &c = d->taps[i + 2];
+    HX_REQUIRE(a.dx == -dil && b.dx == 0 && c.dx == dil && a.dz == b.dz && a.dz == c.dz && a.dy == b.dy &&
+               a.dy == c.dy, "taps must be ordered (dz, dy) groups of dx = -d, 0, +d");
+    HX_REQUIRE((a.dz == 0 || abs(a.dz) == dil) && (a.dy == 0 || abs(a.dy) == dil), "D / H taps must be {-d, 0, d}");
+    if (a.dz) hal[0] = 1;
+    if (a.dy) hal[1] = 1;
+  }
+  HaloxParams& h = pl->halox;
+  fill_epi(d, &h.epi);
+  const int KC = chunk_channels(d->src_C[0], pl->esize);
+  HX_REQUIRE(d->Kpad == KC, "Kpad must equal the k-chunk");
+  pl->kc = KC;
+  pl->rb = KC * pl->esize;
+  const int RB = pl->rb, NMMA = RB / 32;
+  h.d = dil; h.D = d->OD; h.H = d->IH;
+  h.src_d0 = d->src_d0;
+  h.hd = hal[0]; h.hh = hal[1];
+  h.n_groups = d->n_taps / 3;
+  h.CP = d->Cout_pad;
+  h.N_tile = 3 * d->Cout_pad;
+  h.PW = d->IW;
+  h.b_stride = round_up(h.N_tile * RB, 1024);
+  h.w_bytes = h.n_groups * h.b_stride;
+  const int smem_total = 227 * 1024 - h.w_bytes - 4096;   // barriers, TMEM slot, 1024-byte alignment slack
+  HX_REQUIRE(smem_total > 0, "weights do not fit in shared memory");
+  const int HR = 128 / h.PW;                               // h-rows of one plane per M tile
+  const int sD = (d->OD + dil - 1) / dil, sH = (d->IH + dil - 1) / dil;
+  // CTA tile = BD planes x nB blocks of HR h-rows (<= 2 M tiles: two accumulator sets of nM x N_tile columns)
+  double best = -1.0;
+  const int cand[3][2] = {{1, 1}, {1, 2}, {2, 1}};
+  for (int ci = 0; ci < 3; ++ci) {
+    const int BD = cand[ci][0], nB = cand[ci][1];
+    const int BH = nB * HR, PD = BD + 2 * hal[0], PH = BH + 2 * hal[1];
+    if ((PH - 1) * dil + 1 > 256 || (PD - 1) * dil + 1 > 256) continue;
+    const int rows = PD * PH * h.PW;
+    const int stage = round_up(rows * RB, 1024);
+    if (stage > smem_total) continue;
+    const int stages = smem_total / stage;
+    const int nM = BD * nB;
+    int set_stride = 32;
+    while (set_stride < nM * h.N_tile) set_stride *= 2;
+    if (2 * set_stride > 512) continue;
+    // cycles per useful output: MMA issue floor (59 cycles per instruction at N <= 118) plus, single-buffered,
+    // the un-overlapped L2 -> smem fill at the chip's ~42 B/cycle/SM
+    const double eff_d = (double)(sD < BD ? sD : BD) / BD, eff_h = (double)(sH < BH ? sH : BH) / BH;
+    const double mma = (double)nM * h.n_groups * NMMA * (h.N_tile > 118 ? h.N_tile / 2.0 : 59.0);
+    const double fill = stages >= 2 ? 0.0 : (double)rows * RB / 42.0;
+    // (tie-break: the tile that reloads the fewest halo rows per output)
+    const double cost = (mma + fill + 1e-3 * rows * RB) / (BD * BH * h.PW * eff_d * eff_h);
+    if (best < 0 || cost < best) {
+      best = cost;
+      h.BD = BD; h.BH = BH; h.PD = PD; h.PH = PH; h.nM = nM;
+      h.a_stage_bytes = stage; h.stages = stages > 4 ? 4 : stages;
+      h.set_stride = set_stride;
+    }
+  }
+  HX_REQUIRE(best >= 0, "no tile shape fits");
+  {
+    const int nB = h.BH / HR;
+    int m = 0;
+    for (int pd = 0; pd < h.BD; ++pd)
+      for (int blk = 0; blk < nB; ++blk, ++m) {
+        h.mt_pd[m] = pd + h.hd;
+        h.mt_ph0[m] = h.hh + blk * HR;
+        h.mt_row[m] = (h.mt_pd[m] * h.PH + h.mt_ph0[m]) * h.PW;
+      }
+  }
+  h.tmem_cols = 2 * h.set_stride;
+  h.tilesD = (sD + h.BD - 1) / h.BD; h.tilesH = (sH + h.BH - 1) / h.BH;
+  h.box_bytes = h.PD * h.PH * h.PW * RB;
+  for (int g = 0; g < h.n_groups; ++g)
+    h.grp_off[g] = ((d->taps[3 * g].dz / dil) * h.PH + d->taps[3 * g].dy / dil) * h.PW;
+  h.trace = g_trace_buf;
+  h.pdl = pdl_enabled();
+  pl->smem = (size_t)h.w_bytes + (size_t)h.stages * h.a_stage_bytes + 128 + 1024;
+  const long long num_tiles = (long long)d->B * dil * dil * h.tilesD * h.tilesH;
+  HX_REQUIRE(num_tiles < 2147483647LL, "too many tiles");
+  const int n_sms = n_sms_current();
+  pl->grid = dim3((unsigned)(num_tiles < n_sms ? num_tiles : n_sms));
+#undef HX_REQUIRE
+  return OCCD_OK;
+}
+
 static CUtensorMapSwizzle swizzle_for(int rb) {
   return rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
@@ -788,6 +1097,42 @@ static int halo_encode(const occd_conv_desc* d, occd_conv_plan* pl) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { occd_set_last_error("occd_conv_plan_create(halo): cuTensorMapEncodeTiled(weights) failed"); return OCCD_ERR_CUDA; }
+  }
+  return OCCD_OK;
+}
+
+
+static int halox_encode(const occd_conv_desc* d, occd_conv_plan* pl) {
+  const HaloxParams& h = pl->halox;
+  const int KC = pl->kc, C = d->src_C[0], dil = h.d, es = pl->esize;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    occd_set_last_error("occd_conv_plan_create: cuTensorMapEncodeTiled unavailable (no CUDA driver / GPU?)");
+    return OCCD_ERR_CUDA;
+  }
+  const CUtensorMapSwizzle sw = swizzle_for(pl->rb);
+  {
+    const cuuint64_t cs = (cuuint64_t)d->src_cstride[0] * es;
+    cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)d->IW, (cuuint64_t)d->IH, (cuuint64_t)d->ID, (cuuint64_t)d->B};
+    cuuint64_t gstr[4] = {cs, cs * d->IW, cs * d->IW * d->IH, cs * d->IW * d->IH * d->ID};
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)h.PW, (cuuint32_t)((h.PH - 1) * dil + 1),
+                         (cuuint32_t)((h.PD - 1) * dil + 1), 1};
+    cuuint32_t estr[5] = {1, 1, (cuuint32_t)dil, (cuuint32_t)dil, 1};
+    void* base = (void*)((const char*)d->src[0] + (size_t)d->src_coff[0] * es);
+    CUresult r = enc(&pl->tmA[0], tm_dtype(pl->dtype), 5, base, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { occd_set_last_error("occd_conv_plan_create(halox): cuTensorMapEncodeTiled(source) failed"); return OCCD_ERR_CUDA; }
+  }
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)d->Kpad, (cuuint64_t)d->n_taps * d->Cout_pad};
+    cuuint64_t gstr[1] = {(cuuint64_t)d->Kpad * es};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)h.N_tile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&pl->tmW, tm_dtype(pl->dtype), 2, (void*)d->weight, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { occd_set_last_error("occd_conv_plan_create(halox): cuTensorMapEncodeTiled(weights) failed"); return OCCD_ERR_CUDA; }
   }
   return OCCD_OK;
 }
@@ -1017,8 +1362,8 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
                    "occd_conv_plan_create: tap offset");
   }
   OCCD_CHECK_ARG(d->impl == OCCD_CONV_IMPL_TC || d->impl == OCCD_CONV_IMPL_SIMT || d->impl == OCCD_CONV_IMPL_HALO ||
-                 d->impl == OCCD_CONV_IMPL_TCX, "occd_conv_plan_create: impl");
-  OCCD_CHECK_ARG(!d->weight_per_image || d->impl != OCCD_CONV_IMPL_HALO,
+                 d->impl == OCCD_CONV_IMPL_TCX || d->impl == OCCD_CONV_IMPL_HALOX, "occd_conv_plan_create: impl");
+  OCCD_CHECK_ARG(!d->weight_per_image || (d->impl != OCCD_CONV_IMPL_HALO && d->impl != OCCD_CONV_IMPL_HALOX),
                  "occd_conv_plan_create: per-image weights: TC or SIMT impl");
 
   occd_conv_plan* pl = new (std::nothrow) occd_conv_plan;
@@ -1055,6 +1400,9 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
   if (d->impl == OCCD_CONV_IMPL_HALO) {
     rc = halo_geometry(d, pl);
     if (rc == OCCD_OK) rc = halo_encode(d, pl);
+  } else if (d->impl == OCCD_CONV_IMPL_HALOX) {
+    rc = halox_geometry(d, pl);
+    if (rc == OCCD_OK) rc = halox_encode(d, pl);
   } else {
     rc = tc_geometry(d, pl, d->impl == OCCD_CONV_IMPL_TCX);
     if (rc == OCCD_OK) rc = tc_encode(d, pl);
@@ -1081,6 +1429,13 @@ extern "C" int occd_conv_plan_info(const occd_conv_plan* pl, int* info) {
     info[0] = h.BD; info[1] = h.BH; info[2] = h.BW; info[3] = h.N_tile; info[4] = pl->kc;
     info[5] = h.stages * 100 + h.nM; info[6] = (int)pl->grid.x;
     info[7] = h.epi.B * h.d * h.d * h.d * h.tilesD * h.tilesH * h.tilesW;
+    return OCCD_OK;
+  }
+  if (pl->impl == OCCD_CONV_IMPL_HALOX) {
+    const HaloxParams& h = pl->halox;
+    info[0] = h.BD; info[1] = h.BH; info[2] = h.PW; info[3] = h.N_tile; info[4] = pl->kc;
+    info[5] = h.stages * 100 + h.nM; info[6] = (int)pl->grid.x;
+    info[7] = h.epi.B * h.d * h.d * h.tilesD * h.tilesH;
     return OCCD_OK;
   }
   info[0] = pl->tc.TD; info[1] = pl->tc.TH; info[2] = pl->tc.TW; info[3] = pl->tc.N_tile;
@@ -1133,6 +1488,28 @@ static int launch_halo(const occd_conv_plan* pl, cudaStream_t st) {
   return OCCD_OK;
 }
 
+template <typename T, int RB>
+static int launch_halox(const occd_conv_plan* pl, cudaStream_t st) {
+  static bool attr_set[64] = {false};  // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halox_kernel<T, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
+    attr_set[dev] = true;
+  }
+  if (pl->halox.pdl) {
+    cudaError_t e = launch_pdl(conv_halox_kernel<T, RB>, pl->grid, kTcThreads, pl->smem, st, pl->halox, pl->tmA[0],
+                               pl->tmW);
+    if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
+    return OCCD_OK;
+  }
+  conv_halox_kernel<T, RB><<<pl->grid, kTcThreads, pl->smem, st>>>(pl->halox, pl->tmA[0], pl->tmW);
+  OCCD_CHECK_LAUNCH();
+  return OCCD_OK;
+}
+
 template <typename T>
 static int run_typed(const occd_conv_plan* pl, cudaStream_t st) {
   if (pl->impl == OCCD_CONV_IMPL_SIMT) {
@@ -1145,6 +1522,13 @@ static int run_typed(const occd_conv_plan* pl, cudaStream_t st) {
       case 128: return launch_halo<T, 128>(pl, st);
       case 64: return launch_halo<T, 64>(pl, st);
       case 32: return launch_halo<T, 32>(pl, st);
+    }
+  }
+  if (pl->impl == OCCD_CONV_IMPL_HALOX) {
+    switch (pl->rb) {
+      case 128: return launch_halox<T, 128>(pl, st);
+      case 64: return launch_halox<T, 64>(pl, st);
+      case 32: return launch_halox<T, 32>(pl, st);
     }
   }
   if (pl->impl == OCCD_CONV_IMPL_TCX) {

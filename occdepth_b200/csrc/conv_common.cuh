@@ -24,15 +24,18 @@ struct ConvEpi {
   int out1_cstride, out1_coff, out1_C;
 };
 
-// Epilogue for one output position and NV consecutive channels [n0, n0+NV) held in v[] (fp32 accumulators).
-// NV is 8 or 16; n0 is a multiple of 8; channels >= Cout_store are not written.  T is the activation element type
-// (bf16, or fp32 holding TF32 values: Elem<float>::st8 rounds on store).
+__device__ __forceinline__ long long epi_pos(const ConvEpi& e, int b, int od, int oh, int ow) {
+  return (((long long)b * e.ODf + ((long long)od * e.omul[0] + e.oadd[0])) * e.OHf +
+          ((long long)oh * e.omul[1] + e.oadd[1])) * e.OWf +
+         ((long long)ow * e.omul[2] + e.oadd[2]);
+}
+
+// Epilogue arithmetic for one output position `pos` and NV consecutive channels [n0, n0+NV) held in v[] (fp32
+// accumulators): v = acc + bias + res1 (+ res2); the optional second output (pre-activation value: channels-last or
+// fp32 planar) is written here; on return v[] holds the out0 values act(v) (+ res2 when it is added after the
+// activation).  NV is 8 or 16; n0 is a multiple of 8.  T is the activation element type.
 template <typename T, int NV>
-__device__ __forceinline__ void conv_epilogue_row(const ConvEpi& e, int b, int od, int oh, int ow, int n0,
-                                                  float* v) {
-  const long long pos = (((long long)b * e.ODf + ((long long)od * e.omul[0] + e.oadd[0])) * e.OHf +
-                         ((long long)oh * e.omul[1] + e.oadd[1])) * e.OWf +
-                        ((long long)ow * e.omul[2] + e.oadd[2]);
+__device__ __forceinline__ void conv_epilogue_compute(const ConvEpi& e, long long pos, int b, int n0, float* v) {
 #pragma unroll
   for (int g = 0; g < NV; g += 8) {
     const int n = n0 + g;
@@ -72,9 +75,24 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvEpi& e, int b, int o
 #pragma unroll
         for (int i = 0; i < 8; ++i) vv[i] += r2[i];
       }
-      T* o0 = reinterpret_cast<T*>(e.out0) + pos * e.out0_cstride + e.out0_coff + n;
-      if (e.out0_exact) Elem<T>::st8_exact(o0, vv);
-      else Elem<T>::st8(o0, vv);
     }
   }
 }
+
+// compute + direct (per-thread, 8-channel vector) global stores of out0: SIMT kernel, halo kernel
+template <typename T, int NV>
+__device__ __forceinline__ void conv_epilogue_row(const ConvEpi& e, int b, int od, int oh, int ow, int n0,
+                                                  float* v) {
+  const long long pos = epi_pos(e, b, od, oh, ow);
+  conv_epilogue_compute<T, NV>(e, pos, b, n0, v);
+  if (!e.out0) return;
+#pragma unroll
+  for (int g = 0; g < NV; g += 8) {
+    const int n = n0 + g;
+    if (n >= e.Cout_store) break;
+    T* o0 = reinterpret_cast<T*>(e.out0) + pos * e.out0_cstride + e.out0_coff + n;
+    if (e.out0_exact) Elem<T>::st8_exact(o0, v + g);
+    else Elem<T>::st8(o0, v + g);
+  }
+}
+

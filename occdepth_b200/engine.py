@@ -62,10 +62,31 @@ def default_impl():
     narrow-output convs with W taps, else the per-tap tcgen05 kernel; 'tc' / 'tcx' / 'halo' / 'simt' force one
     implementation (simt = CUDA-core cross-check)."""
     v = os.environ.get("OCCDEPTH_CONV_IMPL", "auto").lower()
-    if v not in ("auto", "tc", "simt", "halo", "tcx"):
-        raise ValueError("OCCDEPTH_CONV_IMPL must be 'auto', 'tc', 'tcx', 'halo' or 'simt'")
+    if v not in ("auto", "tc", "simt", "halo", "halox", "tcx"):
+        raise ValueError("OCCDEPTH_CONV_IMPL must be 'auto', 'tc', 'tcx', 'halo', 'halox' or 'simt'")
     return {"auto": None, "tc": _lib.CONV_IMPL_TC, "simt": _lib.CONV_IMPL_SIMT, "halo": _lib.CONV_IMPL_HALO,
-            "tcx": _lib.CONV_IMPL_TCX}[v]
+            "halox": _lib.CONV_IMPL_HALOX, "tcx": _lib.CONV_IMPL_TCX}[v]
+
+
+def halox_eligible(srcs, taps, stride, omul, out_dims, Cout_pad, weight_buf):
+    """shape test mirroring halox_geometry (csrc/conv.cu): stride-1 'same' conv on a grid whose innermost extent W is
+    8 / 16 / 32, taps = (dz, dy) groups of dx = -d, 0, +d with dz, dy in {-d, 0, d}, one K chunk, 3*Cout_pad <= 256"""
+    if len(srcs) != 1 or weight_buf is not None or len(taps) % 3 or not 3 <= len(taps) <= 27:
+        return False
+    if tuple(stride) != (1, 1, 1) or tuple(omul) != (1, 1, 1) or tuple(out_dims) != tuple(srcs[0].dims[1:]):
+        return False
+    if srcs[0].dims[3] not in (8, 16, 32) or srcs[0].C > 128 // srcs[0].esize or 3 * Cout_pad > 256:
+        return False
+    d = taps[2][3]
+    if d < 1 or d >= srcs[0].dims[3]:
+        return False
+    for i in range(0, len(taps), 3):
+        a, b, c = taps[i], taps[i + 1], taps[i + 2]
+        if not (a[:3] == b[:3] == c[:3] and (a[3], b[3], c[3]) == (-d, 0, d)):
+            return False
+        if a[1] not in (-d, 0, d) or a[2] not in (-d, 0, d):
+            return False
+    return True
 
 
 def tcx_eligible(taps, stride, Cout_pad):
@@ -259,6 +280,9 @@ class ConvOp:
                     else _lib.CONV_IMPL_TC)
             if impl == _lib.CONV_IMPL_TC and tcx_eligible(taps, stride, Cout_pad):
                 impl = _lib.CONV_IMPL_TCX
+            if halox_eligible(srcs, taps, stride, omul, out_dims, Cout_pad, weight_buf):
+                self._fallback = impl
+                impl = _lib.CONV_IMPL_HALOX
         d.impl = impl
         d.dtype = LIB_DTYPE[precision_of(adt)]
         d.n_src = len(srcs)
@@ -303,6 +327,9 @@ class ConvOp:
         self.flops = 2 * B * OD * OH * OW * Cout * sum(srcs[t[0]].C for t in taps)
         h = C.c_void_p()
         rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
+        if rc != 0 and auto and d.impl == _lib.CONV_IMPL_HALOX:
+            d.impl = self._fallback         # geometry declined (e.g. weights + one stage do not fit)
+            rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))
         if rc != 0 and auto and d.impl == _lib.CONV_IMPL_TCX:
             d.impl = _lib.CONV_IMPL_TC
             rc = _lib.lib().occd_conv_plan_create(C.byref(d), C.byref(h))

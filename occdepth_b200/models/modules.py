@@ -31,8 +31,10 @@ def _emit_aspp(plan, m, x, out=None, name="aspp"):
         n = len(ts)
         for i, dl in enumerate(m.conv_list):
             last = i == n - 1
+            # the partial sums only feed the next launch's epilogue add (never an MMA operand): unrounded in tf32 mode
             y = plan.conv(ts[i], ws[i], b2s[i], padding=dl, dilation=dl, act="relu" if last else "none", res1=y,
-                          res2=x if last else None, out=out if last else None, name="%s.conv2.%d" % (name, i))
+                          res2=x if last else None, out=out if last else None, name="%s.conv2.%d" % (name, i),
+                          out0_exact=not last)
         return y
     return plan.conv_multi(ts, ws, bs, list(m.conv_list), list(m.conv_list), act="relu", res1=x, out=out,
                            name=name + ".conv2")

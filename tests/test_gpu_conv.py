@@ -59,11 +59,37 @@ def test_conv_halo(case, precision):
     from occdepth_b200 import _lib
     kw = G.HALO_CASES[case]
     one_chunk = 32 if precision == "tf32" else 64           # the resident-weight scheme holds ONE K chunk
-    if kw.get("Cin", 32) > one_chunk:
+    if kw.get("Cin", 32) > one_chunk or (precision == "tf32" and case == "h_big"):
+        # (tf32: 27 resident taps x 32 x 128 B leave no room for a W = 32 box -- auto mode uses the x-packed kernel)
         with pytest.raises(RuntimeError, match="halo"):
             G.conv_case(_lib.CONV_IMPL_HALO, precision=precision, **kw)
         return
     e, info = G.conv_case(_lib.CONV_IMPL_HALO, precision=precision, **kw)
+    assert e <= G.TOL[precision], (e, info)
+
+
+HALOX_CASES = {
+    "hx_w32_d1": dict(Cin=32, Cout=32, dims=(6, 10, 32)),
+    "hx_w32_d2_res": dict(Cin=32, Cout=32, dims=(9, 11, 32), dil=(2, 2, 2), res=True),
+    "hx_w32_d3": dict(Cin=32, Cout=32, dims=(8, 13, 32), dil=(3, 3, 3)),
+    "hx_w16_c16": dict(Cin=16, Cout=16, dims=(5, 9, 16)),
+    "hx_w8_b2": dict(B=2, Cin=24, Cout=40, dims=(7, 6, 8), act="leaky"),
+    "hx_w32_n2_planar": dict(Cin=32, Cout=2, dims=(6, 10, 32), act="none", planar=True),
+    "hx_w32_n20_pre": dict(Cin=32, Cout=20, dims=(5, 12, 32), pre=True),
+    "hx_2d_hw": dict(k=(1, 3, 3), Cin=32, Cout=32, dims=(1, 21, 32), act="leaky"),
+    "hx_1d_w": dict(k=(1, 1, 3), Cin=16, Cout=16, dims=(6, 7, 16), dil=(1, 1, 2)),
+    "hx_c8": dict(Cin=2, Cout=20, dims=(4, 9, 32), act="none"),
+    "hx_big": dict(Cin=32, Cout=32, dims=(20, 40, 32)),
+    "hx_big_d3_respost": dict(Cin=32, Cout=32, dims=(20, 40, 32), dil=(3, 3, 3), res=True, res_post=True),
+}
+
+
+@PREC
+@pytest.mark.parametrize("case", sorted(HALOX_CASES))
+def test_conv_halo_xpacked(case, precision):
+    """x-packed halo kernel (W == one warp row: three W taps per MMA, masked lane shifts == zero padding)"""
+    from occdepth_b200 import _lib
+    e, info = G.conv_case(_lib.CONV_IMPL_HALOX, precision=precision, **HALOX_CASES[case])
     assert e <= G.TOL[precision], (e, info)
 
 
@@ -86,7 +112,8 @@ def test_conv_tc_xpacked(case, precision):
 
 
 def test_auto_picks_tcx_and_halo():
-    """the default ('auto') selection: decoder-width 3x3 convs run x-packed, head-width convs on the halo kernel"""
+    """the default ('auto') selection: decoder-width 3x3 convs run x-packed (per-tap kernel), head convs on the
+    x-packed halo kernel (W = 32 = one warp row), narrow 2-D convs on the halo kernel"""
     import torch
     from occdepth_b200 import _lib
     from occdepth_b200.engine import Plan
@@ -96,4 +123,7 @@ def test_auto_picks_tcx_and_halo():
     plan.conv(x, torch.randn(80, 80, 1, 3, 3, device=dev), torch.zeros(80, device=dev), padding=(0, 1, 1))
     y = plan.alloc(1, 8, 16, 32, 32)
     plan.conv(y, torch.randn(32, 32, 3, 3, 3, device=dev), torch.zeros(32, device=dev), padding=1)
-    assert plan.ops[0].impl == _lib.CONV_IMPL_TCX and plan.ops[1].impl == _lib.CONV_IMPL_HALO
+    z = plan.alloc(1, 1, 24, 40, 32)
+    plan.conv(z, torch.randn(32, 32, 1, 3, 3, device=dev), torch.zeros(32, device=dev), padding=(0, 1, 1))
+    assert plan.ops[0].impl == _lib.CONV_IMPL_TCX and plan.ops[1].impl == _lib.CONV_IMPL_HALOX
+    assert plan.ops[2].impl == _lib.CONV_IMPL_HALO
