@@ -262,6 +262,11 @@ int occd_upsample_bilinear_ac(const void* in, void* out, int dtype, int B, int h
 int occd_frustum_sample_fwd(const float* depth, const float* cams, int V, int Dn, int h, int w, int X, int Y,
                             int Z, float img_w, float img_h, float dmin, float dmax, int mean_mode, float* out,
                             int perm_xzy, void* stream);
+/* the infer_mode / ONNX-export route of the same step (OccDepth.py:310-317, flosp_depth.py:564-565, custom  */
+/* GridSample symbolic f2v/sampler.py:9-34): the caller supplies the sampling grids, grids: [V][X*Y*Z][3] fp32 */
+/* normalised (x, y, z) coordinates of F.grid_sample(bilinear, zeros, align_corners=False)                    */
+int occd_grid_sample_prior_fwd(const float* depth, const float* grids, int V, int Dn, int h, int w, int X, int Y,
+                               int Z, int mean_mode, float* out, int perm_xzy, void* stream);
 /* softmax over the C planar channels of [B][C][S] fp32 (depth_feature.softmax(1), flosp_depth.py:548) */
 int occd_softmax_planar(const float* in, float* out, long long B, int C, long long S, void* stream);
 /* out[b] = act(W in[b] + bias): the Linear / 1x1-on-a-vector layers of DepthNet.mlp and SELayer    */

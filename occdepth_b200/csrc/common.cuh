@@ -184,3 +184,46 @@ template <> struct Elem<float> {
   } while (0)
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch for every kernel of the plan: a kernel launched through occd_launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its blocks may be scheduled while the previous grid drains;
+// pdl_wait() -- the kernel's FIRST statement, before any global read or write -- blocks until that grid has
+// completed and flushed.  OCCD_PDL=0 falls back to plain launches (pdl_wait is then a no-op).
+#include <stdlib.h>
+#include <utility>
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+static inline int occd_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OCCD_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t occd_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                      Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = occd_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+#define OCCD_LAUNCH_CHECKED(...)                              \
+  do {                                                        \
+    cudaError_t e__ = occd_launch(__VA_ARGS__);               \
+    if (e__ != cudaSuccess) {                                 \
+      occd_set_last_error(cudaGetErrorString(e__));           \
+      return OCCD_ERR_CUDA;                                   \
+    }                                                         \
+  } while (0)

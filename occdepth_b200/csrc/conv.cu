@@ -242,17 +242,22 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         // software-pipelined: the tcgen05.ld of this group's next 16 columns is in flight while these are stored
         uint32_t ra[16], rb[16];
         int c0 = c_begin;
+        long long t_ld = 0, t_epi = 0, t_a = 0;
         if (c0 < c_end) tc::tmem_ld16_issue(taddr + (uint32_t)c0, ra);
         for (; c0 < c_end; c0 += 32) {
+          if (tracer) t_a = clock64();
           tc::tmem_ld_wait16(ra);
+          if (tracer) t_ld += clock64() - t_a;
           const bool has_b = c0 + 16 < c_end;
           if (has_b) tc::tmem_ld16_issue(taddr + (uint32_t)(c0 + 16), rb);
+          if (tracer) t_a = clock64();
           if (valid) {
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]);
             conv_epilogue_row<T, 16>(p.epi, b, od, oh, ow, n0 + c0, v);
           }
+          if (tracer) t_epi += clock64() - t_a;
           if (has_b) {
             tc::tmem_ld_wait16(rb);
             if (c0 + 32 < c_end) tc::tmem_ld16_issue(taddr + (uint32_t)(c0 + 32), ra);
@@ -264,6 +269,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
             }
           }
         }
+        if (tracer && j < 64) p.trace[j * 8 + 7] = (t_ld << 32) | (t_epi & 0xffffffffll);
       }
       tc::fence_before_sync();
       tc::mbar_arrive(tmem_empty_bar + 8u * acc);  // this thread's TMEM reads of the buffer are done
@@ -827,18 +833,10 @@ static int fill_epi(const occd_conv_desc* d, ConvEpi* e) {
   return 0;
 }
 
-// Programmatic dependent launch: conv launches carry cudaLaunchAttributeProgrammaticStreamSerialization and the
-// kernels wait on griddepcontrol after their prologue (barrier init, TMEM alloc, tensor-map prefetch overlap the
-// tail of the previous grid).  Measured on B200 (round 2, profiles/r02_ab_experiments.txt): 1.0 % of the config-2
-// forward, results bit-identical.  OCCD_PDL=0 switches it off.
-static int pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("OCCD_PDL");
-    v = (e && atoi(e) == 0) ? 0 : 1;
-  }
-  return v;
-}
+// Programmatic dependent launch (common.cuh): the conv kernels wait on griddepcontrol after their prologue (barrier
+// init, TMEM alloc, tensor-map prefetch overlap the tail of the previous grid).  Measured on B200 (round 2,
+// profiles/r02_ab_experiments.txt): 1.0 % of the config-2 forward, results bit-identical.
+static int pdl_enabled() { return occd_pdl_enabled(); }
 
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t st,
@@ -1204,23 +1202,39 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
   }
   t.TWv = xp ? 30 : t.TW;
   t.tiles_w = (d->OW + t.TWv - 1) / t.TWv; t.tiles_h = (d->OH + t.TH - 1) / t.TH; t.tiles_d = (d->OD + t.TD - 1) / t.TD;
-  // N tile: largest divisor of Cout_pad that is a multiple of 16 and <= 256
+  // N tile: the divisor of Cout_pad (multiple of 16, <= 256) with the smallest estimated makespan.  Three measured
+  // B200 constants drive the model (profiles/r02_mma_issue_bench.txt, r02_conv_role_traces.txt, r02_membw.txt):
+  //   one tcgen05.mma costs max(59, N/2) cycles for M = 128, any operand type
+  //   an SM pulls ~44 bytes/cycle from L2 when the whole chip does (6300 B/cycle chip-wide)
+  //   the epilogue's scattered channels-last stores drain at ~5 bytes/cycle/SM
+  // A tile's main loop (TMA + MMA) overlaps the previous tile's epilogue, so a CTA's time is
+  // waves * max(mainloop, epilogue) + min(mainloop, epilogue).  Small-M layers (late encoder stages: 9 M tiles) get
+  // narrow N tiles that spread the write-bound epilogue over every SM; large-M layers get the widest tile (fewest
+  // re-reads of the A operand).
   t.Cout_pad = d->Cout_pad;
-  t.N_tile = 16;
-  for (int n = 16; n <= 256 && n <= d->Cout_pad; n += 16)
-    if (d->Cout_pad % n == 0) t.N_tile = n;
   {
-    // small-M layers (late encoder stages): a narrower N tile that still keeps >= 64 columns trades some A
-    // re-reads for enough tiles to occupy every SM
+    int iters = 0;
+    for (int i = 0; i < t.n_taps; ++i) iters += t.n_kchunks[t.tap_src[i]];
     const long long m_tiles0 = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w;
     const int n_sms = n_sms_current();
-    int best = t.N_tile;
-    for (int n = t.N_tile; n >= 64; n -= 16) {
+    const double out_bytes_per_col = 128.0 * ((d->out0 ? pl->esize : 0) + (d->out1_mode == OCCD_OUT1_CL ? pl->esize : 0) +
+                                              (d->out1_mode == OCCD_OUT1_F32_PLANAR ? 4 : 0));
+    double best = -1.0;
+    t.N_tile = 16;
+    for (int n = 16; n <= 256 && n <= d->Cout_pad; n += 16) {
       if (d->Cout_pad % n) continue;
-      best = n;
-      if (m_tiles0 * (d->Cout_pad / n) >= n_sms) break;
+      const double mma = (RB / 32) * (n > 118 ? n / 2.0 : 59.0);
+      const double load = (128.0 + n) * RB / 44.0;
+      const double mainloop = iters * (mma > load ? mma : load);
+      const double epi = out_bytes_per_col * n / 5.0;
+      const long long tiles = m_tiles0 * (d->Cout_pad / n);
+      const double waves = (double)((tiles + n_sms - 1) / n_sms);
+      const double span = waves * (mainloop > epi ? mainloop : epi) + (mainloop > epi ? epi : mainloop);
+      if (best < 0 || span <= best * 1.02) {   // within 2 %: the wider tile (fewer tiles, fewer A re-reads) wins
+        if (best < 0 || span < best) best = span;
+        t.N_tile = n;
+      }
     }
-    if (m_tiles0 * (d->Cout_pad / t.N_tile) < n_sms) t.N_tile = best;
   }
   if (xp) t.N_tile = 3 * d->Cout_pad;  // one N tile: the three taps' weights stacked
   t.tmem_cols = 32;

@@ -309,6 +309,7 @@ DWT_HD void phase_pool(const Args& a, BlockIdx blk, int tid, const float* red) {
 template <typename T, int K, int S, int CVB, int TH>
 __global__ void __launch_bounds__(kThreads, 2) dwconv_tiled_kernel(const Args a) {
   using C_ = Cfg<T, K, S, CVB, TH>;
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char dwt_smem[];
   T* tile = reinterpret_cast<T*>(dwt_smem);
   float* wsm = reinterpret_cast<float*>(dwt_smem + C_::kTileBytes);

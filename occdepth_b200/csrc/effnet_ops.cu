@@ -124,6 +124,7 @@ dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float
 __global__ void __launch_bounds__(128)
 se_fc1_kernel(const long long* __restrict__ pool, float inv_hw, const float* __restrict__ w1,
               const float* __restrict__ b1, float* __restrict__ hidden, int C, int R) {
+  pdl_wait();
   __shared__ float red[4];
   const int r = blockIdx.x, b = blockIdx.y;
   const float* wr = w1 + (long long)r * C;
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(256)
 se_fc2_fold_kernel(long long* __restrict__ pool, const float* __restrict__ hidden, const float* __restrict__ w2t,
                    const float* __restrict__ b2, const float* __restrict__ master, T* __restrict__ out,
                    int C, int R, int rows, int Kpad, int rows_per_block) {
+  pdl_wait();
   extern __shared__ float hid[];
   const int img = blockIdx.z;   // one weight set per image
   for (int r = threadIdx.x; r < R; r += 256) hid[r] = hidden[(long long)img * R + r];
@@ -205,6 +207,7 @@ template <typename T>
 __global__ void upsample_bilinear_kernel(const T* __restrict__ in, T* __restrict__ out, int B,
                                          int h, int w, int OH, int OW, int CV, int cs_in, int in_off, int cs_out,
                                          int out_off, float sy, float sx) {
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * OH * OW * CV;
   if (i >= total) return;
@@ -294,8 +297,7 @@ int launch_dw_tiled(const dwt::Args& a, int B, cudaStream_t st) {
   }
   const int tiles_y = (a.OH + TH - 1) / TH;
   dim3 grid(a.tiles_x * tiles_y, (a.C + C_::CT - 1) / C_::CT, B);
-  dwt::dwconv_tiled_kernel<T, K, S, CVB, TH><<<grid, dwt::kThreads, C_::kSmemBytes, st>>>(a);
-  OCCD_CHECK_LAUNCH();
+  OCCD_LAUNCH_CHECKED(dwt::dwconv_tiled_kernel<T, K, S, CVB, TH>, grid, dim3(dwt::kThreads), C_::kSmemBytes, st, a);
   return OCCD_OK;
 }
 
@@ -383,11 +385,9 @@ extern "C" int occd_upsample_bilinear_ac(const void* in, void* out, int dtype, i
   const float sy = OH > 1 ? (float)(h - 1) / (float)(OH - 1) : 0.f;
   const float sx = OW > 1 ? (float)(w - 1) / (float)(OW - 1) : 0.f;
   const long long total = (long long)B * OH * OW * CV;
-  OCCD_DISPATCH_DTYPE(dtype, T, (upsample_bilinear_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0,
-                                                                (cudaStream_t)stream>>>(
-                                     (const T*)in, (T*)out, B, h, w, OH, OW, CV, cs_in, in_off, cs_out, out_off, sy,
-                                     sx)));
-  OCCD_CHECK_LAUNCH();
+  OCCD_DISPATCH_DTYPE(dtype, T, OCCD_LAUNCH_CHECKED(upsample_bilinear_kernel<T>, dim3((unsigned)((total + 255) / 256)),
+                                                    dim3(256), 0, (cudaStream_t)stream, (const T*)in, (T*)out, B, h, w,
+                                                    OH, OW, CV, cs_in, in_off, cs_out, out_off, sy, sx));
   return OCCD_OK;
 }
 
@@ -398,14 +398,13 @@ extern "C" int occd_se_gate_fold_fwd(long long* pool, float inv_hw, const float*
                  Kpad >= C && R <= 8192, "occd_se_gate_fold_fwd: args");
   cudaStream_t st = (cudaStream_t)stream;
   OCCD_CHECK_ARG(B >= 1 && B <= 65535, "occd_se_gate_fold_fwd: B");
-  se_fc1_kernel<<<dim3(R, B), 128, 0, st>>>(pool, inv_hw, w1, b1, hidden, C, R);
-  OCCD_CHECK_LAUNCH();
+  OCCD_LAUNCH_CHECKED(se_fc1_kernel, dim3(R, B), dim3(128), 0, st, (const long long*)pool, inv_hw, w1, b1, hidden, C, R);
   const int kblocks = (Kpad + 255) / 256;
   int rows_per_block = rows;
   while (rows_per_block > 16 && B * kblocks * ((rows + rows_per_block - 1) / rows_per_block) < 296) rows_per_block /= 2;
   dim3 grid(kblocks, (rows + rows_per_block - 1) / rows_per_block, B);
-  OCCD_DISPATCH_DTYPE(wdtype, T, (se_fc2_fold_kernel<T><<<grid, 256, R * sizeof(float), st>>>(
-                                      pool, hidden, w2t, b2, master, (T*)wout, C, R, rows, Kpad, rows_per_block)));
-  OCCD_CHECK_LAUNCH();
+  OCCD_DISPATCH_DTYPE(wdtype, T, OCCD_LAUNCH_CHECKED(se_fc2_fold_kernel<T>, grid, dim3(256), R * sizeof(float), st, pool,
+                                                     (const float*)hidden, w2t, b2, master, (T*)wout, C, R, rows, Kpad,
+                                                     rows_per_block));
   return OCCD_OK;
 }

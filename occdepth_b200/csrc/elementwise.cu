@@ -10,6 +10,7 @@ namespace {
 template <typename T>
 __global__ void softmax_planar_to_cl_kernel(const float* __restrict__ in, T* __restrict__ out, int C,
                                             long long S, long long total, int cstride, int coff) {
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long b = i / S, s = i % S;
@@ -105,10 +106,9 @@ extern "C" int occd_softmax_planar_to_cl(const float* in, void* out, int dtype, 
                                          int cstride, int coff, void* stream) {
   OCCD_CHECK_ARG(in && out && B > 0 && C > 0 && C <= 32 && S > 0 && coff + C <= cstride, "occd_softmax_planar_to_cl: args");
   const long long total = B * S;
-  OCCD_DISPATCH_DTYPE(dtype, T, (softmax_planar_to_cl_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0,
-                                                                   (cudaStream_t)stream>>>(in, (T*)out, C, S, total,
-                                                                                           cstride, coff)));
-  OCCD_CHECK_LAUNCH();
+  OCCD_DISPATCH_DTYPE(dtype, T, OCCD_LAUNCH_CHECKED(softmax_planar_to_cl_kernel<T>, dim3((unsigned)((total + 255) / 256)),
+                                                    dim3(256), 0, (cudaStream_t)stream, in, (T*)out, C, S, total,
+                                                    cstride, coff));
   return OCCD_OK;
 }
 

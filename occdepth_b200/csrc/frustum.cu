@@ -20,7 +20,12 @@ __device__ __forceinline__ float dehom(float z) {  // kornia 0.5.0 convert_point
   return fabsf(z) > 1e-8f ? 1.f / (z + 1e-8f) : 1.f;
 }
 
-__global__ void frustum_sample_kernel(const float* __restrict__ depth, const FrustumCam* __restrict__ cams, int V,
+// GIVEN: the normalised sampling coordinates are read from `grids` ([V][N][3] = (x, y, z) of F.grid_sample's grid:
+// the reference's infer_mode / ONNX route feeds pre-computed grids, OccDepth.py:310-317, flosp_depth.py:564-565)
+// instead of being computed from the camera tables.
+template <bool GIVEN>
+__global__ void frustum_sample_kernel(const float* __restrict__ depth, const FrustumCam* __restrict__ cams,
+                                      const float* __restrict__ grids, int V,
                                       int Dn, int h, int w, int X, int Y, int Z, float img_w, float img_h,
                                       float dmin, float bin_size, int mean_mode, float* __restrict__ out,
                                       int perm_xzy) {
@@ -31,6 +36,11 @@ __global__ void frustum_sample_kernel(const float* __restrict__ depth, const Fru
   const float px = i + 0.5f, py = j + 0.5f, pz = k + 0.5f;
   float fsum = 0.f, msum = 0.f;
   for (int v = 0; v < V; ++v) {
+    float nx, ny, nz;
+    if constexpr (GIVEN) {
+      const float* g = grids + ((long long)v * N + n) * 3;
+      nx = g[0]; ny = g[1]; nz = g[2];
+    } else {
     const FrustumCam& c = cams[v];
     // camera point (homogeneous w == 1 -> scale 1/(1+1e-8) == 1 in fp32)
     const float cx = c.T[0] * px + c.T[1] * py + c.T[2] * pz + c.T[3];
@@ -49,12 +59,13 @@ __global__ void frustum_sample_kernel(const float* __restrict__ depth, const Fru
     const float gz = c.ida[8] * u + c.ida[9] * vv + c.ida[10] * bin + c.ida[11];
     const float gw = c.ida[12] * u + c.ida[13] * vv + c.ida[14] * bin + c.ida[15];
     const float s2 = dehom(gw);
-    float nx = gx * s2 / (img_w - 1.f) * 2.f - 1.f;
-    float ny = gy * s2 / (img_h - 1.f) * 2.f - 1.f;
-    float nz = gz * s2 / ((float)Dn - 1.f) * 2.f - 1.f;
+    nx = gx * s2 / (img_w - 1.f) * 2.f - 1.f;
+    ny = gy * s2 / (img_h - 1.f) * 2.f - 1.f;
+    nz = gz * s2 / ((float)Dn - 1.f) * 2.f - 1.f;
     if (!isfinite(nx)) nx = -2.f;
     if (!isfinite(ny)) ny = -2.f;
     if (!isfinite(nz)) nz = -2.f;
+    }
     // grid_sample, align_corners=False: pixel = ((g + 1) * size - 1) / 2
     const float fx = ((nx + 1.f) * w - 1.f) * 0.5f;
     const float fy = ((ny + 1.f) * h - 1.f) * 0.5f;
@@ -143,9 +154,20 @@ extern "C" int occd_frustum_sample_fwd(const float* depth, const float* cams, in
                  "occd_frustum_sample_fwd: args");
   const float bin_size = 2.f * (dmax - dmin) / ((float)Dn * (1.f + (float)Dn));
   const long long N = (long long)X * Y * Z;
-  frustum_sample_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      depth, reinterpret_cast<const FrustumCam*>(cams), V, Dn, h, w, X, Y, Z, img_w, img_h, dmin, bin_size, mean_mode,
-      out, perm_xzy);
+  frustum_sample_kernel<false><<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      depth, reinterpret_cast<const FrustumCam*>(cams), nullptr, V, Dn, h, w, X, Y, Z, img_w, img_h, dmin, bin_size,
+      mean_mode, out, perm_xzy);
+  OCCD_CHECK_LAUNCH();
+  return OCCD_OK;
+}
+
+extern "C" int occd_grid_sample_prior_fwd(const float* depth, const float* grids, int V, int Dn, int h, int w, int X,
+                                          int Y, int Z, int mean_mode, float* out, int perm_xzy, void* stream) {
+  OCCD_CHECK_ARG(depth && grids && out && V >= 1 && Dn > 1 && h > 0 && w > 0 && X > 0 && Y > 0 && Z > 0,
+                 "occd_grid_sample_prior_fwd: args");
+  const long long N = (long long)X * Y * Z;
+  frustum_sample_kernel<true><<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      depth, nullptr, grids, V, Dn, h, w, X, Y, Z, 0.f, 0.f, 0.f, 1.f, mean_mode, out, perm_xzy);
   OCCD_CHECK_LAUNCH();
   return OCCD_OK;
 }

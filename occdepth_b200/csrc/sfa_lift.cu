@@ -248,6 +248,7 @@ sfa_lift_p1_kernel(const SfaKParams p) {
   constexpr int NS = OCCD_SFA_MAX_SCALES;
   __shared__ longlong2 s_pix[V][VPB * kIters];
   __shared__ unsigned char s_fov[V][VPB * kIters];
+  pdl_wait();
   const long long block_n0 = (long long)blockIdx.x * (VPB * kIters);
   const int n_block = (int)min((long long)(VPB * kIters), p.N - block_n0);
 #pragma unroll
@@ -420,7 +421,8 @@ int launch_g(const SfaKParams& kp, cudaStream_t st) {
   const long long per_block = (long long)VPB * kIters;
   const long long blocks = (kp.N + per_block - 1) / per_block;
   if (kp.P == 1 && sfa_fits_int32(kp, V)) {
-    sfa_lift_p1_kernel<T, V, NV, G><<<(unsigned)blocks, kThreads, 0, st>>>(kp);
+    OCCD_LAUNCH_CHECKED(sfa_lift_p1_kernel<T, V, NV, G>, dim3((unsigned)blocks), dim3(kThreads), 0, st, kp);
+    return OCCD_OK;
   } else {
     const size_t smem = (size_t)V * VPB * kIters * kp.P * (sizeof(longlong2) + 1);
     if (smem > 200 * 1024) {

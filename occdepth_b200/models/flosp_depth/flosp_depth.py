@@ -99,8 +99,6 @@ class FlospDepth(B200Module):
         self.agg_voxel_mode = agg_voxel_mode
         if agg_voxel_mode not in ("mean", "sum"):
             raise NotImplementedError("agg_voxel_mode: {}".format(agg_voxel_mode))
-        if infer_mode:
-            raise NotImplementedError("FlospDepth(infer_mode=True) (pre-computed grids for ONNX export) is not built")
 
     # ---- host-side camera preprocessing (what FlospDepth.forward / FrustumGridGenerator do with torch on the
     # ---- host for 4x4 matrices, flosp_depth.py:466-541, frustum_grid_generator.py:20-67) ----
@@ -195,16 +193,35 @@ class FlospDepth(B200Module):
         prior = torch.empty(B, X * Y * Z, dtype=torch.float32, device=dev)
         perm = 1 if vox_origin is not None else 0      # NYU: x3ds_depth.permute(0,1,2,4,3), OccDepth.py:335-337
         H_img, W_img = self.final_dim
-        for b in range(B):
+        mean_mode = 1 if self.agg_voxel_mode == "mean" else 0
+        if self.infer_mode:
+            # the caller supplies batch["grids"] (one (B, X, Y, Z, 3) grid per camera) and batch["scaled_pixel_size"]
+            # (flosp_depth.py:564-565, OccDepth.py:310-317): staged into these static buffers before every replay
+            grids = torch.zeros(B, n_cams, X * Y * Z, 3, dtype=torch.float32, device=dev)
+            self.__dict__["_grids"] = grids
+            for b in range(B):
+                pb = prob[b * V:b * V + n_cams]
+                plan.add(FnOp(lambda st, pb=pb, gb=grids[b], ob=prior[b]: L.occd_grid_sample_prior_fwd(
+                    pb.data_ptr(), gb.data_ptr(), n_cams, Dn, h, w, X, Y, Z, mean_mode, ob.data_ptr(), perm, st),
+                    "grid_sample_prior", keep=(prob, grids, prior)))
+        for b in range(B if not self.infer_mode else 0):
             pb = prob[b * V:b * V + n_cams]
             plan.add(FnOp(lambda st, pb=pb, cb=cams[b], ob=prior[b]: L.occd_frustum_sample_fwd(
                 pb.data_ptr(), cb.data_ptr(), n_cams, Dn, h, w, X, Y, Z, float(W_img), float(H_img),
-                float(self.d_bound[0]), float(self.d_bound[1]), 1 if self.agg_voxel_mode == "mean" else 0,
+                float(self.d_bound[0]), float(self.d_bound[1]), mean_mode,
                 ob.data_ptr(), perm, st), "frustum_sample", keep=(prob, cams, prior)))
         self.__dict__["_prob"] = prob.view(B, V, Dn, h, w)
         return prior
 
     def stage_inputs(self, batch, dev):
+        if self.infer_mode:
+            g = self.__dict__["_grids"]
+            B, n_cams = g.shape[:2]
+            grids = batch["grids"]
+            for v in range(n_cams):
+                g[:, v].copy_(grids[v].to(torch.float32).reshape(B, -1, 3), non_blocking=True)
+            self.__dict__["_sps"].copy_(batch["scaled_pixel_size"].to(torch.float32).reshape(-1, 1), non_blocking=True)
+            return
         cams, sps, _ = self.camera_tables(batch["cam_k"], batch["T_velo_2_cam"], batch["ida_mats"],
                                           batch.get("vox_origin"), self.__dict__["_n_cams"])
         self.__dict__["_cams"].copy_(cams, non_blocking=True)
@@ -224,6 +241,8 @@ class FlospDepth(B200Module):
         key = (tuple(img_feat.shape), str(img_feat.device), vox_origin is not None, self.precision, self.param_stamp())
         ent = self._plans().get(key)
         batch = {"cam_k": cam_k, "T_velo_2_cam": T_velo_2_cam, "ida_mats": ida_mats}
+        if self.infer_mode:
+            batch = {"grids": grids, "scaled_pixel_size": scaled_pixel_size}
         if vox_origin is not None:
             batch["vox_origin"] = vox_origin
         if ent is None:

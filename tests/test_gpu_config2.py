@@ -53,3 +53,72 @@ def test_config2_logits_vs_oracle(case, precision):
     t = TOL[precision]
     assert rep["ssc_logit"]["rel"] <= t["rel"] and rep["occ_logit"]["rel"] <= t["rel"], rep
     assert agree >= t["argmax"], rep
+
+
+# ---- the config-2 "extended variant" (SURVEY 8d): trans_2d_to_3d = "flosp_depth" as in
+# multicam_flospdepth_crp_stereodepth_cascadecls_a100.yaml with final_dim = (376, 1370): DepthNet over both views' 1/8
+# maps (47 x 172), 104 depth bins, frustum sampling to the 128 x 128 x 16 grid, prior x lift x 100 ----
+TOL_FD = {"tf32": dict(rel=3e-3, argmax=0.997), "bf16": dict(rel=2.5e-2, argmax=0.97)}
+
+
+@pytest.fixture(scope="module")
+def case_flosp_depth():
+    import contextlib
+    import copy
+    import io
+    import bench
+    import synthetic as synth
+    from oracle import functional as OF
+    from occdepth_b200.models.OccDepth import OccDepth
+    import occdepth_b200.models.flosp_depth.flosp_depth as fd
+    H, W = bench.IMG_H, bench.IMG_W
+    saved = copy.deepcopy(fd.flosp_depth_conf_map["kitti"])
+    try:
+        fd.flosp_depth_conf_map["kitti"].update(final_dim=(H, W))
+        cfg = synth.occdepth_cfg(full_scene_size=bench.FULL, project_scale=2, feature=64, feature_2d_oc=64, n_classes=20,
+                                 backbone_2d_name="tf_efficientnet_b7_ns", cascade_cls=True, context_prior=True,
+                                 trans_2d_to_3d="flosp_depth", use_stereo_depth_gt=True)
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = OccDepth(["c"] * 20, torch.ones(20), full_scene_size=bench.FULL, project_res=bench.PROJECT_RES,
+                         config=cfg)
+        conf = copy.deepcopy(m.flosp_depth_conf)
+    finally:
+        fd.flosp_depth_conf_map["kitti"].clear()
+        fd.flosp_depth_conf_map["kitti"].update(saved)
+    synth.randomize_bn_(m)
+    m = m.eval()
+    img, pix, fov = bench.make_inputs(seed=0)
+    K, Ts = synth.kitti_calib(W, H)
+    batch = {"img": img, "projected_pix_2": [pix], "fov_mask_2": [fov],
+             "cam_k": [torch.from_numpy(K).unsqueeze(0).repeat(2, 1, 1)],
+             "T_velo_2_cam": [torch.stack([torch.from_numpy(t) for t in Ts])],
+             "ida_mats": [torch.eye(4).unsqueeze(0).repeat(2, 1, 1)]}
+    ocfg = dict(cfg)
+    ocfg.update(project_res=bench.PROJECT_RES, flosp_depth_conf=conf, with_depth_gt=True)
+    with torch.no_grad():
+        want = OF.occdepth_forward({k: v.clone() for k, v in m.state_dict().items()}, batch, ocfg)
+    b2 = dict(batch)
+    b2["img"] = img.cuda()
+    return m.cuda(), b2, want
+
+
+@pytest.mark.parametrize("precision", G.PRECISIONS)
+def test_config2_flosp_depth_vs_oracle(case_flosp_depth, precision):
+    m, batch, want = case_flosp_depth
+    with torch.no_grad():
+        got = m.set_precision(precision)(batch)
+    rep = {"precision": precision, "depth_pred_shape": list(got["depth_pred"].shape)}
+    assert tuple(got["depth_pred"].shape) == tuple(want["depth_pred"].shape) == (1, 2, 104, 47, 172)
+    for k in ("ssc_logit", "occ_logit", "depth_pred"):
+        g, w = got[k].float().cpu(), want[k]
+        rep[k] = {"max_abs_diff": float((g - w).abs().max()), "max_abs_ref": float(w.abs().max()),
+                  "rel": float((g - w).abs().max() / w.abs().max())}
+    agree = float((got["ssc_logit"].argmax(1).cpu() == want["ssc_logit"].argmax(1)).float().mean())
+    rep["argmax_agreement"] = agree
+    with open("gpurun_out/config2_flospdepth_parity_%s.json" % precision, "w") as f:
+        json.dump(rep, f)
+    print("config-2 (flosp_depth) parity:", rep)
+    t = TOL_FD[precision]
+    assert all(rep[k]["rel"] <= t["rel"] for k in ("ssc_logit", "occ_logit", "depth_pred")), rep
+    assert agree >= t["argmax"], rep

@@ -186,3 +186,66 @@ def test_occdepth_forward_nyu_virtual_view(precision):
     G.record("occdepth_forward_nyu_virtual_view", precision, **{k: _rel(got[k], want[k]) for k in want})
     for k in want:
         assert _rel(got[k], want[k]) <= TOL_E2E[precision], (k, _rel(got[k], want[k]))
+
+
+@PREC
+def test_occdepth_infer_mode_flosp_depth(precision):
+    """SURVEY 8f row 3, the reference's deployment route: OccDepth(infer_mode=True) disables the CRP and the
+    training-only outputs (OccDepth.py:82-84, unet3d_kitti.py:108-125) and FlospDepth consumes caller-supplied sampling
+    grids + scaled pixel sizes instead of camera matrices (OccDepth.py:310-317, flosp_depth.py:564-565).  The grids fed
+    here are what the reference's FrustumGridGenerator produces for the same cameras (oracle.frustum_grid), so the
+    result must equal the oracle's infer_mode forward."""
+    from occdepth_b200.models.OccDepth import OccDepth
+    import occdepth_b200.models.flosp_depth.flosp_depth as fd
+    import copy
+    torch.manual_seed(0)
+    full, ps = (32, 32, 16), 2
+    H, W = 40, 96
+    saved = copy.deepcopy(fd.flosp_depth_conf_map["kitti"])
+    try:
+        fd.flosp_depth_conf_map["kitti"].update(final_dim=(H, W), x_bound=[0, 6.4, 0.2], y_bound=[-3.2, 3.2, 0.2],
+                                                z_bound=[-2, 1.2, 0.2], d_bound=[1.0, 9.0, 0.5])
+        cfg = synth.occdepth_cfg(full_scene_size=full, project_scale=ps, feature=32, feature_2d_oc=32, n_classes=8,
+                                 backbone_2d_name="tf_efficientnet_b3_ns", trans_2d_to_3d="flosp_depth")
+        with ref_import.quiet():
+            m = OccDepth(["c"] * 8, torch.ones(8), full_scene_size=full, project_res=["1", "2", "4", "8"],
+                         config=cfg, infer_mode=True).eval()
+        conf = copy.deepcopy(m.flosp_depth_conf)
+    finally:
+        fd.flosp_depth_conf_map["kitti"].clear()
+        fd.flosp_depth_conf_map["kitti"].update(saved)
+    synth.seed_weights_(m, 9)
+    K, Ts = synth.kitti_calib(W, H, focal=60.0)
+    img = torch.randn(1, 2, 3, H, W)
+    N = 16 * 16 * 8
+    pix, fov = synth.random_indices(N, W, H, n_views=2, P=1, seed=5, margin=(10, 6))
+    cam_k = [torch.from_numpy(K).unsqueeze(0).repeat(2, 1, 1)]
+    T = [torch.stack([torch.from_numpy(t) for t in Ts])]
+    ida = [torch.eye(4).unsqueeze(0).repeat(2, 1, 1)]
+    batch = {"img": img, "projected_pix_2": [pix], "fov_mask_2": [fov], "cam_k": cam_k, "T_velo_2_cam": T,
+             "ida_mats": ida}
+    ocfg = dict(cfg)
+    ocfg.update(project_res=["1", "2", "4", "8"], flosp_depth_conf=conf, infer_mode=True)
+    # what a deployment precomputes on the host: per-camera sampling grids and the scaled pixel size
+    bounds = [conf["x_bound"], conf["y_bound"], conf["z_bound"]]
+    pc_min = torch.tensor([b[0] for b in bounds], dtype=torch.float32)
+    pc_max = torch.tensor([b[1] for b in bounds], dtype=torch.float32)
+    gs = [int((b[1] - b[0]) / b[2] / ps) for b in bounds]
+    nb = int((conf["d_bound"][1] - conf["d_bound"][0]) / conf["d_bound"][2])
+    grids, sps = [], []
+    for v in range(2):
+        K4 = torch.zeros(1, 4, 4)
+        K4[0, :3, :3] = cam_k[0][v].float()
+        K4[0, 3, 3] = 1
+        grids.append(OF.frustum_grid(gs, pc_min, pc_max, T[0][v:v + 1].float(), K4[:, :3, :], ida[0][v:v + 1], (H, W), nb,
+                                     conf["d_bound"][0], conf["d_bound"][1]))
+        inv = torch.inverse(K4[0])
+        sps.append(torch.norm(torch.stack([inv[0, 0], inv[1, 1]])) * 1000.0)
+    with torch.no_grad():
+        want = OF.occdepth_forward({k: v.clone() for k, v in m.state_dict().items()}, batch, ocfg)
+        b2 = {"img": img.cuda(), "projected_pix_2": [pix], "fov_mask_2": [fov], "grids": [g.cuda() for g in grids],
+              "scaled_pixel_size": torch.stack(sps).reshape(2, 1).cuda()}
+        got = m.cuda().set_precision(precision)(b2)
+    assert set(got.keys()) == set(want.keys()) == {"ssc_logit"}
+    G.record("occdepth_infer_mode_flosp_depth", precision, ssc_logit=_rel(got["ssc_logit"], want["ssc_logit"]))
+    assert _rel(got["ssc_logit"], want["ssc_logit"]) <= TOL_E2E[precision]
