@@ -830,6 +830,7 @@ static int fill_epi(const occd_conv_desc* d, ConvEpi* e) {
   e->res2_cstride = d->res2_cstride; e->res2_coff = d->res2_coff; e->res2_post = d->res2_post;
   e->out1_mode = d->out1_mode; e->out1 = d->out1;
   e->out1_cstride = d->out1_cstride; e->out1_coff = d->out1_coff; e->out1_C = d->out1_C;
+  { const char* v = getenv("OCCD_DEBUG_EPI"); e->dbg = v ? atoi(v) : 0; }
   return 0;
 }
 

@@ -22,6 +22,8 @@ struct ConvEpi {
   int out1_mode;
   void* out1;
   int out1_cstride, out1_coff, out1_C;
+  int dbg;   // experiment switch (OCCD_DEBUG_EPI, tools/conv_bench.py only): 1 = skip the out0 stores, 2 = skip the
+             // whole row epilogue (TMEM drain only)
 };
 
 __device__ __forceinline__ long long epi_pos(const ConvEpi& e, int b, int od, int oh, int ow) {
@@ -83,9 +85,17 @@ __device__ __forceinline__ void conv_epilogue_compute(const ConvEpi& e, long lon
 template <typename T, int NV>
 __device__ __forceinline__ void conv_epilogue_row(const ConvEpi& e, int b, int od, int oh, int ow, int n0,
                                                   float* v) {
+  if (e.dbg == 2) return;
   const long long pos = epi_pos(e, b, od, oh, ow);
   conv_epilogue_compute<T, NV>(e, pos, b, n0, v);
   if (!e.out0) return;
+  if (e.dbg == 1) {   // keep the arithmetic alive without storing
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += v[i];
+    if (s == 123456.789f) reinterpret_cast<T*>(e.out0)[0] = Elem<T>::cvt(s);
+    return;
+  }
 #pragma unroll
   for (int g = 0; g < NV; g += 8) {
     const int n = n0 + g;

@@ -322,6 +322,28 @@ sfa_lift_p1_kernel(const SfaKParams p) {
       if (V == 1) {
 #pragma unroll
         for (int i = 0; i < CPL; ++i) acc[i] += f[0][i];
+      } else if (V == 2) {
+        // one pair: accumulate straight into acc (no pair accumulator: 4 vectors per lane stay in registers)
+        float dot = 0.f, na = 0.f, nb = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          dot = fmaf(f[0][i], f[V - 1][i], dot);
+          na = fmaf(f[0][i], f[0][i], na);
+          nb = fmaf(f[V - 1][i], f[V - 1][i], nb);
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+          dot += __shfl_xor_sync(gmask, dot, o);
+          na += __shfl_xor_sync(gmask, na, o);
+          nb += __shfl_xor_sync(gmask, nb, o);
+        }
+        const float eps = 1e-8f;
+        const float cosv = dot / (fmaxf(sqrtf(na), eps) * fmaxf(sqrtf(nb), eps));
+        const float c = cosv * (m[0] * m[V - 1]);
+        const float wa = (c + ((m[0] > m[V - 1]) ? 1.f : 0.f)) * 0.5f;      // / (V (V-1)) with V == 2
+        const float wb = (c + ((m[V - 1] > m[0]) ? 1.f : 0.f)) * 0.5f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) acc[i] += wa * f[0][i] + wb * f[V - 1][i];
       } else {
         float pair_acc[CPL];
 #pragma unroll
@@ -412,9 +434,10 @@ static bool sfa_fits_int32(const SfaKParams& kp, int n_views) {
   return true;
 }
 
-// G lanes cooperate on one voxel, each holding NV 16-byte vectors of the C channels.  G is the smallest power of
-// two (>= 4) that keeps NV <= 2: fewer lanes per voxel = less redundant index / cosine-scalar work per voxel (the
-// kernel is issue bound), two vectors per lane = two independent 16-byte gathers in flight per lane.
+// G lanes cooperate on one voxel, each holding NV 16-byte vectors of the C channels.  Fewer lanes per voxel = less
+// redundant index / cosine-scalar work per voxel (the kernel is issue bound: ncu r02: SM throughput 62 %, DRAM 24 %,
+// L2 19 %), more vectors per lane = more independent 16-byte gathers in flight per lane.  Measured on B200 at config 2
+// (fp32, 16 vectors per voxel; profiles/r02_lift_variants.txt): 16 lanes x 1 vector 135 us, 8 x 2 94 us, 4 x 4 80 us.
 template <typename T, int V, int NV, int G>
 int launch_g(const SfaKParams& kp, cudaStream_t st) {
   constexpr int VPB = kThreads / G;
@@ -441,11 +464,20 @@ template <typename T, int V>
 int launch_nv(const SfaKParams& kp, cudaStream_t st) {
   constexpr int VEC = FeatTraits<T>::VEC;
   const int vecs = (kp.C + VEC - 1) / VEC;           // 16-byte vectors per voxel
+  // experiment hook (tools/lift_bench.py): OCCD_LIFT_NV=2 selects the round-1 split (two vectors per lane)
+  static const int nv2 = [] { const char* e = getenv("OCCD_LIFT_NV"); return e && atoi(e) == 2; }();
   if (vecs <= 4) return launch_g<T, V, 1, 4>(kp, st);
-  if (vecs <= 8) return launch_g<T, V, 2, 4>(kp, st);
-  if (vecs <= 16) return launch_g<T, V, 2, 8>(kp, st);
-  if (vecs <= 32) return launch_g<T, V, 2, 16>(kp, st);
-  if (vecs <= 64) return launch_g<T, V, 2, 32>(kp, st);
+  if (nv2) {
+    if (vecs <= 8) return launch_g<T, V, 2, 4>(kp, st);
+    if (vecs <= 16) return launch_g<T, V, 2, 8>(kp, st);
+    if (vecs <= 32) return launch_g<T, V, 2, 16>(kp, st);
+    if (vecs <= 64) return launch_g<T, V, 2, 32>(kp, st);
+  } else {
+    if (vecs <= 8) return launch_g<T, V, 4, 2>(kp, st);
+    if (vecs <= 16) return launch_g<T, V, 4, 4>(kp, st);
+    if (vecs <= 32) return launch_g<T, V, 4, 8>(kp, st);
+    if (vecs <= 64) return launch_g<T, V, 4, 16>(kp, st);
+  }
   occd_set_last_error("occd_sfa_lift_fwd: C too large (max 256 fp32 / 512 bf16 channels)");
   return OCCD_ERR_UNSUPPORTED;
 }

@@ -135,7 +135,13 @@ class OccDepth(_Base, B200Module):
             S = [x_hi - x_lo, S[1], S[2]]
         virtual = V == 1 and "gt_depth" in batch                          # process_rgbs, OccDepth.py:221-229
         VL = 2 if virtual else V                                           # views seen by the lift
-        img = plan.alloc(B * V, 1, H, W, 3)
+        # slab partition over an even number of ranks: the 2D network is sharded BY VIEW (its receptive field is
+        # global inside a view -- SE pooling -- but the two views are independent, process_rgbs OccDepth.py:208-219):
+        # ranks [0, R/2) run view 0, ranks [R/2, R) view 1, and one all-gather hands every rank both views' maps
+        view_shard = (slab is not None and V == 2 and not virtual and slab.world % 2 == 0
+                      and os.environ.get("OCCDEPTH_SLAB_VIEW_SHARD", "1") == "1")
+        view_sel = (slab.rank // (slab.world // 2)) if view_shard else None
+        img = plan.alloc(B * (1 if view_shard else V), 1, H, W, 3)
         Cf = self.feature_2d_oc
         assert Cf == self.feature, "feature_2d_oc must equal feature (the lift feeds the 3D net directly)"
         assert Cf % 8 == 0, "feature_2d_oc must be a multiple of 8"
@@ -149,7 +155,27 @@ class OccDepth(_Base, B200Module):
                 vb = torch.zeros(2, B, h_s, w_s, Cf, dtype=plan.dtype, device=dev)
                 views[s] = vb
                 outs["1_%d" % s] = CL(vb[0].unsqueeze(1), Cf)
+        gathered = None
+        if view_shard:
+            R2 = slab.world // 2
+            hw = [feature_hw(H, W, s) for s in scales]
+            offs, P_tot = [], 0
+            for (h_s, w_s) in hw:
+                offs.append(P_tot)
+                P_tot += h_s * w_s
+            slice_len = -(-P_tot // R2)
+            P_pad = slice_len * R2
+            packed = torch.zeros(P_pad, Cf, dtype=plan.dtype, device=dev)       # this rank's view, all scales
+            gathered = torch.zeros(2, P_pad, Cf, dtype=plan.dtype, device=dev)  # both views after the all-gather
+            for s, (h_s, w_s), o in zip(scales, hw, offs):
+                outs["1_%d" % s] = CL(packed[o:o + h_s * w_s].view(1, 1, h_s, w_s, Cf), Cf)
         x_rgb = self.net_rgb.emit(plan, img, outs)                          # {"1_s": CL [B*V,1,h,w,Cf]}
+        if view_shard:
+            sl = slab.rank % R2
+            plan.add(slab.all_gather_op(packed[sl * slice_len:(sl + 1) * slice_len],
+                                        gathered.view(2 * R2, slice_len, Cf)))
+            for s, (h_s, w_s), o in zip(scales, hw, offs):
+                views[s] = gathered[:, o:o + h_s * w_s].view(2, 1, h_s, w_s, Cf)   # [view][B=1][h][w][C]
         depth0 = None
         if virtual:
             L = _lib.lib()
@@ -172,8 +198,8 @@ class OccDepth(_Base, B200Module):
         for b in range(B):
             feats = []
             for s in scales:
-                if virtual:
-                    feats.append(views[s][:, b])                            # [2, h, w, Cf], view stride B*h*w*Cf
+                if virtual or view_shard:
+                    feats.append(views[s][:, b])                            # [2, h, w, Cf], strided views
                 else:
                     f = x_rgb["1_%d" % s]
                     assert f.coff == 0 and f.cstride == Cf
@@ -194,7 +220,7 @@ class OccDepth(_Base, B200Module):
             except Exception as e:  # noqa: BLE001 -- same kernels either way; only the launch mechanism differs
                 print("WARNING: CUDA graph capture failed (%r); launching kernels individually" % (e,))
                 plan.graph = None
-        return plan, img, pix, fov, out, depth0, n_lo
+        return plan, img, pix, fov, out, depth0, n_lo, view_sel
 
     def forward(self, batch):
         img = batch["img"]
@@ -225,8 +251,9 @@ class OccDepth(_Base, B200Module):
             with torch.no_grad():
                 ent = self._build(B, V, H, W, N, P, dev, batch)
             self._plans()[key] = ent
-        plan, img_cl, pix, fov, out, depth0, n_lo = ent
-        CL.from_planar(img.reshape(B * V, 3, H, W), out=img_cl)
+        plan, img_cl, pix, fov, out, depth0, n_lo, view_sel = ent
+        CL.from_planar(img.reshape(B * V, 3, H, W) if view_sel is None else img[:, view_sel].reshape(B, 3, H, W),
+                       out=img_cl)
         if depth0 is not None:
             depth0.copy_(batch["gt_depth"][0, 0], non_blocking=True)
         nl = pix.shape[2]

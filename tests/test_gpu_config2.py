@@ -58,7 +58,8 @@ def test_config2_logits_vs_oracle(case, precision):
 # ---- the config-2 "extended variant" (SURVEY 8d): trans_2d_to_3d = "flosp_depth" as in
 # multicam_flospdepth_crp_stereodepth_cascadecls_a100.yaml with final_dim = (376, 1370): DepthNet over both views' 1/8
 # maps (47 x 172), 104 depth bins, frustum sampling to the 128 x 128 x 16 grid, prior x lift x 100 ----
-TOL_FD = {"tf32": dict(rel=3e-3, argmax=0.997), "bf16": dict(rel=2.5e-2, argmax=0.97)}
+# measured on B200 (profiles/r02_config2_flospdepth_parity_*.json): tf32 rel <= 1.06e-3, arg-max 99.935 %; bf16 <= 8.7e-3, 99.12 %
+TOL_FD = {"tf32": dict(rel=2.1e-3, argmax=0.9987), "bf16": dict(rel=1.7e-2, argmax=0.9825)}
 
 
 @pytest.fixture(scope="module")

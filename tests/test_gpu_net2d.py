@@ -237,7 +237,7 @@ def test_occdepth_infer_mode_flosp_depth(precision):
         K4 = torch.zeros(1, 4, 4)
         K4[0, :3, :3] = cam_k[0][v].float()
         K4[0, 3, 3] = 1
-        grids.append(OF.frustum_grid(gs, pc_min, pc_max, T[0][v:v + 1].float(), K4[:, :3, :], ida[0][v:v + 1], (H, W), nb,
+        grids.append(OF.frustum_grid(gs, pc_min, pc_max, T[0][v].float(), K4[0], ida[0][v], (H, W), nb,
                                      conf["d_bound"][0], conf["d_bound"][1]))
         inv = torch.inverse(K4[0])
         sps.append(torch.norm(torch.stack([inv[0, 0], inv[1, 1]])) * 1000.0)

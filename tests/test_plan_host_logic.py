@@ -77,13 +77,46 @@ def test_occdepth_config2_plan(simt, monkeypatch):
     monkeypatch.setenv("OCCDEPTH_CUDA_GRAPH", "0")
     m = bench.build_model()
     N = 128 * 128 * 16
-    plan, img, pix, fov, out, depth0, n_lo = m._build(1, 2, bench.IMG_H, bench.IMG_W, N, 1, torch.device("cpu"), {})
+    plan, img, pix, fov, out, depth0, n_lo, view_sel = m._build(1, 2, bench.IMG_H, bench.IMG_W, N, 1,
+                                                                 torch.device("cpu"), {})
+    assert view_sel is None
     gmac = plan.flops / 2e9
     assert abs(gmac + 2 * 2.7 - (2 * 531.7 + 529.9 + 4.3)) / 1597.6 < 0.02, gmac
     assert sum(1 for op in plan.ops if getattr(op, "name", "") == "sfa_lift") == 1
     assert tuple(out["ssc_logit"].shape) == (1, 20, 256, 256, 32)
     assert img.dims == (2, 1, bench.IMG_H, bench.IMG_W) and tuple(pix.shape) == (1, 2, N, 1, 2)
     assert len(plan.ops) < 500      # both views batched, SE + projection batched over images
+
+
+def test_occdepth_config2_slab_plan_shards_2d_net_by_view(simt, monkeypatch):
+    """X-slab partition of one frame over 8 ranks (BASELINE configs[2]): the 2D net runs ONE view per rank (ranks 0-3
+    view 0, ranks 4-7 view 1) and one all-gather hands every rank both views' feature maps; the lift and the 3D net
+    work on this rank's 16 of 128 X-planes."""
+    import bench
+    from occdepth_b200.parallel import SimSlabGroup
+    monkeypatch.setenv("OCCDEPTH_CUDA_GRAPH", "0")
+    m = bench.build_model()
+    N = 128 * 128 * 16
+    full = m._build(1, 2, bench.IMG_H, bench.IMG_W, N, 1, torch.device("cpu"), {})[0]
+    grp = SimSlabGroup(8, halo=3)
+    ents = {}
+    for r in (1, 6):
+        m.__dict__["slab_ctx"] = grp.ctxs[r]
+        ents[r] = m._build(1, 2, bench.IMG_H, bench.IMG_W, N, 1, torch.device("cpu"), {})
+    m.__dict__.pop("slab_ctx")
+    assert ents[1][7] == 0 and ents[6][7] == 1                      # which view each rank's 2D net processes
+    for r, (plan, img, pix, fov, out, depth0, n_lo, view_sel) in ents.items():
+        assert img.dims == (1, 1, bench.IMG_H, bench.IMG_W)          # one view
+        assert tuple(pix.shape) == (1, 2, N // 8, 1, 2) and n_lo == r * (N // 8)
+        names = [getattr(op, "name", "") for op in plan.ops]
+        assert names.count("all_gather") == 2                       # 2D feature maps + CRP mega-context
+        assert names.index("all_gather") < names.index("sfa_lift")
+        # per-rank tensor-core work: half of the 2D net (one of two views) + an eighth of the 3D net
+        want = (531.7 - 2.7) + (529.9 + 4.3) / 8
+        assert abs(plan.flops / 2e9 - want) / want < 0.03, plan.flops / 2e9
+        assert tuple(out["ssc_logit"].shape) == (1, 20, 32, 256, 32)
+    assert len(ents[1][0].ops) == len(ents[6][0].ops)
+    assert full.flops > 2.5 * ents[1][0].flops
 
 
 def test_variant_eligibility_rules():

@@ -29,6 +29,8 @@ SHAPES = {
     "x_c64_n256": ((128, 128, 16), 64, 256, (3, 3, 3), 1, "relu"),
     "x_c16_n16": ((256, 256, 16), 16, 16, (3, 3, 3), 1, "relu"),
     "b1_expand": ((1, 94, 686), 48, 288, (1, 1, 1), 1, "silu"),      # both views side by side (B = 2 in the net)
+    "b1_expand_noact": ((1, 94, 686), 48, 288, (1, 1, 1), 1, "none"),
+    "b1_expand_relu": ((1, 94, 686), 48, 288, (1, 1, 1), 1, "relu"),
     "bneck5_16_64": ((128, 128, 16), 16, 64, (1, 1, 1), 1, "relu"),
     "up4_conv2": ((1, 94, 686), 320, 320, (1, 3, 3), 1, "leaky"),
     "l1_k1_64_16": ((128, 128, 16), 64, 16, (1, 1, 1), 1, "relu"),

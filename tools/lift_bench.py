@@ -11,7 +11,7 @@ import synthetic as synth  # noqa: E402
 from occdepth_b200.engine import CL  # noqa: E402
 from occdepth_b200.models.SFA import lift_multiscale  # noqa: E402
 
-H, W, C = 376, 1370, 64
+H, W, C = 376, 1370, int(os.environ.get("LIFT_C", "64"))
 FULL, PS = (256, 256, 32), 2
 dev = torch.device("cuda")
 PREC = os.environ.get("OCCDEPTH_PRECISION", "tf32")
