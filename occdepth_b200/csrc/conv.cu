@@ -238,6 +238,17 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
             v[i] += __shfl_up_sync(0xffffffffu, lo[i], 1) + __shfl_down_sync(0xffffffffu, hi[i], 1);
           if (valid) conv_epilogue_row<T, 16>(p.epi, b, od, oh, ow, c0, v);
         }
+      } else if (epi_fast_ok(p.epi)) {
+        // fast path (conv_common.cuh): bias / residual loads ahead of the accumulator, pointers formed once per tile
+        const EpiRow<T> er = epi_row<T>(p.epi, valid, b, od, oh, ow, n0);
+        uint32_t ra[16];
+        EpiPre q;
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+          tc::tmem_ld16_issue(taddr + (uint32_t)c0, ra);
+          epi_prefetch<T>(er, c0, q);                        // in flight together with the TMEM load of this chunk
+          tc::tmem_ld_wait16(ra);
+          epi_finish<T>(er, c0, ra, q);
+        }
       } else {
         // software-pipelined: the tcgen05.ld of this group's next 16 columns is in flight while these are stored
         uint32_t ra[16], rb[16];
@@ -468,10 +479,22 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
                            pw < p.hw + p.BW && od < p.D && oh < p.H && ow < p.W;
         const uint32_t taddr = tmem_base + set * (uint32_t)p.set_stride + (uint32_t)(m * p.N_tile) +
                                ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
-          float v[16];
-          tc::tmem_ld16(taddr + (uint32_t)c0, v);
-          if (valid) conv_epilogue_row<T, 16>(p.epi, b, od, oh, ow, c0, v);
+        if (epi_fast_ok(p.epi)) {
+          const EpiRow<T> er = epi_row<T>(p.epi, valid, b, od, oh, ow, 0);
+          uint32_t ra[16];
+          EpiPre pre;
+          for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
+            tc::tmem_ld16_issue(taddr + (uint32_t)c0, ra);
+            epi_prefetch<T>(er, c0, pre);
+            tc::tmem_ld_wait16(ra);
+            epi_finish<T>(er, c0, ra, pre);
+          }
+        } else {
+          for (int c0 = 0; c0 < p.N_tile; c0 += 16) {
+            float v[16];
+            tc::tmem_ld16(taddr + (uint32_t)c0, v);
+            if (valid) conv_epilogue_row<T, 16>(p.epi, b, od, oh, ow, c0, v);
+          }
         }
       }
       tc::fence_before_sync();

@@ -106,3 +106,110 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvEpi& e, int b, int o
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path of the per-tap and halo kernels' epilogue (out0 only: no second output, no post-activation residual).  Measured
+// on B200 (tools/conv_bench.py with OCCD_DEBUG_EPI, round 2): the row epilogue above is LATENCY bound -- 4 epilogue
+// warps per scheduler walk a serial chain tcgen05.ld -> wait -> bias loads -> (residual loads) -> math -> store per
+// 16 columns, at ~15 % of the SM's issue rate.  Here the chunk's bias (and residual) loads are issued BEFORE the wait
+// on its TMEM load, the output / residual row pointers are formed once per tile, and the activation switch runs once
+// per 16 values.
+template <typename T>
+struct EpiRow {
+  T* out;            // out0 row of this thread: channels [n0, ...) of its output position (nullptr: nothing to store)
+  const T* res;      // res1 row or nullptr
+  const float* bias; // bias + n0
+  int act, exact;
+  int n_store;       // channels of this row that exist from n0 on (Cout_store - n0)
+};
+
+struct EpiPre {      // operands of one 16-column chunk, loaded ahead of the accumulator
+  float4 b[4];
+  float r[16];
+};
+
+template <typename T>
+__device__ __forceinline__ void epi_prefetch(const EpiRow<T>& e, int c0, EpiPre& q) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q.b[i] = __ldg(reinterpret_cast<const float4*>(e.bias + c0) + i);
+  if (e.res) {
+    if (c0 < e.n_store) Elem<T>::ld8(e.res + c0, q.r);
+    if (c0 + 8 < e.n_store) Elem<T>::ld8(e.res + c0 + 8, q.r + 8);
+  }
+}
+
+__device__ __forceinline__ void apply_act16(float* v, int act) {
+  if (act == ACT_NONE) return;
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (act == ACT_LEAKY) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
+  } else if (act == ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
+  }
+}
+
+// v: accumulator values without bias; rr: this chunk's residual values (read only when e.res)
+template <typename T>
+__device__ __forceinline__ void epi_finish_v(const EpiRow<T>& e, int c0, float* v, const float4* qb, const float* rr) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[4 * i] += qb[i].x;
+    v[4 * i + 1] += qb[i].y;
+    v[4 * i + 2] += qb[i].z;
+    v[4 * i + 3] += qb[i].w;
+  }
+  if (e.res) {
+    if (c0 < e.n_store) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += rr[i];
+    }
+    if (c0 + 8 < e.n_store) {
+#pragma unroll
+      for (int i = 8; i < 16; ++i) v[i] += rr[i];
+    }
+  }
+  apply_act16(v, e.act);
+  if (e.out) {
+    if (c0 < e.n_store) {
+      if (e.exact) Elem<T>::st8_exact(e.out + c0, v);
+      else Elem<T>::st8(e.out + c0, v);
+    }
+    if (c0 + 8 < e.n_store) {
+      if (e.exact) Elem<T>::st8_exact(e.out + c0 + 8, v + 8);
+      else Elem<T>::st8(e.out + c0 + 8, v + 8);
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void epi_finish(const EpiRow<T>& e, int c0, const uint32_t* acc, const EpiPre& q) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+  epi_finish_v<T>(e, c0, v, q.b, q.r);
+}
+
+__device__ __forceinline__ bool epi_fast_ok(const ConvEpi& e) {
+  return e.out1_mode == OCCD_OUT1_NONE && e.res2 == nullptr && e.out0 != nullptr && e.dbg <= 1;
+}
+
+// row pointers of output position (b, od, oh, ow), channels from n0 on (valid == false: nothing is read or stored)
+template <typename T>
+__device__ __forceinline__ EpiRow<T> epi_row(const ConvEpi& e, bool valid, int b, int od, int oh, int ow, int n0) {
+  EpiRow<T> er;
+  const long long pos = valid ? epi_pos(e, b, od, oh, ow) : 0;
+  er.out = (valid && e.dbg == 0) ? reinterpret_cast<T*>(e.out0) + pos * e.out0_cstride + e.out0_coff + n0 : nullptr;
+  er.res = (valid && e.res1) ? reinterpret_cast<const T*>(e.res1) + pos * e.res1_cstride + e.res1_coff + n0 : nullptr;
+  er.bias = e.bias + n0;
+  er.act = e.act;
+  er.exact = e.out0_exact;
+  er.n_store = e.Cout_store - n0;
+  return er;
+}
