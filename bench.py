@@ -598,6 +598,15 @@ def run_slab_block(m, dev, world, rank, args, barrier):
         ctx = parallel.SlabContext(halo=3)
         m.enable_slab_parallel(ctx)
         try:
+            # every rank builds its slab plan first (no collective runs while building) and the ranks agree on the
+            # outcome: a rank that cannot build must not leave its neighbours waiting in a halo exchange
+            err = None
+            try:
+                m.prepare(batch)
+            except Exception as ex:  # noqa: BLE001
+                err = repr(ex)
+            if parallel.max_over_ranks(0.0 if err is None else 1.0, dev) > 0:
+                raise RuntimeError(err or "another rank could not build its slab plan")
             for _ in range(3):
                 part = m(batch)
             ms_s, part = time_forwards(m, batch, args.steps, barrier, dev)

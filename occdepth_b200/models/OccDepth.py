@@ -244,6 +244,17 @@ class OccDepth(_Base, B200Module):
         with torch.cuda.device(dev):           # launches, tensor maps and function attributes follow the tensors
             return self._forward_on(batch, key, img, pp, fm, B, V, H, W, N, P, dev)
 
+    def prepare(self, batch):
+        """build and cache the launch plan (weight snapshot, buffers, tensor maps, CUDA graph) for this batch's
+        shapes without running it: the first forward() then costs what every later one does.  No collective is
+        executed, so a multi-rank caller can agree on success before any rank starts a halo exchange."""
+        self.__dict__["_build_only"] = True
+        try:
+            self.forward(batch)
+        finally:
+            self.__dict__.pop("_build_only", None)
+        return self
+
     def _forward_on(self, batch, key, img, pp, fm, B, V, H, W, N, P, dev):
         ent = self._plans().get(key)
         if ent is None:
@@ -251,6 +262,8 @@ class OccDepth(_Base, B200Module):
             with torch.no_grad():
                 ent = self._build(B, V, H, W, N, P, dev, batch)
             self._plans()[key] = ent
+        if self.__dict__.get("_build_only"):
+            return None
         plan, img_cl, pix, fov, out, depth0, n_lo, view_sel = ent
         CL.from_planar(img.reshape(B * V, 3, H, W) if view_sel is None else img[:, view_sel].reshape(B, 3, H, W),
                        out=img_cl)
