@@ -25,11 +25,29 @@ constexpr int kThreads = 256;
 constexpr int kIters = 4;  // voxel batches per block
 
 template <typename T> struct FeatTraits;
+// predicated 16-byte read-only load: zeros when !ok, no branch (the gather loop is issue bound; a divergent branch
+// per load costs a BSSY/BSYNC pair and splits the warp's loads)
+__device__ __forceinline__ uint4 ldg16_pred(const void* p, bool ok) {
+  uint4 v;
+  asm("{\n"
+      " .reg .pred q;\n"
+      " setp.ne.s32 q, %5, 0;\n"
+      " mov.b32 %0, 0;\n mov.b32 %1, 0;\n mov.b32 %2, 0;\n mov.b32 %3, 0;\n"
+      " @q ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+      "}"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+      : "l"(p), "r"((int)ok));
+  return v;
+}
 template <> struct FeatTraits<float> {
   static constexpr int VEC = 4;   // elements per 16-byte vector
   static __device__ __forceinline__ void load(const float* p, float* f) {
     float4 v = __ldg(reinterpret_cast<const float4*>(p));
     f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  static __device__ __forceinline__ void load_pred(const float* p, bool ok, float* f) {
+    const uint4 v = ldg16_pred(p, ok);
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
   }
 };
 template <> struct FeatTraits<__nv_bfloat16> {
@@ -38,6 +56,9 @@ template <> struct FeatTraits<__nv_bfloat16> {
     uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
     unpack8(v, f);
   }
+  static __device__ __forceinline__ void load_pred(const __nv_bfloat16* p, bool ok, float* f) {
+    unpack8(ldg16_pred(p, ok), f);
+  }
 };
 
 struct SfaKParams {
@@ -45,6 +66,7 @@ struct SfaKParams {
   int h[OCCD_SFA_MAX_SCALES], w[OCCD_SFA_MAX_SCALES];
   int div[OCCD_SFA_MAX_SCALES], shift[OCCD_SFA_MAX_SCALES];
   long long vstride[OCCD_SFA_MAX_SCALES];  // elements between views
+  int vrow[OCCD_SFA_MAX_SCALES];           // the same in rows of C elements (P == 1 fast path: fits 32 bits)
   int n_scales, C, P;
   long long N;
   const long long* pix;
@@ -93,7 +115,6 @@ sfa_lift_kernel(const SfaKParams p) {
 
   const int lane_g = threadIdx.x % G;
   const int grp = threadIdx.x / G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
 
 #pragma unroll 1
   for (int it = 0; it < kIters; ++it) {
@@ -168,9 +189,9 @@ sfa_lift_kernel(const SfaKParams p) {
             }
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) {
-              dot += __shfl_xor_sync(gmask, dot, o);
-              na += __shfl_xor_sync(gmask, na, o);
-              nb += __shfl_xor_sync(gmask, nb, o);
+              dot += __shfl_xor_sync(0xffffffffu, dot, o);
+              na += __shfl_xor_sync(0xffffffffu, na, o);
+              nb += __shfl_xor_sync(0xffffffffu, nb, o);
             }
             const float eps = 1e-8f;
             const float cosv = dot / (fmaxf(sqrtf(na), eps) * fmaxf(sqrtf(nb), eps));
@@ -236,68 +257,137 @@ sfa_lift_kernel(const SfaKParams p) {
   }
 }
 
+// one scale's contribution: acc += sum over view pairs of the cosine-weighted features (SFA.py:65-92 semantics)
+template <int V, int CPL, int G>
+__device__ __forceinline__ void sfa_reduce_views(const float (&f)[V][CPL], const float (&m)[V], float (&acc)[CPL]) {
+  if (V == 1) {
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) acc[i] += f[0][i];
+  } else if (V == 2) {
+    // one pair: accumulate straight into acc (no pair accumulator: 4 vectors per lane stay in registers)
+    float dot = 0.f, na = 0.f, nb = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      dot = fmaf(f[0][i], f[V - 1][i], dot);
+      na = fmaf(f[0][i], f[0][i], na);
+      nb = fmaf(f[V - 1][i], f[V - 1][i], nb);
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      na += __shfl_xor_sync(0xffffffffu, na, o);
+      nb += __shfl_xor_sync(0xffffffffu, nb, o);
+    }
+    // dot / (max(|a|, eps) max(|b|, eps)) with eps = 1e-8: max(sqrt(x), eps) == sqrt(max(x, eps^2))
+    const float cosv = dot * rsqrtf(fmaxf(na, 1e-16f)) * rsqrtf(fmaxf(nb, 1e-16f));
+    const float c = cosv * (m[0] * m[V - 1]);
+    const float wa = (c + ((m[0] > m[V - 1]) ? 1.f : 0.f)) * 0.5f;      // / (V (V-1)) with V == 2
+    const float wb = (c + ((m[V - 1] > m[0]) ? 1.f : 0.f)) * 0.5f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) acc[i] += wa * f[0][i] + wb * f[V - 1][i];
+  } else {
+    float pair_acc[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) pair_acc[i] = 0.f;
+#pragma unroll
+    for (int a = 0; a < V; ++a) {
+#pragma unroll
+      for (int b = a + 1; b < V; ++b) {
+        float dot = 0.f, na = 0.f, nb = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          dot = fmaf(f[a][i], f[b][i], dot);
+          na = fmaf(f[a][i], f[a][i], na);
+          nb = fmaf(f[b][i], f[b][i], nb);
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+          dot += __shfl_xor_sync(0xffffffffu, dot, o);
+          na += __shfl_xor_sync(0xffffffffu, na, o);
+          nb += __shfl_xor_sync(0xffffffffu, nb, o);
+        }
+        const float eps = 1e-8f;
+        const float cosv = dot / (fmaxf(sqrtf(na), eps) * fmaxf(sqrtf(nb), eps));
+        const float c = cosv * (m[a] * m[b]);
+        const float wa = c + ((m[a] > m[b]) ? 1.f : 0.f);
+        const float wb = c + ((m[b] > m[a]) ? 1.f : 0.f);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) pair_acc[i] += wa * f[a][i] + wb * f[b][i];
+      }
+    }
+    const float inv = 1.f / (float)(V * (V - 1));
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) acc[i] += pair_acc[i] * inv;
+  }
+}
+
 // Fast path for P == 1 (pattern_id 0, every shipped config): one (x,y,fov) record per (view, voxel).
-// All V x n_scales gathers of a voxel are issued before the first use (memory-level parallelism), index math is
-// 32-bit (h*w < 2^31), the records are read once per view instead of once per scale.
-template <typename T, int V, int NV, int G>
-__global__ void __launch_bounds__(kThreads)   // (kThreads, 4) forces 64 registers + spills: measured slower
+// Index math is 32-bit (h*w < 2^31) and done once per (view, voxel) by one thread (staged in shared memory); the gather
+// loop issues a scale's V x NV predicated 16-byte loads per lane back to back, then reduces them.
+template <typename T, int V, int NV, int G, int KI>
+__global__ void __launch_bounds__(kThreads)   // (kThreads, 4) forces 64 registers + spills: measured slower (r02)
 sfa_lift_p1_kernel(const SfaKParams p) {
   constexpr int VEC = FeatTraits<T>::VEC;
   constexpr int VPB = kThreads / G;
   constexpr int CPL = NV * VEC;
   constexpr int NS = OCCD_SFA_MAX_SCALES;
-  __shared__ longlong2 s_pix[V][VPB * kIters];
-  __shared__ unsigned char s_fov[V][VPB * kIters];
+  // row index of the gathered pixel at every scale (or -1), worked out ONCE per (view, voxel) by one thread; the
+  // gather loop below only reads them back (the kernel is issue bound: with every lane of a voxel's group redoing
+  // this arithmetic it executed ~250 warp instructions per voxel, ncu r02)
+  __shared__ int4 s_off[V][VPB * KI];
+  __shared__ unsigned char s_in[V][VPB * KI];
+  static_assert(OCCD_SFA_MAX_SCALES == 4, "offsets are staged as one int4 per (view, voxel)");
   pdl_wait();
-  const long long block_n0 = (long long)blockIdx.x * (VPB * kIters);
-  const int n_block = (int)min((long long)(VPB * kIters), p.N - block_n0);
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    const longlong2* gp = reinterpret_cast<const longlong2*>(p.pix) + (long long)v * p.N + block_n0;
-    const unsigned char* gf = p.fov + (long long)v * p.N + block_n0;
-    for (int i = threadIdx.x; i < n_block; i += kThreads) {
-      s_pix[v][i] = gp[i];
-      s_fov[v][i] = gf[i];
+  const long long block_n0 = (long long)blockIdx.x * (VPB * KI);
+  const int n_block = (int)min((long long)(VPB * KI), p.N - block_n0);
+  const int ns = p.n_scales;
+  for (int i = threadIdx.x; i < V * n_block; i += kThreads) {
+    const int v = i / n_block, ln = i - v * n_block;
+    longlong2 xy = __ldg(reinterpret_cast<const longlong2*>(p.pix) + (long long)v * p.N + block_n0 + ln);
+    const bool in = p.fov[(long long)v * p.N + block_n0 + ln] != 0;
+    // 32-bit fast math is valid for |x|,|y| < 2^30; anything else cannot address a feature map anyway
+    if (xy.x < -(1LL << 30) || xy.x > (1LL << 30) || xy.y < -(1LL << 30) || xy.y > (1LL << 30)) {
+      xy.x = -1; xy.y = 0;  // flat index negative -> treated as the zero column, mask stays as given
     }
+    const int x = (int)xy.x, y = (int)xy.y;
+    int o4[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      int o = -1;
+      if (in && s < ns) {
+        int xs, ys;
+        if (p.shift[s] >= 0) { xs = x >> p.shift[s]; ys = y >> p.shift[s]; }
+        else { xs = (int)floordiv64(x, p.div[s], -1); ys = (int)floordiv64(y, p.div[s], -1); }
+        const long long idx = (long long)ys * p.w[s] + xs;
+        const int hw = p.h[s] * p.w[s];
+        if (idx >= 0 && idx < hw) o = v * p.vrow[s] + (int)idx;
+      }
+      o4[s] = o;
+    }
+    s_off[v][ln] = make_int4(o4[0], o4[1], o4[2], o4[3]);
+    s_in[v][ln] = in ? 1 : 0;
   }
   __syncthreads();
   const int lane_g = threadIdx.x % G;
   const int grp = threadIdx.x / G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
-  const int ns = p.n_scales;
 
 #pragma unroll 1
-  for (int it = 0; it < kIters; ++it) {
+  for (int it = 0; it < KI; ++it) {
     const int ln = it * VPB + grp;
     const bool active = ln < n_block;
     float m[V];
     int off[V][NS];  // element offset of the gathered pixel's channel vector, or -1
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      bool in = active && s_fov[v][active ? ln : 0];
-      longlong2 xy = s_pix[v][active ? ln : 0];
-      // 32-bit fast math is valid for |x|,|y| < 2^30; anything else cannot address a feature map anyway
-      if (xy.x < -(1LL << 30) || xy.x > (1LL << 30) || xy.y < -(1LL << 30) || xy.y > (1LL << 30)) {
-        xy.x = -1; xy.y = 0;  // flat index negative -> treated as the zero column, mask stays as given
-      }
-      const int x = (int)xy.x, y = (int)xy.y;
-      m[v] = in ? 1.f : 0.f;
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        int o = -1;
-        if (in && s < ns) {
-          int xs, ys;
-          if (p.shift[s] >= 0) { xs = x >> p.shift[s]; ys = y >> p.shift[s]; }
-          else { xs = (int)floordiv64(x, p.div[s], -1); ys = (int)floordiv64(y, p.div[s], -1); }
-          const long long idx = (long long)ys * p.w[s] + xs;
-          const int hw = p.h[s] * p.w[s];
-          if (idx >= 0 && idx < hw) o = (int)((long long)v * p.vstride[s] / p.C) + (int)idx;
-        }
-        off[v][s] = o;
-      }
+      const int4 o = active ? s_off[v][ln] : make_int4(-1, -1, -1, -1);
+      off[v][0] = o.x; off[v][1] = o.y; off[v][2] = o.z; off[v][3] = o.w;
+      m[v] = (active && s_in[v][ln]) ? 1.f : 0.f;
     }
-    // per scale: both views' gathers are issued back to back, then reduced (keeping all V x scales loads in
-    // flight costs 93 registers and measured slower than the extra occupancy this 60-register form gets)
+    // per scale: the V x NV gathers of a lane are issued back to back, then reduced.  Two or four scales per phase
+    // (more loads in flight per lane, fewer dependent phases) measured the same or slower on B200, as did 1 / 2 / 4
+    // batches per block and a 64-register cap: every variant sits at ~63 us for config 2 in fp32 (53 us in bf16 with
+    // half the bytes), DRAM traffic equals the algorithmic bytes (ncu r02b) -- the floor is the scattered 256-byte
+    // row fetches themselves (profiles/r02_lift_variants.txt)
     float acc[CPL];
 #pragma unroll
     for (int i = 0; i < CPL; ++i) acc[i] = 0.f;
@@ -308,76 +398,13 @@ sfa_lift_p1_kernel(const SfaKParams p) {
       float f[V][CPL];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
+        const bool ok = off[v][s] >= 0;
+        const T* row = feat + (long long)(ok ? off[v][s] : 0) * p.C + lane_g * VEC;
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          const int c0 = (j * G + lane_g) * VEC;
-          if (off[v][s] >= 0 && c0 < p.C) {
-            FeatTraits<T>::load(feat + (long long)off[v][s] * p.C + c0, &f[v][j * VEC]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) f[v][j * VEC + e] = 0.f;
-          }
-        }
+        for (int j = 0; j < NV; ++j)
+          FeatTraits<T>::load_pred(row + j * G * VEC, ok && (j * G + lane_g) * VEC < p.C, &f[v][j * VEC]);
       }
-      if (V == 1) {
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) acc[i] += f[0][i];
-      } else if (V == 2) {
-        // one pair: accumulate straight into acc (no pair accumulator: 4 vectors per lane stay in registers)
-        float dot = 0.f, na = 0.f, nb = 0.f;
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) {
-          dot = fmaf(f[0][i], f[V - 1][i], dot);
-          na = fmaf(f[0][i], f[0][i], na);
-          nb = fmaf(f[V - 1][i], f[V - 1][i], nb);
-        }
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-          dot += __shfl_xor_sync(gmask, dot, o);
-          na += __shfl_xor_sync(gmask, na, o);
-          nb += __shfl_xor_sync(gmask, nb, o);
-        }
-        const float eps = 1e-8f;
-        const float cosv = dot / (fmaxf(sqrtf(na), eps) * fmaxf(sqrtf(nb), eps));
-        const float c = cosv * (m[0] * m[V - 1]);
-        const float wa = (c + ((m[0] > m[V - 1]) ? 1.f : 0.f)) * 0.5f;      // / (V (V-1)) with V == 2
-        const float wb = (c + ((m[V - 1] > m[0]) ? 1.f : 0.f)) * 0.5f;
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) acc[i] += wa * f[0][i] + wb * f[V - 1][i];
-      } else {
-        float pair_acc[CPL];
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) pair_acc[i] = 0.f;
-#pragma unroll
-        for (int a = 0; a < V; ++a) {
-#pragma unroll
-          for (int b = a + 1; b < V; ++b) {
-            float dot = 0.f, na = 0.f, nb = 0.f;
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-              dot = fmaf(f[a][i], f[b][i], dot);
-              na = fmaf(f[a][i], f[a][i], na);
-              nb = fmaf(f[b][i], f[b][i], nb);
-            }
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) {
-              dot += __shfl_xor_sync(gmask, dot, o);
-              na += __shfl_xor_sync(gmask, na, o);
-              nb += __shfl_xor_sync(gmask, nb, o);
-            }
-            const float eps = 1e-8f;
-            const float cosv = dot / (fmaxf(sqrtf(na), eps) * fmaxf(sqrtf(nb), eps));
-            const float c = cosv * (m[a] * m[b]);
-            const float wa = c + ((m[a] > m[b]) ? 1.f : 0.f);
-            const float wb = c + ((m[b] > m[a]) ? 1.f : 0.f);
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) pair_acc[i] += wa * f[a][i] + wb * f[b][i];
-          }
-        }
-        const float inv = 1.f / (float)(V * (V - 1));
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) acc[i] += pair_acc[i] * inv;
-      }
+      sfa_reduce_views<V, CPL, G>(f, m, acc);
     }
     if (!active) continue;
     const long long n = block_n0 + ln;
@@ -444,7 +471,10 @@ int launch_g(const SfaKParams& kp, cudaStream_t st) {
   const long long per_block = (long long)VPB * kIters;
   const long long blocks = (kp.N + per_block - 1) / per_block;
   if (kp.P == 1 && sfa_fits_int32(kp, V)) {
-    OCCD_LAUNCH_CHECKED(sfa_lift_p1_kernel<T, V, NV, G>, dim3((unsigned)blocks), dim3(kThreads), 0, st, kp);
+    // two voxel batches per block (1 / 2 / 4 measured within 3 % of each other, profiles/r02_lift_variants.txt)
+    constexpr int KI = 2;
+    const unsigned nb = (unsigned)((kp.N + VPB * KI - 1) / (VPB * KI));
+    OCCD_LAUNCH_CHECKED((sfa_lift_p1_kernel<T, V, NV, G, KI>), dim3(nb), dim3(kThreads), 0, st, kp);
     return OCCD_OK;
   } else {
     const size_t smem = (size_t)V * VPB * kIters * kp.P * (sizeof(longlong2) + 1);
@@ -464,8 +494,10 @@ template <typename T, int V>
 int launch_nv(const SfaKParams& kp, cudaStream_t st) {
   constexpr int VEC = FeatTraits<T>::VEC;
   const int vecs = (kp.C + VEC - 1) / VEC;           // 16-byte vectors per voxel
-  // experiment hook (tools/lift_bench.py): OCCD_LIFT_NV=2 selects the round-1 split (two vectors per lane)
-  static const int nv2 = [] { const char* e = getenv("OCCD_LIFT_NV"); return e && atoi(e) == 2; }();
+  // vectors per lane: 4 for fp32 (16 channels), 2 for bf16 (16 channels: four 8-element vectors cost 64 registers of
+  // gathered values per scale).  OCCD_LIFT_NV=2 / 4 overrides (experiment hook, tools/lift_bench.py)
+  static const int nv_env = [] { const char* e = getenv("OCCD_LIFT_NV"); return e ? atoi(e) : 0; }();
+  const bool nv2 = nv_env == 2 || (nv_env != 4 && VEC == 8);
   if (vecs <= 4) return launch_g<T, V, 1, 4>(kp, st);
   if (nv2) {
     if (vecs <= 8) return launch_g<T, V, 2, 4>(kp, st);
@@ -510,13 +542,14 @@ extern "C" int occd_sfa_lift_fwd(const occd_sfa_params* a, void* stream) {
   if (a->N == 0) return OCCD_OK;
   SfaKParams kp;
   for (int s = 0; s < OCCD_SFA_MAX_SCALES; ++s) {
-    kp.feat[s] = nullptr; kp.h[s] = kp.w[s] = 0; kp.div[s] = 1; kp.shift[s] = 0; kp.vstride[s] = 0;
+    kp.feat[s] = nullptr; kp.h[s] = kp.w[s] = 0; kp.div[s] = 1; kp.shift[s] = 0; kp.vstride[s] = 0; kp.vrow[s] = 0;
   }
   for (int s = 0; s < a->n_scales; ++s) {
     OCCD_CHECK_ARG(a->feat[s] != nullptr && a->h[s] > 0 && a->w[s] > 0 && a->div[s] != 0, "occd_sfa_lift_fwd: scale spec");
     kp.feat[s] = a->feat[s]; kp.h[s] = a->h[s]; kp.w[s] = a->w[s]; kp.div[s] = a->div[s];
     kp.vstride[s] = a->vstride[s] ? a->vstride[s] : (long long)a->h[s] * a->w[s] * a->C;
     OCCD_CHECK_ARG(kp.vstride[s] % a->C == 0, "occd_sfa_lift_fwd: view stride must be a multiple of C");
+    kp.vrow[s] = (int)(kp.vstride[s] / a->C < (1LL << 31) ? kp.vstride[s] / a->C : 0);   // used only when sfa_fits_int32
     int sh = -1;
     for (int b = 0; b < 30; ++b) if (a->div[s] == (1 << b)) sh = b;
     kp.shift[s] = sh;
