@@ -1230,7 +1230,7 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
   // B200 constants drive the model (profiles/r02_mma_issue_bench.txt, r02_conv_role_traces.txt, r02_membw.txt):
   //   one tcgen05.mma costs max(59, N/2) cycles for M = 128, any operand type
   //   an SM pulls ~44 bytes/cycle from L2 when the whole chip does (6300 B/cycle chip-wide)
-  //   the epilogue's scattered channels-last stores drain at ~5 bytes/cycle/SM
+  //   the epilogue drains ~7-12 bytes/cycle/SM (fast path; 12 measured best for the whole forward, r02c)
   // A tile's main loop (TMA + MMA) overlaps the previous tile's epilogue, so a CTA's time is
   // waves * max(mainloop, epilogue) + min(mainloop, epilogue).  Small-M layers (late encoder stages: 9 M tiles) get
   // narrow N tiles that spread the write-bound epilogue over every SM; large-M layers get the widest tile (fewest
@@ -1243,6 +1243,9 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
     const int n_sms = n_sms_current();
     const double out_bytes_per_col = 128.0 * ((d->out0 ? pl->esize : 0) + (d->out1_mode == OCCD_OUT1_CL ? pl->esize : 0) +
                                               (d->out1_mode == OCCD_OUT1_F32_PLANAR ? 4 : 0));
+    // experiment hook (tools/conv_bench.py, bench.py): OCCD_EPI_RATE overrides the model's epilogue drain rate
+    static const double epi_rate = [] { const char* e = getenv("OCCD_EPI_RATE"); const double v = e ? atof(e) : 0.0;
+                                        return v > 0.0 ? v : 12.0; }();
     double best = -1.0;
     t.N_tile = 16;
     for (int n = 16; n <= 256 && n <= d->Cout_pad; n += 16) {
@@ -1250,7 +1253,7 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
       const double mma = (RB / 32) * (n > 118 ? n / 2.0 : 59.0);
       const double load = (128.0 + n) * RB / 44.0;
       const double mainloop = iters * (mma > load ? mma : load);
-      const double epi = out_bytes_per_col * n / 5.0;
+      const double epi = out_bytes_per_col * n / epi_rate;
       const long long tiles = m_tiles0 * (d->Cout_pad / n);
       const double waves = (double)((tiles + n_sms - 1) / n_sms);
       const double span = waves * (mainloop > epi ? mainloop : epi) + (mainloop > epi ? epi : mainloop);
