@@ -330,61 +330,30 @@ def run_b200(args):
     barrier()
     ms_e2e = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
 
-    # ---- end-to-end, pipelined: the same per-step copies inside the timed region, but on copy streams with
-    # double-buffered, PRE-ALLOCATED device and pinned host buffers (what a serving loop does): the H2D of step i+1
-    # and the D2H read of step i-1 run while the forward of step i computes.  Nothing is allocated inside the loop
-    # (a caching-allocator block shared across streams would serialise the streams again).  No collective inside
-    # the try block: a rank that fails reports inf and every rank falls back to the sequential number above.
+    # ---- end-to-end, pipelined: the same per-step copies inside the timed region, through the package's serving
+    # helper (occdepth_b200.serving.FramePipeline): two copy streams, double-buffered PRE-ALLOCATED device and pinned
+    # host buffers, so the H2D of step i+1 and the D2H read of step i-1 run while the forward of step i computes.
+    # No collective inside the try block: a rank that fails reports inf and every rank falls back to the sequential
+    # number above.
     ms_pipe_local = float("inf")
     pipe_err = None
     if not slab_only:
         try:
-            hs, cs = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-            main = torch.cuda.current_stream(dev)
-            host_bufs = [logits_h, torch.empty(logits_h.shape, dtype=torch.float32).pin_memory()]
-            dev_out = [torch.empty_like(out["ssc_logit"]) for _ in range(2)]
-            dev_in = [{"img": torch.empty_like(batch_dev["img"]), "pix": torch.empty_like(batch_dev["projected_pix_2"][0]),
-                       "fov": torch.empty_like(batch_dev["fov_mask_2"][0])} for _ in range(2)]
-            ev = lambda: torch.cuda.Event()  # noqa: E731
-            in_ready, in_free, out_ready, out_free = ([ev(), ev()] for _ in range(4))
-            for j in range(2):
-                in_free[j].record(main)
-                out_free[j].record(main)
-
-            def pipe_step(i):
-                j = i & 1
-                with torch.cuda.stream(hs):                     # H2D of this step's inputs
-                    hs.wait_event(in_free[j])
-                    dev_in[j]["img"].copy_(img_h, non_blocking=True)
-                    dev_in[j]["pix"].copy_(pix_h, non_blocking=True)
-                    dev_in[j]["fov"].copy_(fov_h, non_blocking=True)
-                    in_ready[j].record(hs)
-                main.wait_event(in_ready[j])
-                res = m({"img": dev_in[j]["img"], "projected_pix_2": [dev_in[j]["pix"]],
-                         "fov_mask_2": [dev_in[j]["fov"]]})["ssc_logit"]
-                in_free[j].record(main)
-                main.wait_event(out_free[j])
-                dev_out[j].copy_(res)                           # the result leaves the allocator-owned tensor
-                out_ready[j].record(main)
-                with torch.cuda.stream(cs):                     # D2H read of this step's logits
-                    cs.wait_event(out_ready[j])
-                    host_bufs[j].copy_(dev_out[j], non_blocking=True)
-                    out_free[j].record(cs)
-
-            with torch.no_grad():
-                for i in range(4):
-                    pipe_step(i)
-                main.wait_stream(cs)
-                torch.cuda.synchronize()
-                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                p0.record()
-                for i in range(args.steps):
-                    pipe_step(i)
-                main.wait_stream(cs)          # the last D2H read ends inside the timed region
-                p1.record()
-                torch.cuda.synchronize()
+            from occdepth_b200.serving import FramePipeline
+            pipe = FramePipeline(m, img_h.shape, pix_h.shape, fov_h.shape, device=dev)
+            for _ in range(4):
+                pipe.submit(img_h, pix_h, fov_h)
+            pipe.join()
+            torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(args.steps):
+                pipe.submit(img_h, pix_h, fov_h)
+            pipe.join()                       # the last D2H read ends inside the timed region
+            p1.record()
+            torch.cuda.synchronize()
             ms_pipe_local = p0.elapsed_time(p1)
-            if not torch.equal(host_bufs[(args.steps - 1) & 1], out["ssc_logit"].cpu()):
+            if not torch.equal(pipe.result(pipe.flush()), out["ssc_logit"].cpu()):
                 raise RuntimeError("pipelined e2e: the logits read back differ from the device-resident forward's")
         except Exception as ex:  # noqa: BLE001
             pipe_err = repr(ex)
@@ -551,9 +520,9 @@ def run_b200(args):
             "e2e": {"value": frames * N_OUT * args.steps / (ms_e2e_best * 1e-3), "unit": "voxels/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_best / args.steps,
                     "mode": ("pipelined: every step copies its inputs H2D from pinned host memory and reads its "
-                             "logits back D2H inside the timed region; the copies run on two copy streams with "
-                             "double-buffered pre-allocated buffers, so the H2D of step i+1 and the D2H of step i-1 "
-                             "overlap the forward of step i"
+                             "logits back D2H inside the timed region, through occdepth_b200.serving.FramePipeline: "
+                             "two copy streams, double-buffered pre-allocated buffers, so the H2D of step i+1 and the "
+                             "D2H of step i-1 overlap the forward of step i"
                              if pipelined and ms_pipe <= ms_e2e else "sequential: H2D, forward, D2H back to back"),
                     "sequential_ms_per_step": ms_e2e / args.steps,
                     "pipelined_ms_per_step": ms_pipe / args.steps if pipelined else None,

@@ -74,3 +74,41 @@ def test_generate_output_loop_body():
     with torch.no_grad():
         pred3 = model(batch)
     assert float((pred3["ssc_logit"].argmax(1) == 5).float().mean()) == 1.0
+
+
+def test_frame_pipeline_matches_forward():
+    """occdepth_b200.serving.FramePipeline (copy streams + double buffers around forward): every frame's read-back
+    equals what a plain forward returns for that frame"""
+    from occdepth_b200.models.OccDepth import OccDepth
+    from occdepth_b200.serving import FramePipeline
+    torch.manual_seed(0)
+    full, ps, ncls = (32, 32, 16), 2, 20
+    cfg = synth.occdepth_cfg(dataset="kitti", full_scene_size=full, project_scale=ps, feature=32, feature_2d_oc=32,
+                             n_classes=ncls, cascade_cls=True, backbone_2d_name="tf_efficientnet_b3_ns")
+    with ref_import.quiet():
+        model = OccDepth(["c"] * ncls, torch.ones(ncls), full_scene_size=full, project_res=["1", "2", "4", "8"],
+                         config=cfg)
+        synth.randomize_bn_(model)
+    model.cuda().eval()
+    H, W = 33, 49
+    N = (full[0] // ps) * (full[1] // ps) * (full[2] // ps)
+    frames = []
+    for i in range(5):
+        g = torch.Generator().manual_seed(i)
+        pix, fov = synth.random_indices(N, W, H, n_views=2, P=1, seed=5 + i, margin=(10, 6))
+        frames.append((torch.randn(1, 2, 3, H, W, generator=g).pin_memory(), pix.pin_memory(), fov.pin_memory()))
+    with torch.no_grad():
+        want = [model({"img": f[0].cuda(), "projected_pix_2": [f[1]], "fov_mask_2": [f[2]]})["ssc_logit"].cpu()
+                for f in frames]
+    pipe = FramePipeline(model, frames[0][0].shape, frames[0][1].shape, frames[0][2].shape)
+    got = {}
+    for f in frames:
+        t = pipe.submit(*f)
+        if t is not None:
+            got[t] = pipe.result(t).clone()
+    got[pipe.flush()] = pipe.result(pipe.flush()).clone()
+    assert sorted(got) == list(range(5))
+    for i in range(5):
+        assert torch.equal(got[i], want[i]), i
+    with pytest.raises(ValueError):
+        pipe.result(0)

@@ -64,3 +64,13 @@ def test_install_then_reference_imports():
 def test_install_without_reference_tree():
     r = _run(WITHOUT_REFERENCE % {"root": ROOT})
     assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+def test_frame_pipeline_refuses_without_cuda():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    from occdepth_b200.serving import FramePipeline
+    with pytest.raises(RuntimeError, match="CUDA"):
+        FramePipeline(None, (1, 2, 3, 8, 8), (2, 8, 1, 2), (2, 8, 1))
