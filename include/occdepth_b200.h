@@ -94,6 +94,7 @@ int occd_cl_to_planar(const void* in, int in_dtype, float* out, long long B, int
 /* accumulator) and concat-free skip connections are all tap lists.                                */
 #define OCCD_CONV_MAX_TAPS 81
 #define OCCD_CONV_MAX_SRC 3
+#define OCCD_CONV_MAX_GROUPS 8
 #define OCCD_ACT_NONE 0
 #define OCCD_ACT_RELU 1
 #define OCCD_ACT_LEAKY 2 /* slope 0.01 */
@@ -166,6 +167,14 @@ typedef struct {
   void* out1;
   int out1_cstride, out1_coff; /* channels-last mode                                               */
   int out1_C;                  /* planar mode: channels of the planar tensor, written at coff+n    */
+  /* tap groups (OCCD_CONV_IMPL_TC only; 0 or 1 = off): n_groups convolutions over the same sources, iteration    */
+  /* space, weights tensor and bias in ONE launch.  Group g uses taps [group_tap0[g], group_tap0[g+1]) and writes   */
+  /* o_full = o*omul + group_oadd[g] (`oadd` is ignored): the 8 sub-pixel phases of ConvTranspose3d(k3, s2, p1,     */
+  /* op1) (modules.py:278-296).  Order the groups by descending tap count.  Needs out1_mode == NONE and at most     */
+  /* one residual (res1, or res2 with res2_post).                                                                  */
+  int n_groups;
+  int group_tap0[OCCD_CONV_MAX_GROUPS + 1];
+  int group_oadd[OCCD_CONV_MAX_GROUPS][3];
 } occd_conv_desc;
 
 typedef struct occd_conv_plan occd_conv_plan;

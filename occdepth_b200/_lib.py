@@ -42,7 +42,7 @@ class SfaParams(C.Structure):
     ]
 
 
-CONV_MAX_TAPS, CONV_MAX_SRC = 81, 3
+CONV_MAX_TAPS, CONV_MAX_SRC, CONV_MAX_GROUPS = 81, 3, 8
 CONV_IMPL_TC, CONV_IMPL_SIMT, CONV_IMPL_HALO, CONV_IMPL_HALOX, CONV_IMPL_TCX = 0, 1, 2, 3, 4
 OUT1_NONE, OUT1_CL, OUT1_F32_PLANAR = 0, 1, 2
 
@@ -85,6 +85,9 @@ class ConvDesc(C.Structure):
         ("out1", C.c_void_p),
         ("out1_cstride", C.c_int), ("out1_coff", C.c_int),
         ("out1_C", C.c_int),
+        ("n_groups", C.c_int),
+        ("group_tap0", C.c_int * (CONV_MAX_GROUPS + 1)),
+        ("group_oadd", (C.c_int * 3) * CONV_MAX_GROUPS),
     ]
 
 

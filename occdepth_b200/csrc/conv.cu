@@ -39,6 +39,13 @@ struct TcParams {
   long long* trace;  // optional [tile][8] clock64 stamps of CTA 0 (occd_conv_debug_trace, tools/conv_trace.py)
   signed char tap_src[OCCD_CONV_MAX_TAPS];
   short tap_dz[OCCD_CONV_MAX_TAPS], tap_dy[OCCD_CONV_MAX_TAPS], tap_dx[OCCD_CONV_MAX_TAPS];
+  // tap groups: n_groups convolutions over the same sources and iteration space in one launch (the sub-pixel phases
+  // of a stride-2 transposed conv).  Tiles are ordered group-major, so every CTA of the persistent grid takes the
+  // same share of each group (the groups differ in tap count).  n_groups == 1: the whole tap list, epi.oadd.
+  int n_groups;
+  short grp_tap0[OCCD_CONV_MAX_GROUPS + 1];
+  short grp_iters[OCCD_CONV_MAX_GROUPS];
+  signed char grp_oadd[OCCD_CONV_MAX_GROUPS][3];
 };
 
 // XP: x-packed variant: the pipeline items are (source, dz, dy) groups whose B operand stacks the three W taps
@@ -75,10 +82,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles_n = XP ? 1 : p.Cout_pad / p.N_tile;
-  const int num_tiles = p.num_m_tiles * n_tiles_n;
-
-  int iters_per_tile = 0;
-  for (int i = 0; i < p.n_taps; ++i) iters_per_tile += p.n_kchunks[p.tap_src[i]];
+  const int tiles_per_group = p.num_m_tiles * n_tiles_n;
+  const int num_tiles = tiles_per_group * p.n_groups;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA0);
@@ -117,8 +122,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % n_tiles_n;
-        int t = tile / n_tiles_n;
+        const int grp = tile / tiles_per_group;
+        const int tg = tile - grp * tiles_per_group;
+        const int nt = tg % n_tiles_n;
+        int t = tg / n_tiles_n;
         const int tw = t % p.tiles_w; t /= p.tiles_w;
         const int th = t % p.tiles_h; t /= p.tiles_h;
         const int td = t % p.tiles_d; t /= p.tiles_d;
@@ -128,10 +135,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         const int n0 = nt * p.N_tile;
         // items (tap, k-chunk) are loaded in groups of p.group per pipeline stage: one barrier hand-off per group
         int g = 0;
-        int remaining = iters_per_tile;
+        int remaining = p.grp_iters[grp];
         const int jt = (tile - blockIdx.x) / gridDim.x;
         if (p.trace && blockIdx.x == 0 && jt < 64) p.trace[jt * 8 + 0] = clock64();
-        for (int tp = 0; tp < p.n_taps; ++tp) {
+        for (int tp = p.grp_tap0[grp]; tp < p.grp_tap0[grp + 1]; ++tp) {
           const int src = p.tap_src[tp];
           const int cw = iw0 + p.tap_dx[tp], ch = ih0 + p.tap_dy[tp], cd = id0 + p.tap_dz[tp];
           const int wrow = b * p.w_batch_rows + (XP ? tp * p.N_tile : tp * p.Cout_pad + n0);
@@ -171,6 +178,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         tc::fence_after_sync();
         if (p.trace && blockIdx.x == 0 && j < 64) p.trace[j * 8 + 2] = clock64();
         const uint32_t d_tmem = tmem_base + acc * acc_stride;
+        const int iters_per_tile = p.grp_iters[tile / tiles_per_group];
         for (int it = 0; it < iters_per_tile;) {
           tc::mbar_wait(full_bar + 8u * s, ph);
           tc::fence_after_sync();
@@ -211,8 +219,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
     int j = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
       if ((j & 1) != grp) continue;
-      const int nt = tile % n_tiles_n;
-      int t = tile / n_tiles_n;
+      const int tgrp = tile / tiles_per_group;       // tap group (sub-pixel phase) of this tile
+      const int tg = tile - tgrp * tiles_per_group;
+      const int nt = tg % n_tiles_n;
+      int t = tg / n_tiles_n;
       const int tw = t % p.tiles_w; t /= p.tiles_w;
       const int th = t % p.tiles_h; t /= p.tiles_h;
       const int td = t % p.tiles_d; t /= p.tiles_d;
@@ -240,7 +250,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUten
         }
       } else if (epi_fast_ok(p.epi)) {
         // fast path (conv_common.cuh): bias / residual loads ahead of the accumulator, pointers formed once per tile
-        const EpiRow<T> er = epi_row<T>(p.epi, valid, b, od, oh, ow, n0);
+        const EpiRow<T> er = p.n_groups > 1 ? epi_row<T>(p.epi, valid, b, od, oh, ow, n0, p.grp_oadd[tgrp][0],
+                                                         p.grp_oadd[tgrp][1], p.grp_oadd[tgrp][2])
+                                            : epi_row<T>(p.epi, valid, b, od, oh, ow, n0);
         uint32_t ra[16];
         EpiPre q;
         for (int c0 = c_begin; c0 < c_end; c0 += 16) {
@@ -1174,10 +1186,31 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
     return OCCD_ERR_ARG;
   }
   t.n_taps = xp ? d->n_taps / 3 : d->n_taps;  // x-packed: one pipeline item per (source, dz, dy) group
+  const int n_groups = d->n_groups > 1 ? d->n_groups : 1;
+  if (n_groups > 1) {
+    bool ok = !xp && n_groups <= OCCD_CONV_MAX_GROUPS && d->group_tap0[0] == 0 && d->group_tap0[n_groups] == d->n_taps &&
+              d->out1_mode == OCCD_OUT1_NONE && d->out0 != nullptr &&
+              (d->res2 == nullptr || (d->res2_post && d->res1 == nullptr));
+    for (int g = 0; ok && g < n_groups; ++g) {
+      ok = d->group_tap0[g + 1] > d->group_tap0[g];
+      for (int i = 0; i < 3; ++i) ok = ok && d->group_oadd[g][i] >= 0 && d->group_oadd[g][i] < d->omul[i];
+    }
+    if (!ok) {
+      occd_set_last_error("occd_conv_plan_create: tap groups need the per-tap TC kernel, ascending non-empty tap "
+                          "ranges covering all taps, 0 <= group_oadd < omul, no second output and at most one residual");
+      return OCCD_ERR_UNSUPPORTED;
+    }
+  }
+  t.n_groups = n_groups;
   t.src_d0 = d->src_d0;
   t.w_batch_rows = d->weight_per_image ? d->n_taps * d->Cout_pad : 0;
   for (int s = 0; s < OCCD_CONV_MAX_SRC; ++s) t.n_kchunks[s] = s < d->n_src ? (d->src_C[s] + KC - 1) / KC : 0;
   for (int i = 0; i < 3; ++i) t.stride[i] = d->stride[i];
+  for (int g = 0; g < n_groups; ++g) {
+    t.grp_tap0[g] = (short)(n_groups > 1 ? d->group_tap0[g] : 0);
+    t.grp_tap0[g + 1] = (short)(n_groups > 1 ? d->group_tap0[g + 1] : t.n_taps);
+    for (int i = 0; i < 3; ++i) t.grp_oadd[g][i] = (signed char)(n_groups > 1 ? d->group_oadd[g][i] : 0);
+  }
   if (xp) {
     // groups of three W taps -1, 0, +1 share one MMA with N = 3 * Cout_pad; the tile is 32 positions wide (30
     // outputs + one halo column each side) so that lane == column in the epilogue
@@ -1239,7 +1272,8 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
   {
     int iters = 0;
     for (int i = 0; i < t.n_taps; ++i) iters += t.n_kchunks[t.tap_src[i]];
-    const long long m_tiles0 = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w;
+    iters = (iters + n_groups - 1) / n_groups;   // tap groups: the mean group; every CTA gets its share of each
+    const long long m_tiles0 = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w * n_groups;
     const int n_sms = n_sms_current();
     const double out_bytes_per_col = 128.0 * ((d->out0 ? pl->esize : 0) + (d->out1_mode == OCCD_OUT1_CL ? pl->esize : 0) +
                                               (d->out1_mode == OCCD_OUT1_F32_PLANAR ? 4 : 0));
@@ -1273,8 +1307,13 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
   t.b_bytes = t.N_tile * RB;
   t.b_stride = round_up(t.b_bytes, 1024);
   const int stage_bytes = t.a_bytes + t.b_stride;
-  int total_iters = 0;
-  for (int i = 0; i < t.n_taps; ++i) total_iters += t.n_kchunks[t.tap_src[i]];
+  int total_iters = 0;   // (tap, k-chunk) items of one tile; with tap groups: of the largest group
+  for (int g = 0; g < n_groups; ++g) {
+    int it = 0;
+    for (int i = t.grp_tap0[g]; i < t.grp_tap0[g + 1]; ++i) it += t.n_kchunks[t.tap_src[i]];
+    t.grp_iters[g] = (short)it;
+    if (it > total_iters) total_iters = it;
+  }
   const int budget = 200 * 1024;  // persistent kernel: one CTA per SM owns the shared memory
   // (tap, k-chunk) items per pipeline stage: the single-thread producer/MMA hand-off costs ~0.25 us, so a stage
   // must carry >= ~512 tensor-pipe cycles of work (or up to 9 items) while leaving >= 3 stages in flight
@@ -1298,7 +1337,7 @@ static int tc_geometry(const occd_conv_desc* d, occd_conv_plan* pl, bool xp) {
   t.stages = stages;
   pl->smem = (size_t)stages * group * stage_bytes + 16 * kMaxStages + 64 + 1024;  // + barriers + alignment slack
   const long long m_tiles = (long long)d->B * t.tiles_d * t.tiles_h * t.tiles_w;
-  const long long all_tiles = m_tiles * (xp ? 1 : d->Cout_pad / t.N_tile);
+  const long long all_tiles = m_tiles * (xp ? 1 : d->Cout_pad / t.N_tile) * n_groups;
   if (all_tiles > 2147483647LL) {
     occd_set_last_error("occd_conv_plan_create: too many tiles");
     return OCCD_ERR_UNSUPPORTED;
@@ -1404,6 +1443,7 @@ extern "C" int occd_conv_plan_create(const occd_conv_desc* d, occd_conv_plan** o
   }
   OCCD_CHECK_ARG(d->impl == OCCD_CONV_IMPL_TC || d->impl == OCCD_CONV_IMPL_SIMT || d->impl == OCCD_CONV_IMPL_HALO ||
                  d->impl == OCCD_CONV_IMPL_TCX || d->impl == OCCD_CONV_IMPL_HALOX, "occd_conv_plan_create: impl");
+  OCCD_CHECK_ARG(d->n_groups <= 1 || d->impl == OCCD_CONV_IMPL_TC, "occd_conv_plan_create: tap groups: TC impl only");
   OCCD_CHECK_ARG(!d->weight_per_image || (d->impl != OCCD_CONV_IMPL_HALO && d->impl != OCCD_CONV_IMPL_HALOX),
                  "occd_conv_plan_create: per-image weights: TC or SIMT impl");
 

@@ -26,10 +26,14 @@ struct ConvEpi {
              // whole row epilogue (TMEM drain only)
 };
 
+__device__ __forceinline__ long long epi_pos(const ConvEpi& e, int b, int od, int oh, int ow, int oa0, int oa1,
+                                             int oa2) {
+  return (((long long)b * e.ODf + ((long long)od * e.omul[0] + oa0)) * e.OHf +
+          ((long long)oh * e.omul[1] + oa1)) * e.OWf +
+         ((long long)ow * e.omul[2] + oa2);
+}
 __device__ __forceinline__ long long epi_pos(const ConvEpi& e, int b, int od, int oh, int ow) {
-  return (((long long)b * e.ODf + ((long long)od * e.omul[0] + e.oadd[0])) * e.OHf +
-          ((long long)oh * e.omul[1] + e.oadd[1])) * e.OWf +
-         ((long long)ow * e.omul[2] + e.oadd[2]);
+  return epi_pos(e, b, od, oh, ow, e.oadd[0], e.oadd[1], e.oadd[2]);
 }
 
 // Epilogue arithmetic for one output position `pos` and NV consecutive channels [n0, n0+NV) held in v[] (fp32
@@ -117,7 +121,8 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvEpi& e, int b, int o
 template <typename T>
 struct EpiRow {
   T* out;            // out0 row of this thread: channels [n0, ...) of its output position (nullptr: nothing to store)
-  const T* res;      // res1 row or nullptr
+  const T* res;      // residual row (res1, or a post-activation res2) or nullptr
+  int res_post;      // 1: the residual is added after the activation (Upsample + skip)
   const float* bias; // bias + n0
   int act, exact;
   int n_store;       // channels of this row that exist from n0 on (Cout_store - n0)
@@ -165,7 +170,7 @@ __device__ __forceinline__ void epi_finish_v(const EpiRow<T>& e, int c0, float* 
     v[4 * i + 2] += qb[i].z;
     v[4 * i + 3] += qb[i].w;
   }
-  if (e.res) {
+  if (e.res && !e.res_post) {
     if (c0 < e.n_store) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] += rr[i];
@@ -176,6 +181,16 @@ __device__ __forceinline__ void epi_finish_v(const EpiRow<T>& e, int c0, float* 
     }
   }
   apply_act16(v, e.act);
+  if (e.res && e.res_post) {
+    if (c0 < e.n_store) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += rr[i];
+    }
+    if (c0 + 8 < e.n_store) {
+#pragma unroll
+      for (int i = 8; i < 16; ++i) v[i] += rr[i];
+    }
+  }
   if (e.out) {
     if (c0 < e.n_store) {
       if (e.exact) Elem<T>::st8_exact(e.out + c0, v);
@@ -196,20 +211,35 @@ __device__ __forceinline__ void epi_finish(const EpiRow<T>& e, int c0, const uin
   epi_finish_v<T>(e, c0, v, q.b, q.r);
 }
 
+// out0 only, and at most one residual: res1 (before the activation) or a post-activation res2
 __device__ __forceinline__ bool epi_fast_ok(const ConvEpi& e) {
-  return e.out1_mode == OCCD_OUT1_NONE && e.res2 == nullptr && e.out0 != nullptr && e.dbg <= 1;
+  return e.out1_mode == OCCD_OUT1_NONE && e.out0 != nullptr && e.dbg <= 1 &&
+         (e.res2 == nullptr || (e.res2_post && e.res1 == nullptr));
 }
 
-// row pointers of output position (b, od, oh, ow), channels from n0 on (valid == false: nothing is read or stored)
+// row pointers of output position (b, od, oh, ow) + (oa0, oa1, oa2), channels from n0 on (valid == false: nothing is
+// read or stored)
 template <typename T>
-__device__ __forceinline__ EpiRow<T> epi_row(const ConvEpi& e, bool valid, int b, int od, int oh, int ow, int n0) {
+__device__ __forceinline__ EpiRow<T> epi_row(const ConvEpi& e, bool valid, int b, int od, int oh, int ow, int n0,
+                                             int oa0, int oa1, int oa2) {
   EpiRow<T> er;
-  const long long pos = valid ? epi_pos(e, b, od, oh, ow) : 0;
+  const long long pos = valid ? epi_pos(e, b, od, oh, ow, oa0, oa1, oa2) : 0;
   er.out = (valid && e.dbg == 0) ? reinterpret_cast<T*>(e.out0) + pos * e.out0_cstride + e.out0_coff + n0 : nullptr;
-  er.res = (valid && e.res1) ? reinterpret_cast<const T*>(e.res1) + pos * e.res1_cstride + e.res1_coff + n0 : nullptr;
+  er.res = nullptr;
+  er.res_post = 0;
+  if (valid && e.res1) {
+    er.res = reinterpret_cast<const T*>(e.res1) + pos * e.res1_cstride + e.res1_coff + n0;
+  } else if (valid && e.res2) {
+    er.res = reinterpret_cast<const T*>(e.res2) + pos * e.res2_cstride + e.res2_coff + n0;
+    er.res_post = 1;
+  }
   er.bias = e.bias + n0;
   er.act = e.act;
   er.exact = e.out0_exact;
   er.n_store = e.Cout_store - n0;
   return er;
+}
+template <typename T>
+__device__ __forceinline__ EpiRow<T> epi_row(const ConvEpi& e, bool valid, int b, int od, int oh, int ow, int n0) {
+  return epi_row<T>(e, valid, b, od, oh, ow, n0, e.oadd[0], e.oadd[1], e.oadd[2]);
 }

@@ -238,10 +238,12 @@ class ConvOp:
     def __init__(self, srcs, taps, tap_weights, bias, out_dims, out0=None, act="none", res1=None, res2=None,
                  stride=(1, 1, 1), omul=(1, 1, 1), oadd=(0, 0, 0), full_dims=None, out1=None, out1_mode="none",
                  out1_coff=0, impl=None, name="", res2_post=False, weight_buf=None, weight_per_image=False,
-                 out0_exact=False):
+                 out0_exact=False, groups=None):
         """srcs: list[CL] (same B,D,H,W);  taps: [(src_idx, dz, dy, dx)];  tap_weights: list of fp32 [Cout, C_src]
         bias: fp32 [Cout];  out0/res1/res2: CL on the full output grid;  out1: CL (pre-activation bf16 copy) or
-        fp32 planar tensor [B, C1, D, H, W] (mode "planar", written at channel out1_coff)."""
+        fp32 planar tensor [B, C1, D, H, W] (mode "planar", written at channel out1_coff).
+        groups: [(n_taps_of_group, (oadd_d, oadd_h, oadd_w))] -- several convolutions over the same sources in one
+        launch, each with its own slice of `taps` and output offset (occd_conv_desc.n_groups; per-tap TC kernel)."""
         self.name = name
         dev = srcs[0].buf.device
         B, ID, IH, IW = srcs[0].dims
@@ -275,6 +277,8 @@ class ConvOp:
         if impl is None:
             impl = default_impl()
         auto = impl is None
+        if groups:
+            auto, impl = False, _lib.CONV_IMPL_TC
         if auto:
             impl = (_lib.CONV_IMPL_HALO if halo_eligible(srcs, taps, stride, omul, out_dims, Cout_pad, weight_buf)
                     else _lib.CONV_IMPL_TC)
@@ -297,6 +301,15 @@ class ConvOp:
         d.n_taps = len(taps)
         for i, (si, dz, dy, dx) in enumerate(taps):
             d.taps[i].src, d.taps[i].dz, d.taps[i].dy, d.taps[i].dx = si, dz, dy, dx
+        if groups:
+            assert sum(g[0] for g in groups) == len(taps) and len(groups) <= _lib.CONV_MAX_GROUPS
+            d.n_groups, t0 = len(groups), 0
+            for gi, (cnt, off) in enumerate(groups):
+                d.group_tap0[gi] = t0
+                t0 += cnt
+                for i in range(3):
+                    d.group_oadd[gi][i] = off[i]
+            d.group_tap0[len(groups)] = t0
         d.weight, d.bias = self.weight.data_ptr(), self.bias.data_ptr()
         d.Cout, d.Cout_pad, d.Kpad = Cout, Cout_pad, Kpad
         d.weight_per_image = 1 if weight_per_image else 0
@@ -478,6 +491,7 @@ class Plan:
             out = self.alloc(B, 2 * ID, 2 * IH, 2 * IW, co)
         sel = {0: [(1, 0)], 1: [(2, 0), (0, 1)]}  # parity -> [(kernel index, input offset)]
         self.need_halo(x, [(0, 1, 0, 0)], 1, ID)
+        phases = []
         for pd in (0, 1):
             for ph in (0, 1):
                 for pw in (0, 1):
@@ -487,10 +501,24 @@ class Plan:
                             for (kc, oc) in sel[pw]:
                                 taps.append((0, oa, ob, oc))
                                 ws.append(weight[:, :, ka, kb, kc].t())
-                    self.add(ConvOp([x], taps, ws, bias, (ID, IH, IW), out0=out, act=act, omul=(2, 2, 2),
-                                    res2=res_post, res2_post=True,
-                                    oadd=(pd, ph, pw), full_dims=(2 * ID, 2 * IH, 2 * IW),
-                                    name="%s.p%d%d%d" % (name, pd, ph, pw), impl=impl))
+                    phases.append(((pd, ph, pw), taps, ws))
+        if impl is None:
+            impl = default_impl()
+        grouped = impl in (None, _lib.CONV_IMPL_TC) and os.environ.get("OCCDEPTH_CONVT_GROUPED", "1") == "1"
+        if grouped:
+            # ONE launch: the 8 phases as tap groups of the per-tap kernel, largest group first (the persistent grid
+            # walks the tiles group-major, so every CTA gets the same share of each phase)
+            phases.sort(key=lambda p: -len(p[1]))
+            self.add(ConvOp([x], [t for p in phases for t in p[1]], [w for p in phases for w in p[2]], bias,
+                            (ID, IH, IW), out0=out, act=act, omul=(2, 2, 2), res2=res_post, res2_post=True,
+                            full_dims=(2 * ID, 2 * IH, 2 * IW), name=name,
+                            groups=[(len(p[1]), p[0]) for p in phases]))
+            return out
+        for (pd, ph, pw), taps, ws in phases:
+            self.add(ConvOp([x], taps, ws, bias, (ID, IH, IW), out0=out, act=act, omul=(2, 2, 2),
+                            res2=res_post, res2_post=True,
+                            oadd=(pd, ph, pw), full_dims=(2 * ID, 2 * IH, 2 * IW),
+                            name="%s.p%d%d%d" % (name, pd, ph, pw), impl=impl))
         return out
 
     def run(self, stream=None):

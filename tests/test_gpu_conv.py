@@ -30,6 +30,35 @@ def test_conv_transpose_and_multi(impl, precision):
 
 
 @PREC
+def test_conv_transpose_grouped_launch(precision, monkeypatch):
+    """the 8 sub-pixel phases as tap groups of ONE launch (default) == the 8 separate launches, bit for bit; the
+    level shapes of the 3-D decoder (odd extents, Cout 32 / 64)"""
+    import torch
+    from occdepth_b200.engine import CL, Plan
+    dev = torch.device("cuda")
+    for (ci, co, dims) in ((32, 16, (4, 6, 5)), (64, 32, (9, 7, 16)), (128, 64, (5, 8, 4))):
+        g = torch.Generator().manual_seed(3)
+        x = G.rnd(precision)(torch.randn(1, ci, *dims, generator=g)).to(dev)
+        w = G.rnd(precision)(torch.randn(ci, co, 3, 3, 3, generator=g) / (ci * 8) ** 0.5).to(dev)
+        b = torch.randn(co, generator=g).to(dev)
+        sk = G.rnd(precision)(torch.randn(1, co, *[2 * d for d in dims], generator=g)).to(dev)
+        outs, n_ops = [], []
+        for grouped in ("1", "0"):
+            monkeypatch.setenv("OCCDEPTH_CONVT_GROUPED", grouped)
+            plan = Plan(dev, precision=precision)
+            y = plan.conv_transpose_k3s2(CL.from_planar(x, precision=precision), w, b, act="relu",
+                                         res_post=CL.from_planar(sk, precision=precision))
+            plan.run()
+            torch.cuda.synchronize()
+            outs.append(y.to_planar())
+            n_ops.append(len(plan.ops))
+        assert n_ops == [1, 8]
+        assert torch.equal(outs[0], outs[1])
+        ref = torch.relu(torch.nn.functional.conv_transpose3d(x.cpu(), w.cpu(), b.cpu(), 2, 1, 1)) + sk.cpu()
+        assert G.rel_err(outs[0].cpu(), ref) <= G.TOL[precision]
+
+
+@PREC
 def test_conv_large_vs_simt(precision):
     """full-size head conv shape (Cin=Cout=32, dil 3) on a 64x64x32 slab: auto (halo) / TC vs SIMT on the same
     buffers."""
