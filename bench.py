@@ -283,6 +283,8 @@ def run_b200(args):
     world, rank, local = parallel.env_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries the ONE JSON line: NCCL's own banner / debug log ("NCCL version ...") goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     parallel.init("nccl", dev)
     prec = args.precision
     m = build_model().to(dev).set_precision(prec)
