@@ -108,9 +108,10 @@ DWT_HD float tf32_rna(float v) {
 }
 
 // one 8-channel vector of the staged tile -> 4 float2
-DWT_HD void load8f2(const __nv_bfloat16* p, float2* f) { unpack8f2(*reinterpret_cast<const uint4*>(p), f); }
-DWT_HD void load8f2(const float* p, float2* f) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+// (sw: the fp32 tile's halves are stored swapped at this column, see phase_load)
+DWT_HD void load8f2(const __nv_bfloat16* p, float2* f, int) { unpack8f2(*reinterpret_cast<const uint4*>(p), f); }
+DWT_HD void load8f2(const float* p, float2* f, int sw) {
+  const float4 a = *reinterpret_cast<const float4*>(p + 4 * sw), b = *reinterpret_cast<const float4*>(p + 4 - 4 * sw);
   f[0] = make_float2(a.x, a.y); f[1] = make_float2(a.z, a.w);
   f[2] = make_float2(b.x, b.y); f[3] = make_float2(b.z, b.w);
 }
@@ -181,7 +182,11 @@ DWT_HD void phase_load(const Args& a, BlockIdx blk, int tid, T* tile, float* wsm
     const int piece = i % (CVB * PC), pix = i / (CVB * PC);   // piece = (cv, half): consecutive 16-byte runs
     const int iy = pix / C_::ITW, ix = pix - iy * C_::ITW;
     const int gy = gy0 + iy, gx = gx0 + ix, c = c0 + piece * EPP;
-    T* dst = tile + (long long)pix * C_::CT + piece * EPP;
+    // fp32 tiles: the two 16-byte halves of an 8-channel vector swap places in every other group of kPX*S columns, so
+    // the 8 lanes of a quarter warp (4 channel vectors x 2 column groups, 512 bytes apart) hit 32 distinct banks when
+    // they read the same half (ncu r02: a third of the kernel's shared-memory wavefronts were bank conflicts)
+    const int sw = PC == 2 ? ((ix / (kPX * S)) & 1) : 0;
+    T* dst = tile + (long long)pix * C_::CT + (piece ^ sw) * EPP;
     if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && c < a.C)
       copy16_async(dst, inb + ((long long)gy * a.W + gx) * a.cs_in + c);
     else
@@ -245,7 +250,7 @@ DWT_HD void phase_compute(const Args& a, BlockIdx blk, int tid, const T* tile, c
 #pragma unroll
       for (int j = 0; j < C_::NIN; ++j) {
         float2 x[4];
-        load8f2(rowp + j * C_::CT, x);
+        load8f2(rowp + j * C_::CT, x, C_::PIECES == 2 ? ((gxi + j / (kPX * S)) & 1) : 0);
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
           const int d = j - kx;  // input column j feeds output p = d / S through tap kx (compile-time resolved)
