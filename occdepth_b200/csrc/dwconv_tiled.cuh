@@ -19,9 +19,10 @@
 
 namespace dwt {
 
-constexpr int kThreads = 256;
 constexpr int kTW = 16;  // output tile width
-constexpr int kPX = 4;   // consecutive outputs (along W) per thread
+// PXV = consecutive outputs (along W) per thread: 4 with 256-thread CTAs, or 8 with 128-thread CTAs -- one input
+// vector then feeds up to K taps of 8 outputs, and the filter row is fetched once per 8 outputs: 28 % fewer
+// shared-memory wavefronts per output (the kernel is shared-memory-pipe bound: ncu r02, MIO throttle the top stall)
 
 #define DWT_HD __host__ __device__ __forceinline__
 
@@ -34,17 +35,19 @@ struct Args {
   int H, W, OH, OW, C, cs_in, cs_out, pad_top, pad_left, act, tiles_x;
 };
 
-template <typename T, int K, int S, int CVB, int TH>
+template <typename T, int K, int S, int CVB, int TH, int PXV = 4>
 struct Cfg {
+  static constexpr int PX = PXV;
+  static constexpr int NT = 1024 / PXV;           // threads per CTA (256 / 128): the slots of one pass cover 16 x 16
   static constexpr int PIECES = (int)sizeof(T) / 2;  // 16-byte pieces per 8-channel vector
   static constexpr int CT = CVB * 8;              // channels per CTA
-  static constexpr int GX = kTW / kPX;            // thread groups along W
-  static constexpr int GROUPS = kThreads / CVB;   // (row, x-group) slots per pass
+  static constexpr int GX = kTW / PX;             // thread groups along W
+  static constexpr int GROUPS = NT / CVB;         // (row, x-group) slots per pass
   static constexpr int RPP = GROUPS / GX;         // output rows per pass
   static constexpr int PASSES = TH / RPP;
   static_assert(TH % RPP == 0 && PASSES >= 1, "tile height must be a multiple of the rows per pass");
   static constexpr int ITH = (TH - 1) * S + K, ITW = (kTW - 1) * S + K;  // input halo tile
-  static constexpr int NIN = (kPX - 1) * S + K;   // input vectors one thread reads per filter row
+  static constexpr int NIN = (PX - 1) * S + K;    // input vectors one thread reads per filter row
   static constexpr int TILE_ELEMS = ITH * ITW * CT;  // T
   static constexpr int W_ELEMS = K * K * CT;         // fp32, layout [tap][half][CVB][4]
   static constexpr int RED_ELEMS = GROUPS * CT;      // fp32
@@ -170,22 +173,22 @@ struct BlockIdx {
 };
 
 // ---- phase 1: stage the zero-filled input halo tile and this CTA's filter taps in shared memory ----------------
-template <typename T, int K, int S, int CVB, int TH>
+template <typename T, int K, int S, int CVB, int TH, int PXV = 4>
 DWT_HD void phase_load(const Args& a, BlockIdx blk, int tid, T* tile, float* wsm) {
-  using C_ = Cfg<T, K, S, CVB, TH>;
+  using C_ = Cfg<T, K, S, CVB, TH, PXV>;
   const int b = blk.z, c0 = blk.y * C_::CT;
   const int gy0 = (blk.x / a.tiles_x) * TH * S - a.pad_top;
   const int gx0 = (blk.x % a.tiles_x) * kTW * S - a.pad_left;
   constexpr int PC = C_::PIECES, EPP = 8 / PC;   // 16-byte pieces per vector, elements per piece
   const T* inb = reinterpret_cast<const T*>(a.in) + (long long)b * a.H * a.W * a.cs_in;
-  for (int i = tid; i < C_::ITH * C_::ITW * CVB * PC; i += kThreads) {
+  for (int i = tid; i < C_::ITH * C_::ITW * CVB * PC; i += C_::NT) {
     const int piece = i % (CVB * PC), pix = i / (CVB * PC);   // piece = (cv, half): consecutive 16-byte runs
     const int iy = pix / C_::ITW, ix = pix - iy * C_::ITW;
     const int gy = gy0 + iy, gx = gx0 + ix, c = c0 + piece * EPP;
-    // fp32 tiles: the two 16-byte halves of an 8-channel vector swap places in every other group of kPX*S columns, so
+    // fp32 tiles: the two 16-byte halves of an 8-channel vector swap places in every other group of C_::PX*S columns, so
     // the 8 lanes of a quarter warp (4 channel vectors x 2 column groups, 512 bytes apart) hit 32 distinct banks when
     // they read the same half (ncu r02: a third of the kernel's shared-memory wavefronts were bank conflicts)
-    const int sw = PC == 2 ? ((ix / (kPX * S)) & 1) : 0;
+    const int sw = PC == 2 ? ((ix / (C_::PX * S)) & 1) : 0;
     T* dst = tile + (long long)pix * C_::CT + (piece ^ sw) * EPP;
     if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && c < a.C)
       copy16_async(dst, inb + ((long long)gy * a.W + gx) * a.cs_in + c);
@@ -193,7 +196,7 @@ DWT_HD void phase_load(const Args& a, BlockIdx blk, int tid, T* tile, float* wsm
       zero16(dst);
   }
   // filter taps: wsm[tap][half][cv][4] so that the 8 lanes of a quarter warp read 128 contiguous bytes
-  for (int i = tid; i < K * K * 2 * CVB; i += kThreads) {
+  for (int i = tid; i < K * K * 2 * CVB; i += C_::NT) {
     const int cv = i % CVB, h = (i / CVB) % 2, tap = i / (2 * CVB);
     const int c = c0 + cv * 8 + h * 4;
     float* dst = wsm + ((tap * 2 + h) * CVB + cv) * 4;
@@ -205,14 +208,14 @@ DWT_HD void phase_load(const Args& a, BlockIdx blk, int tid, T* tile, float* wsm
 }
 
 // ---- phase 2: FMA loop out of shared memory, activation, bf16 store, per-thread squeeze partials -> red[] -----
-template <typename T, int K, int S, int CVB, int TH>
+template <typename T, int K, int S, int CVB, int TH, int PXV = 4>
 DWT_HD void phase_compute(const Args& a, BlockIdx blk, int tid, const T* tile, const float* wsm,
                           float* red) {
-  using C_ = Cfg<T, K, S, CVB, TH>;
+  using C_ = Cfg<T, K, S, CVB, TH, PXV>;
   const int cv = tid % CVB, g = tid / CVB;
   const int gxi = g % C_::GX, r0 = g / C_::GX;
   const int b = blk.z, c = blk.y * C_::CT + cv * 8;
-  const int ty0 = (blk.x / a.tiles_x) * TH, ox0 = (blk.x % a.tiles_x) * kTW + gxi * kPX;
+  const int ty0 = (blk.x / a.tiles_x) * TH, ox0 = (blk.x % a.tiles_x) * kTW + gxi * C_::PX;
   const bool cvalid = c < a.C;
   float2 psum[4];
 #pragma unroll
@@ -221,12 +224,12 @@ DWT_HD void phase_compute(const Args& a, BlockIdx blk, int tid, const T* tile, c
   for (int pass = 0; pass < C_::PASSES; ++pass) {
     const int orow = r0 + pass * C_::RPP, oy = ty0 + orow;
     if (!cvalid || oy >= a.OH || ox0 >= a.OW) continue;
-    float2 acc[kPX][4];
+    float2 acc[C_::PX][4];
     {
       const float4 b0 = *reinterpret_cast<const float4*>(a.bias + c);
       const float4 b1 = *reinterpret_cast<const float4*>(a.bias + c + 4);
 #pragma unroll
-      for (int p = 0; p < kPX; ++p) {
+      for (int p = 0; p < C_::PX; ++p) {
         acc[p][0] = make_float2(b0.x, b0.y);
         acc[p][1] = make_float2(b0.z, b0.w);
         acc[p][2] = make_float2(b1.x, b1.y);
@@ -246,15 +249,15 @@ DWT_HD void phase_compute(const Args& a, BlockIdx blk, int tid, const T* tile, c
         wv[kx][2] = make_float2(w1.x, w1.y);
         wv[kx][3] = make_float2(w1.z, w1.w);
       }
-      const T* rowp = tile + ((long long)(orow * S + ky) * C_::ITW + gxi * kPX * S) * C_::CT + cv * 8;
+      const T* rowp = tile + ((long long)(orow * S + ky) * C_::ITW + gxi * C_::PX * S) * C_::CT + cv * 8;
 #pragma unroll
       for (int j = 0; j < C_::NIN; ++j) {
         float2 x[4];
-        load8f2(rowp + j * C_::CT, x, C_::PIECES == 2 ? ((gxi + j / (kPX * S)) & 1) : 0);
+        load8f2(rowp + j * C_::CT, x, C_::PIECES == 2 ? ((gxi + j / (C_::PX * S)) & 1) : 0);
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
           const int d = j - kx;  // input column j feeds output p = d / S through tap kx (compile-time resolved)
-          if (d >= 0 && d % S == 0 && d / S < kPX) {
+          if (d >= 0 && d % S == 0 && d / S < C_::PX) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[d / S][i] = fma2(x[i], wv[kx][i], acc[d / S][i]);
           }
@@ -263,7 +266,7 @@ DWT_HD void phase_compute(const Args& a, BlockIdx blk, int tid, const T* tile, c
     }
     T* orow_p = reinterpret_cast<T*>(a.out) + (((long long)b * a.OH + oy) * a.OW + ox0) * a.cs_out + c;
 #pragma unroll
-    for (int p = 0; p < kPX; ++p) {
+    for (int p = 0; p < C_::PX; ++p) {
       if (ox0 + p >= a.OW) break;
       float v[8];
 #pragma unroll
@@ -295,9 +298,9 @@ DWT_HD void phase_compute(const Args& a, BlockIdx blk, int tid, const T* tile, c
 
 // ---- phase 3: one thread per channel folds the CTA's partials and adds them to pool[b][c] (integer atomics:
 //      order-independent, so the SE gates are bit-reproducible run to run) ---------------------------------------
-template <typename T, int K, int S, int CVB, int TH>
+template <typename T, int K, int S, int CVB, int TH, int PXV = 4>
 DWT_HD void phase_pool(const Args& a, BlockIdx blk, int tid, const float* red) {
-  using C_ = Cfg<T, K, S, CVB, TH>;
+  using C_ = Cfg<T, K, S, CVB, TH, PXV>;
   const int c = blk.y * C_::CT + tid;
   if (tid >= C_::CT || c >= a.C) return;
   float s = 0.f;
@@ -311,9 +314,9 @@ DWT_HD void phase_pool(const Args& a, BlockIdx blk, int tid, const float* red) {
 }
 
 #ifdef __CUDACC__
-template <typename T, int K, int S, int CVB, int TH>
-__global__ void __launch_bounds__(kThreads, 2) dwconv_tiled_kernel(const Args a) {
-  using C_ = Cfg<T, K, S, CVB, TH>;
+template <typename T, int K, int S, int CVB, int TH, int PXV = 4>
+__global__ void __launch_bounds__(1024 / PXV, PXV == 4 ? 2 : 3) dwconv_tiled_kernel(const Args a) {
+  using C_ = Cfg<T, K, S, CVB, TH, PXV>;
   pdl_wait();
   extern __shared__ __align__(16) unsigned char dwt_smem[];
   T* tile = reinterpret_cast<T*>(dwt_smem);
@@ -321,14 +324,14 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv_tiled_kernel(const Args a)
   float* red = wsm + C_::W_ELEMS;
   const BlockIdx blk{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z};
   const int tid = threadIdx.x;
-  phase_load<T, K, S, CVB, TH>(a, blk, tid, tile, wsm);
+  phase_load<T, K, S, CVB, TH, PXV>(a, blk, tid, tile, wsm);
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  phase_compute<T, K, S, CVB, TH>(a, blk, tid, tile, wsm, red);
+  phase_compute<T, K, S, CVB, TH, PXV>(a, blk, tid, tile, wsm, red);
   if (a.pool) {
     __syncthreads();
-    phase_pool<T, K, S, CVB, TH>(a, blk, tid, red);
+    phase_pool<T, K, S, CVB, TH, PXV>(a, blk, tid, red);
   }
 }
 #endif

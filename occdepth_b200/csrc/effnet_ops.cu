@@ -283,28 +283,36 @@ extern "C" int occd_dwconv2d_fwd(const void* in, const float* w, const float* bi
 
 namespace {
 
-template <typename T, int K, int S, int CVB, int TH>
+template <typename T, int K, int S, int CVB, int TH, int PXV = 4>
 int launch_dw_tiled(const dwt::Args& a, int B, cudaStream_t st) {
-  using C_ = dwt::Cfg<T, K, S, CVB, TH>;
+  using C_ = dwt::Cfg<T, K, S, CVB, TH, PXV>;
   static bool attr_set[64] = {false};  // per instantiation, per device
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) dev = 0;
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv_tiled_kernel<T, K, S, CVB, TH>,
+    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv_tiled_kernel<T, K, S, CVB, TH, PXV>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::kSmemBytes);
     if (e != cudaSuccess) { occd_set_last_error(cudaGetErrorString(e)); return OCCD_ERR_CUDA; }
     attr_set[dev] = true;
   }
   const int tiles_y = (a.OH + TH - 1) / TH;
   dim3 grid(a.tiles_x * tiles_y, (a.C + C_::CT - 1) / C_::CT, B);
-  OCCD_LAUNCH_CHECKED(dwt::dwconv_tiled_kernel<T, K, S, CVB, TH>, grid, dim3(dwt::kThreads), C_::kSmemBytes, st, a);
+  OCCD_LAUNCH_CHECKED((dwt::dwconv_tiled_kernel<T, K, S, CVB, TH, PXV>), grid, dim3(C_::NT), C_::kSmemBytes, st, a);
   return OCCD_OK;
 }
 
 template <typename T, int K, int S>
 int launch_dw_tiled_ks(const dwt::Args& a, int B, dwt::Choice ch, cudaStream_t st) {
-  if (ch.cvb == 4) return launch_dw_tiled<T, K, S, 4, 16>(a, B, st);   // 16 rows per pass: TH = 16 only
+  if (ch.cvb == 4) {   // 16 rows per pass: TH = 16 only
+    if constexpr (sizeof(T) == 4 && S == 1) {
+      // fp32, stride 1: 8 outputs per thread / 128-thread CTAs (B200, tools/dw_bench.py: b2 5x5 31 -> 26 us, b1 3x3
+      // 50 -> 44 us; the stride-2 layers lose, 82 -> 96 us, and keep 4).  OCCD_DW_PX=4 forces 4 (experiment hook)
+      static const bool px4 = [] { const char* e = getenv("OCCD_DW_PX"); return e && atoi(e) == 4; }();
+      if (!px4) return launch_dw_tiled<T, K, S, 4, 16, 8>(a, B, st);
+    }
+    return launch_dw_tiled<T, K, S, 4, 16>(a, B, st);
+  }
   if constexpr (sizeof(T) == 2) {
     if (ch.th == 16) return launch_dw_tiled<T, K, S, 8, 16>(a, B, st);
     return launch_dw_tiled<T, K, S, 8, 8>(a, B, st);

@@ -8,9 +8,9 @@ extern "C" void occd_set_last_error(const char*) {}
 
 namespace {
 
-template <typename T, int K, int S, int CVB, int TH>
+template <typename T, int K, int S, int CVB, int TH, int PXV = 4>
 void run(const dwt::Args& a, int B) {
-  using C_ = dwt::Cfg<T, K, S, CVB, TH>;
+  using C_ = dwt::Cfg<T, K, S, CVB, TH, PXV>;
   const int tiles_y = (a.OH + TH - 1) / TH;
   std::vector<T> tile(C_::TILE_ELEMS);
   std::vector<float> wsm(C_::W_ELEMS), red(C_::RED_ELEMS);
@@ -22,17 +22,18 @@ void run(const dwt::Args& a, int B) {
         memset(tile.data(), 0xff, tile.size() * sizeof(T));
         memset(wsm.data(), 0xff, wsm.size() * 4);
         memset(red.data(), 0xff, red.size() * 4);
-        for (int t = 0; t < dwt::kThreads; ++t) dwt::phase_load<T, K, S, CVB, TH>(a, blk, t, tile.data(), wsm.data());
-        for (int t = 0; t < dwt::kThreads; ++t)
-          dwt::phase_compute<T, K, S, CVB, TH>(a, blk, t, tile.data(), wsm.data(), red.data());
+        for (int t = 0; t < C_::NT; ++t) dwt::phase_load<T, K, S, CVB, TH, PXV>(a, blk, t, tile.data(), wsm.data());
+        for (int t = 0; t < C_::NT; ++t)
+          dwt::phase_compute<T, K, S, CVB, TH, PXV>(a, blk, t, tile.data(), wsm.data(), red.data());
         if (a.pool)
-          for (int t = 0; t < dwt::kThreads; ++t) dwt::phase_pool<T, K, S, CVB, TH>(a, blk, t, red.data());
+          for (int t = 0; t < C_::NT; ++t) dwt::phase_pool<T, K, S, CVB, TH, PXV>(a, blk, t, red.data());
       }
 }
 
 template <typename T, int K, int S>
 void run_ks(const dwt::Args& a, int B, dwt::Choice ch) {
-  if (ch.cvb == 4) run<T, K, S, 4, 16>(a, B);
+  if (ch.cvb == 4 && sizeof(T) == 4 && S == 1) run<T, K, S, 4, 16, 8>(a, B);   // fp32 stride 1: 8 outputs per thread, as the launcher
+  else if (ch.cvb == 4) run<T, K, S, 4, 16>(a, B);
   else if (ch.th == 16) run<T, K, S, 8, 16>(a, B);
   else run<T, K, S, 8, 8>(a, B);
 }
