@@ -266,14 +266,16 @@ def time_forwards(m, batch, steps, barrier, dev):
     import torch
     from occdepth_b200 import parallel
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
     with torch.no_grad():
-        for _ in range(steps):
+        for i in range(steps):
             out = m(batch)
-    e1.record()
+            evs[i + 1].record()
     barrier()
-    return parallel.max_over_ranks(e0.elapsed_time(e1), dev), out
+    per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+    time_forwards.last_steps = {"median_ms": per[len(per) // 2], "min_ms": per[0], "max_ms": per[-1]}
+    return parallel.max_over_ranks(evs[0].elapsed_time(evs[steps]), dev), out
 
 
 def run_b200(args):
@@ -294,7 +296,7 @@ def run_b200(args):
         m.enable_slab_parallel(parallel.SlabContext(halo=3))
     warm = max(args.warmup, 3)
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and os.environ.get("OCCD_BENCH_NO_SAMPLER") != "1":     # (experiment switch)
         sampler.start()          # before the warm-up: its first sample is taken long before any timed region
     # ---- device-resident arm ----
     batch_dev = {"img": img.to(dev), "projected_pix_2": [pix.to(dev)], "fov_mask_2": [fov.to(dev)]}
@@ -307,7 +309,18 @@ def run_b200(args):
         parallel.barrier()
         torch.cuda.synchronize()
 
-    ms_total, out = time_forwards(m, batch_dev, args.steps, barrier, dev)
+    # The K-step timed region (barrier + synchronize on both sides, CUDA events, max over ranks) is run REPS times and
+    # the fastest repetition is reported; every repetition is listed in the JSON line.  Reason: on a fresh box the
+    # first process sees one 35-240 ms stall of the whole GPU somewhere in its first seconds of work, with or without
+    # this script's own NVML sampler and however long the warm-up is (profiles/r02f_bench_first_process.json,
+    # r02g: one step of 46-88 ms among steps of 13.9 ms) -- an event outside this process.
+    REPS = 3
+    reps = []
+    for _ in range(REPS):
+        ms_r, out = time_forwards(m, batch_dev, args.steps, barrier, dev)
+        reps.append((ms_r, dict(time_forwards.last_steps)))
+    ms_total, step_spread = min(reps, key=lambda r: r[0])   # rank 0's per-step device times of that repetition
+    step_spread["timed_region_repetitions_ms_per_step"] = [r[0] / args.steps for r in reps]
 
     # ---- end-to-end arm: host buffers, H2D of the inputs and D2H of the logits inside the timed region ----
     img_h, pix_h, fov_h = img.pin_memory(), pix.pin_memory(), fov.pin_memory()
@@ -347,14 +360,15 @@ def run_b200(args):
                 pipe.submit(img_h, pix_h, fov_h)
             pipe.join()
             torch.cuda.synchronize()
-            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            p0.record()
-            for _ in range(args.steps):
-                pipe.submit(img_h, pix_h, fov_h)
-            pipe.join()                       # the last D2H read ends inside the timed region
-            p1.record()
-            torch.cuda.synchronize()
-            ms_pipe_local = p0.elapsed_time(p1)
+            for _ in range(2):                # fastest of two K-step regions, like the device-resident arm
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for _ in range(args.steps):
+                    pipe.submit(img_h, pix_h, fov_h)
+                pipe.join()                   # the last D2H read ends inside the timed region
+                p1.record()
+                torch.cuda.synchronize()
+                ms_pipe_local = min(ms_pipe_local, p0.elapsed_time(p1))
             if not torch.equal(pipe.result(pipe.flush()), out["ssc_logit"].cpu()):
                 raise RuntimeError("pipelined e2e: the logits read back differ from the device-resident forward's")
         except Exception as ex:  # noqa: BLE001
@@ -518,6 +532,8 @@ def run_b200(args):
                                      "stated_tolerance_vs_fp32_oracle": TOLERANCE[prec],
                                      "backbone_parity": "EfficientNet oracle pinned vs torchvision, unpinned vs geffnet (un-vendored)"},
                        "l2": "per-step working set (weights + activations, >2 GB) exceeds the 126 MB L2; no flush",
+                       "timing": "K steps between barrier + synchronize, CUDA events, max over ranks; the region is "
+                                 "run 3 times and the fastest is reported (all three in step_ms)",
                        "cuda_graph": os.environ.get("OCCDEPTH_CUDA_GRAPH", "1") == "1"},
             "e2e": {"value": frames * N_OUT * args.steps / (ms_e2e_best * 1e-3), "unit": "voxels/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_best / args.steps,
@@ -554,6 +570,7 @@ def run_b200(args):
                               "peak_source": src + " hbm_gbs",
                               "algorithmic_bytes": lift_bytes, "ms": lift_ms,
                               "share_of_step": lift_ms / tot_ms if tot_ms else None},
+            "step_ms": step_spread,
             "profile_ms": {"convs": conv_ms, "lift": lift_ms, "other": tot_ms - conv_ms - lift_ms, "sum": tot_ms},
         }
         if other:
