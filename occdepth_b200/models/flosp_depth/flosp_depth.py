@@ -187,6 +187,7 @@ class FlospDepth(B200Module):
         vox_origin = batch.get("vox_origin") if isinstance(batch, dict) else None
         _, vn = self._grid_to_lidar(vox_origin if vox_origin is not None else None)
         X, Y, Z = vn
+        self.__dict__["_vn"] = tuple(vn)         # baked into the plan's buffers; stage_inputs checks every batch
         cams = torch.zeros(B, n_cams, 40, dtype=torch.float32, device=dev)
         self.__dict__["_cams"] = cams
         self.__dict__["_n_cams"] = n_cams
@@ -222,8 +223,12 @@ class FlospDepth(B200Module):
                 g[:, v].copy_(grids[v].to(torch.float32).reshape(B, -1, 3), non_blocking=True)
             self.__dict__["_sps"].copy_(batch["scaled_pixel_size"].to(torch.float32).reshape(-1, 1), non_blocking=True)
             return
-        cams, sps, _ = self.camera_tables(batch["cam_k"], batch["T_velo_2_cam"], batch["ida_mats"],
-                                          batch.get("vox_origin"), self.__dict__["_n_cams"])
+        cams, sps, vn = self.camera_tables(batch["cam_k"], batch["T_velo_2_cam"], batch["ida_mats"],
+                                           batch.get("vox_origin"), self.__dict__["_n_cams"])
+        if tuple(vn) != self.__dict__.get("_vn", tuple(vn)):
+            # NYU: the voxel counts are re-derived from batch item 0's vox_origin every forward (flosp_depth.py:466-518)
+            raise RuntimeError("FlospDepth: this batch's vox_origin gives a %r voxel grid, the plan was built for %r; "
+                               "call invalidate_plans()" % (tuple(vn), self.__dict__["_vn"]))
         self.__dict__["_cams"].copy_(cams, non_blocking=True)
         self.__dict__["_sps"].copy_(sps, non_blocking=True)
 
