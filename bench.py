@@ -187,7 +187,7 @@ def run_reference(args):
                          "sample": "%d full forward(s) of the workload (oracle/functional.py, PyTorch CPU fp32)" % len(times)},
         "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit_json(line)
 
 
 def eager_cuda_baseline(dev, steps=3):
@@ -593,7 +593,7 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     if line:
-        print(json.dumps(line))
+        emit_json(line)
 
 
 def run_slab_block(m, dev, world, rank, args, barrier):
@@ -645,7 +645,31 @@ def run_slab_block(m, dev, world, rank, args, barrier):
     return res
 
 
+_JSON_FD = None
+
+
+def protect_stdout():
+    """stdout carries exactly ONE JSON line: file descriptor 1 is pointed at stderr for the whole run (NCCL prints its
+    version banner to stdout from C, libraries may print warnings) and the line is written to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
