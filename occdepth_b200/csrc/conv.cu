@@ -537,6 +537,25 @@ conv_halo_kernel(const __grid_constant__ HaloParams p, const __grid_constant__ C
 // neighbour would fall outside [0, W) -- which is exactly the convolution's zero padding, so the W axis needs no
 // halo columns and no sub-sampling.  D and H keep the halo-tile scheme (one zero-filled halo position per side on
 // the d-sub-sampled grids, TMA traversal stride d).  27 taps become 9 instructions per 32 bytes of K.
+// out[r] = Q0[r - d] + Q1[r] + Q2[r + d] for 16 channels of this lane's row: the three accumulator column groups of
+// the x-packed MMA (lane == W position; lanes shifted out of [0, W) contribute the conv's zero padding).  The three
+// tcgen05.ld are issued back to back and share ONE wait.
+__device__ __forceinline__ void halox_gather16(uint32_t taddr, int c0, int CP, int d, bool lo_ok, bool hi_ok, float* v) {
+  uint32_t lo[16], mid[16], hi[16];
+  tc::tmem_ld16_issue(taddr + (uint32_t)c0, lo);
+  tc::tmem_ld16_issue(taddr + (uint32_t)(CP + c0), mid);
+  tc::tmem_ld16_issue(taddr + (uint32_t)(2 * CP + c0), hi);
+  tc::tmem_ld_wait16(lo);
+  tc::tmem_ld_dep16(mid);
+  tc::tmem_ld_dep16(hi);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float l = __shfl_up_sync(0xffffffffu, __uint_as_float(lo[i]), (unsigned)d);
+    const float h = __shfl_down_sync(0xffffffffu, __uint_as_float(hi[i]), (unsigned)d);
+    v[i] = __uint_as_float(mid[i]) + (lo_ok ? l : 0.f) + (hi_ok ? h : 0.f);
+  }
+}
+
 struct HaloxParams {
   ConvEpi epi;
   int d;                      // dilation (== padding) of the taps
@@ -555,6 +574,14 @@ struct HaloxParams {
   int grp_off[9];             // (a*PH + b)*PW: smem row offset of a group's A operand relative to the M tile
   int pdl;
   long long* trace;
+  // plane-ring mode (ring == 1; chosen when the halo box leaves room for ONE stage only, i.e. the TF32 head whose
+  // resident weights take 110 KB): the output planes of all columns (image, residue class, H tile) form one sequence
+  // of n_cols * sD M tiles; every CTA takes a contiguous, equal share of it (at most one column change inside).  The
+  // four stages are a ring of single input planes, output plane z reads ring planes z-1, z, z+1, so every M tile costs
+  // ONE new 6-row plane (prefetched a plane ahead) instead of half a 4-plane box loaded while the tensor pipe waits
+  int ring, sD, n_cols;
+  signed char grp_dz[9];      // -1 / 0 / +1: which ring plane a group reads
+  short grp_row[9];           // (hh + dy) * PW: its row offset inside the plane
 };
 
 template <typename T, int RB>
@@ -578,6 +605,10 @@ conv_halox_kernel(const __grid_constant__ HaloxParams p, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int d = p.d;
   const int num_tiles = p.epi.B * d * d * p.tilesD * p.tilesH;
+  // ring mode: this CTA's share [ring_lo, ring_hi) of the n_cols * sD output planes
+  const long long ring_total = (long long)p.n_cols * p.sD;
+  const long long ring_lo = p.ring ? ring_total * blockIdx.x / gridDim.x : 0;
+  const long long ring_hi = p.ring ? ring_total * (blockIdx.x + 1) / gridDim.x : 0;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
@@ -617,8 +648,41 @@ conv_halox_kernel(const __grid_constant__ HaloxParams p, const __grid_constant__
     b = t;
   };
 
+  // ring mode: position in the plane sequence -> (batch, residue class, H tile) and the run of planes [z0, z1) this CTA
+  // takes from that column
+  auto decode_ring = [&](long long pos, int& b, int& ra, int& rb, int& th, int& z0, int& z1) {
+    int t = (int)(pos / p.sD);
+    z0 = (int)(pos - (long long)t * p.sD);
+    const long long left = ring_hi - pos;
+    z1 = (long long)(p.sD - z0) < left ? p.sD : z0 + (int)left;
+    th = t % p.tilesH; t /= p.tilesH;
+    rb = t % d; t /= d;
+    ra = t % d; t /= d;
+    b = t;
+  };
+
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0 && p.ring) {
+      // ===== TMA producer, ring mode: weights once, then planes z0-1 .. z1 of every unit, one ring slot each =====
+      tc::mbar_expect_tx(w_bar, (uint32_t)(p.n_groups * p.N_tile * RB));
+      for (int g = 0; g < p.n_groups; ++g)
+        tc::tma_load_2d(smem_w + (uint32_t)g * p.b_stride, &tmW, w_bar, 0, g * p.N_tile);
+      uint32_t n = 0;
+      for (long long pos = ring_lo; pos < ring_hi;) {
+        int b, ra, rb, th, z0, z1;
+        decode_ring(pos, b, ra, rb, th, z0, z1);
+        pos += z1 - z0;
+        for (int z = z0 - 1; z <= z1; ++z, ++n) {
+          const uint32_t slot = n & 3u;
+          if (p.trace && blockIdx.x == 0 && n < 64) p.trace[n * 8 + 0] = clock64();
+          tc::mbar_wait(empty_bar + 8u * slot, ((n >> 2) & 1u) ^ 1u);
+          if (p.trace && blockIdx.x == 0 && n < 64) p.trace[n * 8 + 1] = clock64();
+          tc::mbar_expect_tx(full_bar + 8u * slot, (uint32_t)p.box_bytes);
+          tc::tma_load_5d(smem_a + slot * (uint32_t)p.a_stage_bytes, &tmA, full_bar + 8u * slot, 0, 0,
+                          (th * p.BH - p.hh) * d + rb, z * d + ra + p.src_d0, b);
+        }
+      }
+    } else if (lane == 0) {
       // ===== TMA producer: resident weights once, then one halo box per tile =====
       tc::mbar_expect_tx(w_bar, (uint32_t)(p.n_groups * p.N_tile * RB));
       for (int g = 0; g < p.n_groups; ++g)
@@ -636,7 +700,64 @@ conv_halox_kernel(const __grid_constant__ HaloxParams p, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && p.ring) {
+      // ===== MMA issuer, ring mode =====
+      const uint32_t idesc = tc::Mma<T>::idesc(128, p.N_tile);
+      const uint64_t db_w = tc::make_sdesc(smem_w, RB);
+      const int w_step16 = p.b_stride / 16;
+      // A descriptors of the nine groups for each of the four ring rotations, built once (the issuing thread must not
+      // spend its ~60 cycles per MMA on address arithmetic)
+      uint64_t* dtab = reinterpret_cast<uint64_t*>(smem_raw + (bar_base - tc::smem_u32(smem_raw)) + 128u);
+      for (int r = 0; r < 4; ++r)
+        for (int g = 0; g < 9; ++g) {
+          const uint32_t slot = (uint32_t)(r + (g < p.n_groups ? p.grp_dz[g] : 0)) & 3u;
+          dtab[r * 9 + g] = tc::make_sdesc(smem_a + slot * (uint32_t)p.a_stage_bytes, RB) +
+                            (uint64_t)((g < p.n_groups ? p.grp_row[g] : 0) * (RB / 16));
+        }
+      tc::mbar_wait(w_bar, 0);
+      uint32_t n0 = 0;     // ring index of this unit's first plane (z0 - 1)
+      uint32_t j = 0;      // output planes so far == accumulator uses
+      for (long long pos = ring_lo; pos < ring_hi;) {
+        int b, ra, rb, th, z0, z1;
+        decode_ring(pos, b, ra, rb, th, z0, z1);
+        pos += z1 - z0;
+        const int K = z1 - z0;
+        for (int k = 0; k < K; ++k, ++j) {
+          const uint32_t set = j & 1u;
+          tc::mbar_wait(tempty_bar + 8u * set, ((j >> 1) & 1u) ^ 1u);
+          for (uint32_t i = (k == 0 ? 0u : 2u); i < 3u; ++i) {     // planes z-1 and z were waited for by plane z-1
+            const uint32_t n = n0 + (uint32_t)k + i;
+            tc::mbar_wait(full_bar + 8u * (n & 3u), (n >> 2) & 1u);
+          }
+          tc::fence_after_sync();
+          if (p.trace && blockIdx.x == 0 && j < 64) p.trace[j * 8 + 2] = clock64();
+          const uint32_t d_tmem = tmem_base + set * (uint32_t)p.set_stride;
+          const uint64_t* drow = dtab + ((n0 + (uint32_t)k + 1u) & 3u) * 9u;
+          uint64_t dg[9];
+#pragma unroll
+          for (int g = 0; g < 9; ++g) dg[g] = drow[g];
+#pragma unroll
+          for (int g = 0; g < 9; ++g) {
+            if (g < p.n_groups) {
+              const uint64_t da = dg[g];
+              const uint64_t db = db_w + (uint64_t)(g * w_step16);
+              if (g == 0) tc::Mma<T>::template issue<0>(d_tmem, da, db, idesc);
+              else tc::Mma<T>::template issue<1>(d_tmem, da, db, idesc);
+#pragma unroll
+              for (int kk = 1; kk < NMMA; ++kk) tc::Mma<T>::template issue<1>(d_tmem, da + 2 * kk, db + 2 * kk, idesc);
+            }
+          }
+          tc::mma_commit(tfull_bar + 8u * set);
+          if (p.trace && blockIdx.x == 0 && j < 64) p.trace[j * 8 + 3] = clock64();
+          tc::mma_commit(empty_bar + 8u * ((n0 + (uint32_t)k) & 3u));            // plane z-1 is done with
+          if (k == K - 1) {                                                       // ... and the unit's last two
+            tc::mma_commit(empty_bar + 8u * ((n0 + (uint32_t)k + 1u) & 3u));
+            tc::mma_commit(empty_bar + 8u * ((n0 + (uint32_t)k + 2u) & 3u));
+          }
+        }
+        n0 += (uint32_t)K + 2u;
+      }
+    } else if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc = tc::Mma<T>::idesc(128, p.N_tile);
       const uint64_t db_w = tc::make_sdesc(smem_w, RB);
@@ -689,8 +810,38 @@ conv_halox_kernel(const __grid_constant__ HaloxParams p, const __grid_constant__
     const int chunks = p.CP >> 4;
     const int n_items = p.nM * chunks;
     const bool tracer = p.trace && blockIdx.x == 0 && threadIdx.x == 64;
+    if (p.ring) {
+      // ring mode: one M tile (one plane, 128 / PW h-rows) per accumulator use
+      uint32_t jr = 0;
+      for (long long pos = ring_lo; pos < ring_hi;) {
+        int b, ra, rb, th, z0, z1;
+        decode_ring(pos, b, ra, rb, th, z0, z1);
+        pos += z1 - z0;
+        for (int z = z0; z < z1; ++z, ++jr) {
+          const uint32_t set = jr & 1u;
+          if ((int)set != grp) continue;
+          if (tracer && jr < 64) p.trace[jr * 8 + 4] = clock64();
+          tc::mbar_wait(tfull_bar + 8u * set, (jr >> 1) & 1u);
+          tc::fence_after_sync();
+          if (tracer && jr < 64) p.trace[jr * 8 + 5] = clock64();
+          const int od = z * d + ra;
+          const int oh = (th * p.BH + hr) * d + rb;
+          const bool valid = od < p.D && oh < p.H;
+          const uint32_t taddr = tmem_base + set * (uint32_t)p.set_stride + ((uint32_t)(q * 32) << 16);
+          for (int it = half; it < chunks; it += 2) {
+            const int c0 = it * 16;
+            float v[16];
+            halox_gather16(taddr, c0, p.CP, d, lo_ok, hi_ok, v);
+            if (valid) conv_epilogue_row<T, 16>(p.epi, b, od, oh, pw, c0, v);
+          }
+          tc::fence_before_sync();
+          tc::mbar_arrive(tempty_bar + 8u * set);
+          if (tracer && jr < 64) p.trace[jr * 8 + 6] = clock64();
+        }
+      }
+    }
     int j = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+    for (int tile = blockIdx.x; !p.ring && tile < num_tiles; tile += gridDim.x, ++j) {
       const uint32_t set = (uint32_t)j & 1u;
       const uint32_t use = (uint32_t)j >> 1;
       if ((int)set != grp) continue;
@@ -707,16 +858,8 @@ conv_halox_kernel(const __grid_constant__ HaloxParams p, const __grid_constant__
         const bool valid = od < p.D && oh < p.H;
         const uint32_t taddr = tmem_base + set * (uint32_t)p.set_stride + (uint32_t)(m * p.N_tile) +
                                ((uint32_t)(q * 32) << 16);
-        float lo[16], v[16], hi[16];
-        tc::tmem_ld16(taddr + (uint32_t)c0, lo);
-        tc::tmem_ld16(taddr + (uint32_t)(p.CP + c0), v);
-        tc::tmem_ld16(taddr + (uint32_t)(2 * p.CP + c0), hi);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float l = __shfl_up_sync(0xffffffffu, lo[i], (unsigned)d);
-          const float h = __shfl_down_sync(0xffffffffu, hi[i], (unsigned)d);
-          v[i] += (lo_ok ? l : 0.f) + (hi_ok ? h : 0.f);
-        }
+        float v[16];
+        halox_gather16(taddr, c0, p.CP, d, lo_ok, hi_ok, v);
         if (valid) conv_epilogue_row<T, 16>(p.epi, b, od, oh, pw, c0, v);
       }
       tc::fence_before_sync();
@@ -1066,6 +1209,21 @@ static int halox_geometry(const occd_conv_desc* d, occd_conv_plan* pl) {
     }
   }
   HX_REQUIRE(best >= 0, "no tile shape fits");
+  h.ring = 0;
+  {
+    // plane ring instead of a single-stage box (see HaloxParams): needs D taps and four single-plane stages.
+    // OCCD_HALOX_RING=0 keeps the box (experiment hook, tools/conv_bench.py)
+    static const bool ring_off = [] { const char* e = getenv("OCCD_HALOX_RING"); return e && atoi(e) == 0; }();
+    const int PHr = HR + 2 * hal[1];
+    const int plane = round_up(PHr * h.PW * RB, 1024);
+    if (!ring_off && h.stages < 2 && hal[0] == 1 && 4 * plane <= smem_total && (PHr - 1) * dil + 1 <= 256) {
+      h.ring = 1;
+      h.BD = 1; h.BH = HR; h.PD = 3; h.PH = PHr; h.nM = 1;
+      h.a_stage_bytes = plane; h.stages = 4;
+      h.set_stride = 32;
+      while (h.set_stride < h.N_tile) h.set_stride *= 2;
+    }
+  }
   {
     const int nB = h.BH / HR;
     int m = 0;
@@ -1078,13 +1236,19 @@ static int halox_geometry(const occd_conv_desc* d, occd_conv_plan* pl) {
   }
   h.tmem_cols = 2 * h.set_stride;
   h.tilesD = (sD + h.BD - 1) / h.BD; h.tilesH = (sH + h.BH - 1) / h.BH;
-  h.box_bytes = h.PD * h.PH * h.PW * RB;
-  for (int g = 0; g < h.n_groups; ++g)
+  h.box_bytes = (h.ring ? 1 : h.PD) * h.PH * h.PW * RB;
+  for (int g = 0; g < h.n_groups; ++g) {
     h.grp_off[g] = ((d->taps[3 * g].dz / dil) * h.PH + d->taps[3 * g].dy / dil) * h.PW;
+    h.grp_dz[g] = (signed char)(d->taps[3 * g].dz / dil);
+    h.grp_row[g] = (short)((h.hh + d->taps[3 * g].dy / dil) * h.PW);
+  }
+  h.sD = sD;
+  h.n_cols = d->B * dil * dil * h.tilesH;
   h.trace = g_trace_buf;
   h.pdl = pdl_enabled();
-  pl->smem = (size_t)h.w_bytes + (size_t)h.stages * h.a_stage_bytes + 128 + 1024;
-  const long long num_tiles = (long long)d->B * dil * dil * h.tilesD * h.tilesH;
+  pl->smem = (size_t)h.w_bytes + (size_t)h.stages * h.a_stage_bytes + 128 + 512 + 1024;   // barriers, ring-mode descriptor table, alignment slack
+  const long long num_tiles = h.ring ? (long long)h.n_cols * sD      // ring mode: M tiles; each CTA takes a contiguous share
+                                     : (long long)d->B * dil * dil * h.tilesD * h.tilesH;
   HX_REQUIRE(num_tiles < 2147483647LL, "too many tiles");
   const int n_sms = n_sms_current();
   pl->grid = dim3((unsigned)(num_tiles < n_sms ? num_tiles : n_sms));
@@ -1150,7 +1314,7 @@ static int halox_encode(const occd_conv_desc* d, occd_conv_plan* pl) {
     cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)d->IW, (cuuint64_t)d->IH, (cuuint64_t)d->ID, (cuuint64_t)d->B};
     cuuint64_t gstr[4] = {cs, cs * d->IW, cs * d->IW * d->IH, cs * d->IW * d->IH * d->ID};
     cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)h.PW, (cuuint32_t)((h.PH - 1) * dil + 1),
-                         (cuuint32_t)((h.PD - 1) * dil + 1), 1};
+                         (cuuint32_t)(h.ring ? 1 : (h.PD - 1) * dil + 1), 1};   // ring mode: one plane per load
     cuuint32_t estr[5] = {1, 1, (cuuint32_t)dil, (cuuint32_t)dil, 1};
     void* base = (void*)((const char*)d->src[0] + (size_t)d->src_coff[0] * es);
     CUresult r = enc(&pl->tmA[0], tm_dtype(pl->dtype), 5, base, gdim, gstr, box, estr,

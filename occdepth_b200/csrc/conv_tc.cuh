@@ -219,4 +219,14 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
                : "memory");
 }
 
+// after one tmem_ld_wait16: ties further destination arrays of loads issued before that wait to the wait's position
+// (asm volatile statements keep their order), so their uses cannot be scheduled above it
+__device__ __forceinline__ void tmem_ld_dep16(uint32_t* r) {
+  asm volatile(""
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 }  // namespace tc
