@@ -42,6 +42,17 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 // activation over 8 values with ONE uniform branch (keeps the epilogues free of per-element switches)
+// SiLU with ONE MUFU op per element: x sigmoid(x) = h + h tanh(h), h = x / 2 (tanh.approx.f32: max relative error
+// 2^-11).  Used by the bf16 mode only, whose stores round to 2^-9; the tf32 mode keeps ex2 + rcp (two MUFU ops):
+// a SiLU epilogue runs within 2x of the MUFU pipe (16 lanes / cycle / SM), see DESIGN.md section 4
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+template <bool FAST_SILU = false>
 __device__ __forceinline__ void apply_act8(float* v, int act) {
   if (act == ACT_NONE) return;
   if (act == ACT_RELU) {
@@ -52,7 +63,7 @@ __device__ __forceinline__ void apply_act8(float* v, int act) {
     for (int i = 0; i < 8; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
   } else if (act == ACT_SILU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
+    for (int i = 0; i < 8; ++i) v[i] = FAST_SILU ? silu_tanh(v[i]) : __fdividef(v[i], 1.f + __expf(-v[i]));
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));

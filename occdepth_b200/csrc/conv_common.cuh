@@ -76,7 +76,7 @@ __device__ __forceinline__ void conv_epilogue_compute(const ConvEpi& e, long lon
         if (n + i < e.Cout) o[(long long)i * S] = vv[i];
     }
     if (e.out0) {
-      apply_act8(vv, e.act);
+      apply_act8<sizeof(T) == 2>(vv, e.act);
       if (e.res2 && e.res2_post) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) vv[i] += r2[i];
@@ -143,6 +143,7 @@ __device__ __forceinline__ void epi_prefetch(const EpiRow<T>& e, int c0, EpiPre&
   }
 }
 
+template <bool FAST_SILU>
 __device__ __forceinline__ void apply_act16(float* v, int act) {
   if (act == ACT_NONE) return;
   if (act == ACT_RELU) {
@@ -153,7 +154,7 @@ __device__ __forceinline__ void apply_act16(float* v, int act) {
     for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
   } else if (act == ACT_SILU) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
+    for (int i = 0; i < 16; ++i) v[i] = FAST_SILU ? silu_tanh(v[i]) : __fdividef(v[i], 1.f + __expf(-v[i]));
   } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.f, 1.f + __expf(-v[i]));
@@ -180,7 +181,7 @@ __device__ __forceinline__ void epi_finish_v(const EpiRow<T>& e, int c0, float* 
       for (int i = 8; i < 16; ++i) v[i] += rr[i];
     }
   }
-  apply_act16(v, e.act);
+  apply_act16<sizeof(T) == 2>(v, e.act);
   if (e.res && e.res_post) {
     if (c0 < e.n_store) {
 #pragma unroll

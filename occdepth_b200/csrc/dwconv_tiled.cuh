@@ -152,9 +152,10 @@ DWT_HD float2 fma2(float2 a, float2 b, float2 c) {
 }
 
 // activation over one 8-channel vector (device: the same uniform-branch fast-math epilogue as the direct kernel)
+template <bool FAST_SILU>
 DWT_HD void act8(float* v, int act) {
 #ifdef __CUDA_ARCH__
-  apply_act8(v, act);
+  apply_act8<FAST_SILU>(v, act);
 #else
   for (int i = 0; i < 8; ++i) {
     switch (act) {
@@ -274,7 +275,7 @@ DWT_HD void phase_compute(const Args& a, BlockIdx blk, int tid, const T* tile, c
         v[2 * i] = acc[p][i].x;
         v[2 * i + 1] = acc[p][i].y;
       }
-      act8(v, a.act);
+      act8<sizeof(T) == 2>(v, a.act);
       store8(orow_p + (long long)p * a.cs_out, v);
       if (a.pool) {
         // squeeze what the next layer will actually read (the rounded activation)
