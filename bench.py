@@ -11,7 +11,14 @@ A step = one OccDepth.forward over one frame per GPU (frames are independent: re
 The headline (`value`, `e2e`, `roofline`) is measured in the reference-precision mode: TF32 tensor-core operands,
 fp32 accumulation, fp32 activations holding TF32 values (`dtype: "tf32"`) -- the arithmetic PyTorch itself uses for the
 reference's fp32 nn.Conv*d on CUDA.  The bf16 mode is reported beside it as `throughput_mode` with its own tolerance.
-Prints ONE JSON line (rank 0).
+
+Timing: W (>= 3) warm-up forwards, then K forwards between barrier + torch.cuda.synchronize() on both sides, CUDA events
+on the launching stream, max over ranks; that K-step region is run three times and the fastest is reported, all three
+are listed under `step_ms` (a one-off GPU stall of 35-240 ms hits some first regions on a fresh box).  `e2e` is the same
+metric with pinned host inputs copied H2D and the logits read back D2H inside the timed region, through
+occdepth_b200.serving.FramePipeline (copies on their own streams, double-buffered); the back-to-back figure is listed
+beside it.  Prints ONE JSON line (rank 0) on the original stdout; everything else this process or its libraries print
+goes to stderr.
 """
 import argparse
 import json
