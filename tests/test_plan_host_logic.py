@@ -154,6 +154,38 @@ def test_auto_impl_selection_reaches_tensor_map_encode(monkeypatch, precision):
             plan.conv(x, torch.randn(co, ci, *k), torch.randn(co), padding=tuple(kk // 2 for kk in k))
 
 
+def test_tap_group_plans_are_validated_on_the_host(monkeypatch):
+    """tap groups (the transposed conv's eight phases as ONE launch): the grouped plan passes the host-side geometry
+    and reaches the tensor-map encode (the first step that needs a driver); malformed group tables, a second output or
+    a non-TC kernel are refused by occd_conv_plan_create with a message"""
+    import ctypes as C
+    from occdepth_b200 import _lib
+    from occdepth_b200.engine import ConvOp, Plan
+    monkeypatch.delenv("OCCDEPTH_CONV_IMPL", raising=False)
+    plan = Plan(torch.device("cpu"), precision="tf32")
+    x = plan.alloc(1, 4, 6, 8, 32)
+    with pytest.raises(RuntimeError, match="cuTensorMapEncodeTiled unavailable"):
+        plan.conv_transpose_k3s2(x, torch.randn(32, 16, 3, 3, 3), torch.randn(16), act="relu")
+    out = plan.alloc(1, 8, 12, 16, 16)
+    taps = [(0, 0, 0, 0), (0, 0, 0, 1), (0, 0, 1, 0)]
+    ws = [torch.randn(16, 32) for _ in taps]
+    L = _lib.lib()
+
+    def create(groups, **kw):
+        with pytest.raises(RuntimeError) as ei:
+            ConvOp([x], taps, ws, torch.randn(16), (4, 6, 8), out0=out, omul=(2, 2, 2), full_dims=(8, 12, 16),
+                   groups=groups, **kw)
+        return str(ei.value)
+
+    assert "cuTensorMapEncodeTiled" in create([(2, (1, 1, 1)), (1, (0, 0, 0))])          # well-formed
+    assert "tap groups" in create([(2, (2, 0, 0)), (1, (0, 0, 0))])                         # oadd >= omul
+    assert "tap groups" in create([(2, (1, 1, 1)), (1, (0, 0, 0))], out1=plan.alloc(1, 8, 12, 16, 16), out1_mode="cl")
+    d = _lib.ConvDesc()
+    d.impl, d.n_groups = _lib.CONV_IMPL_SIMT, 2
+    h = C.c_void_p()
+    assert L.occd_conv_plan_create(C.byref(d), C.byref(h)) != 0
+
+
 def test_widened_rows_fail_loudly_without_cuda():
     """no CPU fallback anywhere: the data-pipeline and post-processing entry points refuse to run without a GPU"""
     import numpy as np
